@@ -1,0 +1,188 @@
+/* mlbsim.h — C ABI of the B200 Monte Carlo game sampler.
+ *
+ * The reference (BLON333/MLB_Odds_Engine) has no FFI: its seam is the Python call
+ *   simulate_game(home_lineup, away_lineup, home_pitcher, away_pitcher, env, home_bullpen,
+ *                 away_bullpen, ..., use_noise)              core/game_simulator.py:14-25
+ * made once per simulation from cli/run_distribution_simulator.py:368-382, plus the process-global
+ * outcome counters PA_RECAP_LOG (core/pa_simulator.py:10-20) that tools/ read.  This header is
+ * what a binding for that seam links against (ctypes stub: INTEGRATION.md).  Plain C, no torch
+ * or CUDA types; every pointer is caller-owned; nothing throws across the boundary.
+ */
+#ifndef MLBSIM_H
+#define MLBSIM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MLBSIM_ABI_VERSION 1
+
+/* ---- model dimensions ------------------------------------------------------------------- */
+#define MLBSIM_MAX_LINEUP 9   /* len(lineup); 9 in every caller (half_inning_simulator.py:175) */
+#define MLBSIM_MAX_BULLPEN 6  /* max_relievers=6, assets/bullpen_utils.py:19,104 */
+#define MLBSIM_MAX_PITCHERS 7 /* starter (index 0) + bullpen (index 1 + position in the list) */
+#define MLBSIM_N_OUTCOMES 7   /* K BB 1B 2B 3B HR OUT — order of PA_RECAP_LOG, pa_simulator.py:11 */
+#define MLBSIM_N_TIERS 4      /* TTO 1, 2, 3, >=4 — fatigue_modeling.py:25-32 */
+#define MLBSIM_N_BIP 4        /* GB LD FB POP — pa_simulator.py:54 */
+
+enum { MLBSIM_K = 0, MLBSIM_BB, MLBSIM_1B, MLBSIM_2B, MLBSIM_3B, MLBSIM_HR, MLBSIM_OUT };
+
+/* "side" everywhere = the BATTING side: 0 = away bats (top half, home staff pitches),
+ * 1 = home bats (bottom half, away staff pitches).  pit_* [side] is the staff that FACES it. */
+
+/* ---- raw float64 parameters of one matchup (replay mode) ---------------------------------- */
+typedef struct mlbsim_params {
+  int32_t lineup_len[2];  /* [side] */
+  int32_t bullpen_len[2]; /* [side]: relievers of the staff facing `side`; 0 = None or [] */
+  int32_t use_noise;      /* simulate_game(use_noise=...) */
+  int32_t reserved;
+  double k_mod, bb_mod; /* env["umpire"].get("k_mod"/"bb_mod", 1.0), pa_simulator.py:112-114 */
+  double bat_k[2][MLBSIM_MAX_LINEUP];
+  double bat_bb[2][MLBSIM_MAX_LINEUP];
+  double pit_k[2][MLBSIM_MAX_PITCHERS];
+  double pit_bb[2][MLBSIM_MAX_PITCHERS];
+  double pit_hr[2][MLBSIM_MAX_PITCHERS]; /* hr_pa_projected * weather_hr, pa_simulator.py:46 */
+  /* resolve_bip probability after all modifiers and the [0.05,0.55] clamp, computed on the host
+   * in float64 in the reference's multiply order (core/bip_resolution.py:20-57) */
+  double hit_prob[2][MLBSIM_MAX_PITCHERS][MLBSIM_MAX_LINEUP][MLBSIM_N_BIP];
+  double cdf_bip[4]; /* cumsum([.28,.32,.30,.10]) / last       pa_simulator.py:54 */
+  double cdf_hit[3]; /* normalised [0.76*1.01, 0.22, 0.02]     pa_simulator.py:68-72 */
+  double cdf_fb[2];  /* normalised [0.92*1.01, 0.08]           pa_simulator.py:75-79 */
+} mlbsim_params;
+
+/* ---- per-game integers replay mode returns (core/game_simulator.py:134-144) ---------------- */
+#define MLBSIM_REPLAY_MAX_INNINGS 40
+#define MLBSIM_REPLAY_MAX_USED 16
+#define MLBSIM_ST_INNINGS_OVERFLOW 1 /* more innings than recorded; scores still exact */
+#define MLBSIM_ST_USED_OVERFLOW 2
+#define MLBSIM_ST_TAPE_UNDERRUN 4 /* the tape ended before the game did */
+
+typedef struct mlbsim_replay_game {
+  int32_t home_score, away_score;
+  int32_t n_innings;  /* len(result["innings"]) */
+  int32_t tape_used;  /* tape entries consumed; == tape length for a well-formed tape */
+  int32_t n_used[2];  /* [0] len(used_home_relievers), [1] len(used_away_relievers) */
+  int32_t status;
+  int32_t reserved;
+  uint8_t away_runs[MLBSIM_REPLAY_MAX_INNINGS]; /* innings[i]["away_runs"] */
+  uint8_t home_runs[MLBSIM_REPLAY_MAX_INNINGS];
+  uint8_t used_home[MLBSIM_REPLAY_MAX_USED]; /* indices into home_bullpen */
+  uint8_t used_away[MLBSIM_REPLAY_MAX_USED];
+  uint16_t pa[2][8]; /* [side][outcome] per-game PA_RECAP_LOG deltas; [7] unused */
+} mlbsim_replay_game;
+
+/* ---- native mode: per-matchup integer threshold table --------------------------------------
+ * One PA consumes one Philox4x32-10 block (w0..w3).  u = w0 >> 1 (31 bits); the outcome is the
+ * number of thresholds thr[..][j] (j = 0..5, cumulative over K BB 1B 2B 3B HR) with u >= thr,
+ * so OUT = 6.  thr = round(cdf * 2^31) in [0, 2^31].  For pitch counts above 75
+ * (fatigue_modeling.py:38) starters use thr + (pitch_count - 75) * slope.                      */
+#define MLBSIM_TABLE_MAGIC 0x4d4c4254u /* "MLBT" */
+#define MLBSIM_ROW_WORDS 8
+#define MLBSIM_FLAG_FATIGUE 1u /* some staff has no bullpen: pitch_count can exceed 75 */
+
+typedef struct mlbsim_table {
+  uint32_t magic;
+  uint32_t flags;
+  uint32_t lineup_len[2];
+  uint32_t bullpen_len[2];
+  uint32_t reserved[2];
+  uint32_t thr[2][MLBSIM_MAX_PITCHERS][MLBSIM_N_TIERS][MLBSIM_MAX_LINEUP][MLBSIM_ROW_WORDS];
+  int32_t slope[2][MLBSIM_N_TIERS][MLBSIM_MAX_LINEUP][MLBSIM_ROW_WORDS]; /* starters only */
+} mlbsim_table;
+
+/* ---- native mode: per-matchup output, all uint64 counters ---------------------------------- */
+#define MLBSIM_HIST_BINS 64 /* runs per team, last bin = ">= 63" */
+#define MLBSIM_N_CAPS 5     /* first 1, 3, 5, 7 innings, full game (run_distribution_simulator.py:414) */
+#define MLBSIM_INN_BINS 32  /* innings played, last bin = ">= 31" */
+
+typedef struct mlbsim_hist {
+  uint64_t joint[MLBSIM_N_CAPS][MLBSIM_HIST_BINS][MLBSIM_HIST_BINS]; /* [cap][away][home] */
+  uint64_t innings[MLBSIM_INN_BINS];
+  uint64_t pa[2][8];        /* [side][outcome] = PA_RECAP_LOG["AWAY"|"HOME"]; [7] unused */
+  uint64_t rel_games[2][8]; /* [0] home bullpen, [1] away bullpen: sims in which reliever i appeared
+                               (run_distribution_simulator.py:391-397) */
+  uint64_t rel_picks[2][8]; /* total picks of reliever i */
+  uint64_t n_games;
+  uint64_t reserved[7];
+} mlbsim_hist;
+
+#define MLBSIM_HIST_WORDS (sizeof(mlbsim_hist) / 8)
+
+/* ---- error codes --------------------------------------------------------------------------- */
+#define MLBSIM_OK 0
+#define MLBSIM_ERR_CUDA 1       /* a CUDA runtime call failed; see mlbsim_last_error */
+#define MLBSIM_ERR_ARG 2        /* bad argument (NULL, range, size mismatch) */
+#define MLBSIM_ERR_TABLE 3      /* table failed validation (magic, lengths) */
+#define MLBSIM_ERR_NO_DEVICE 4  /* no CUDA device / not an sm_100 part */
+#define MLBSIM_ERR_STATE 5      /* call order (e.g. run before upload) */
+
+typedef struct mlbsim_ctx mlbsim_ctx;
+
+/* Creates a context bound to CUDA device `device` with its own stream.  Replaces nothing in the
+ * reference (it has no device); one ctx per host thread. */
+int mlbsim_init(int device, mlbsim_ctx** out);
+void mlbsim_destroy(mlbsim_ctx* ctx);
+const char* mlbsim_last_error(const mlbsim_ctx* ctx); /* ctx may be NULL: last init error */
+int mlbsim_abi_version(void);
+
+/* Device facts for roofline arithmetic. */
+int mlbsim_device_info(const mlbsim_ctx* ctx, int* sm_count, int* sm_clock_khz, char* name, size_t name_len);
+
+/* Uses an externally owned stream (e.g. torch's current stream) for all later calls; 0 restores
+ * the context's own stream.  `stream` is a cudaStream_t passed as an integer. */
+int mlbsim_set_stream(mlbsim_ctx* ctx, uintptr_t stream);
+int mlbsim_synchronize(mlbsim_ctx* ctx);
+
+/* Copies `n_matchups` host tables to the device (replaces the per-call dict arguments of
+ * simulate_game, core/game_simulator.py:14-21, for native mode).  Synchronous w.r.t. the host
+ * buffer: it may be reused on return. */
+int mlbsim_upload_tables(mlbsim_ctx* ctx, const mlbsim_table* tables, int n_matchups);
+
+/* Native-RNG mode: for every uploaded matchup m in [matchup_lo, matchup_hi) simulate the sims
+ * [sim_lo, sim_hi) — the loop of cli/run_distribution_simulator.py:368-382 — and ADD the results
+ * into hist_dev[m - matchup_lo] (device memory, caller-allocated, caller-zeroed).  Sim i of
+ * matchup m draws from Philox4x32-10 with key = seed and counter (i_lo, i_hi, pa_seq, m), so its
+ * outcome does not depend on the launch geometry or the number of GPUs.  Asynchronous on the
+ * context's stream.  `flags` bit 0: 0 = also count PA outcomes (default), 1 = skip them. */
+int mlbsim_run_native(mlbsim_ctx* ctx, int matchup_lo, int matchup_hi, uint64_t sim_lo, uint64_t sim_hi,
+                      uint64_t seed, mlbsim_hist* hist_dev, uint32_t flags);
+
+/* Host-buffer convenience used by the Python layer and the e2e benchmark: zero device
+ * histograms, run, copy to `hist_host`, synchronise. */
+int mlbsim_run_native_host(mlbsim_ctx* ctx, int matchup_lo, int matchup_hi, uint64_t sim_lo, uint64_t sim_hi,
+                           uint64_t seed, mlbsim_hist* hist_host, uint32_t flags);
+
+/* Replay mode: game g consumes tape[tape_offsets[g] .. tape_offsets[g+1]) (float64 values in the
+ * reference's draw order) and writes out[g].  Host pointers; synchronous.
+ * Integer results are bit-exact with core/game_simulator.py:14-156 on the same draws. */
+int mlbsim_run_replay(mlbsim_ctx* ctx, const mlbsim_params* params, const double* tape,
+                      const uint64_t* tape_offsets, int64_t n_games, mlbsim_replay_game* out);
+
+/* Device-pointer variant (tape, offsets and out already resident in HBM); asynchronous. */
+int mlbsim_run_replay_dev(mlbsim_ctx* ctx, const mlbsim_params* params_host, const double* tape_dev,
+                          const uint64_t* tape_offsets_dev, int64_t n_games, mlbsim_replay_game* out_dev);
+
+/* Device memory helpers so a ctypes-only caller needs no CUDA binding. */
+int mlbsim_malloc(mlbsim_ctx* ctx, size_t bytes, void** dev_ptr);
+int mlbsim_free(mlbsim_ctx* ctx, void* dev_ptr);
+int mlbsim_memset(mlbsim_ctx* ctx, void* dev_ptr, int value, size_t bytes);
+int mlbsim_memcpy_h2d(mlbsim_ctx* ctx, void* dev_dst, const void* host_src, size_t bytes);
+int mlbsim_memcpy_d2h(mlbsim_ctx* ctx, void* host_dst, const void* dev_src, size_t bytes);
+
+/* Kernel launches issued by this context since creation (bench.py's gpu_launches). */
+uint64_t mlbsim_launch_count(const mlbsim_ctx* ctx);
+
+/* Tuning knobs (0 = default): threads per block and blocks per SM of the native kernel. */
+int mlbsim_set_launch_config(mlbsim_ctx* ctx, int threads_per_block, int blocks_per_sm);
+
+/* Timing of the last mlbsim_run_native* kernel(s) in milliseconds, measured with CUDA events on
+ * the launching stream (synchronises). */
+int mlbsim_last_kernel_ms(mlbsim_ctx* ctx, float* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MLBSIM_H */

@@ -1,0 +1,289 @@
+"""Host-side builders: reference argument dicts -> device tables (float64 numpy).
+
+Inputs are exactly the keyword arguments of `simulate_game` (core/game_simulator.py:14-25).  Two
+products per matchup:
+
+* `build_params`  -> `mlbsim_params`  raw float64 numbers for REPLAY mode.  Every quantity the
+  reference computes per PA from dict values is either copied verbatim or precomputed here with
+  the same float64 operation order, so the device compares the same doubles
+  (core/bip_resolution.py:20-57, core/pa_simulator.py:46,54,68-79).
+* `build_table`   -> `mlbsim_table`   31-bit integer outcome thresholds for NATIVE mode: the
+  per-PA law of core/pa_simulator.py:91-143 with the Beta(30p, 30(1-p)) noise of :23-32
+  integrated out (it is redrawn independently every PA and only the outcome is consumed), the
+  TTO tiers of core/fatigue_modeling.py:25-35 tabulated and the pitch-count ramp of :38-43 kept
+  as an integer slope per pitch above 75.
+
+Only keys the reference's hot path reads are used; everything else in the
+dicts (iso, avg, woba, stuff_plus, park multipliers, ...) is inert there and therefore here.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from . import _abi
+
+# ---- model literals (reference file:line) ---------------------------------------------------
+BIP_TYPES = ("GB", "LD", "FB", "POP")            # pa_simulator.py:54
+BIP_WEIGHTS = (0.28, 0.32, 0.30, 0.10)           # pa_simulator.py:54
+BASE_BABIP = {"LD": 0.65, "GB": 0.305, "FB": 0.10, "POP": 0.02}  # bip_resolution.py:13-18
+TTO_PENALTY = (0.0, 0.015, 0.035, 0.060)         # fatigue_modeling.py:25-32 (tto 1, 2, 3, >=4)
+NOISE_WEIGHT = 30                                # pa_simulator.py:23
+INFIELD_FALLBACK = 0.10                          # pa_simulator.py:74
+FATIGUE_START = 75                               # fatigue_modeling.py:38
+SLOPE_SPAN = 100                                 # pitches over which the integer slope is fitted
+
+
+def _normalised_cdf(p):
+    """legacy `np.random.choice(p=...)`: cdf = cumsum(p); cdf /= cdf[-1]."""
+    cdf = np.cumsum(np.asarray(p, dtype=np.float64))
+    cdf /= cdf[-1]
+    return cdf
+
+
+def contact_cdfs():
+    """The three categorical CDFs of resolve_contact (pa_simulator.py:54, :68-72, :75-79)."""
+    cdf_bip = _normalised_cdf(BIP_WEIGHTS)
+    probs = [0.76, 0.22, 0.02]
+    probs[0] *= 1.01
+    total = sum(probs)
+    cdf_hit = _normalised_cdf([p / total for p in probs])
+    fb = [0.92, 0.08]
+    fb[0] *= 1.01
+    total = sum(fb)
+    cdf_fb = _normalised_cdf([p / total for p in fb])
+    return cdf_bip, cdf_hit, cdf_fb
+
+
+def bip_hit_probability(bip_type, ev, la, batter_speed, fielder_rating):
+    """P(hit | ball in play of `bip_type`) — core/bip_resolution.py:20-57, same multiply order."""
+    prob = BASE_BABIP[bip_type]
+    if batter_speed > 65:
+        prob *= 1.025
+    elif batter_speed < 40:
+        prob *= 0.97
+    if fielder_rating > 60:
+        prob *= 0.97
+    elif fielder_rating < 40:
+        prob *= 1.03
+    hard_hit = ev if ev is not None else 88
+    barrels = la if la is not None else 12
+    mult = 1.0
+    if hard_hit < 85:
+        mult *= 0.97
+    elif hard_hit > 95:
+        mult *= 1.03
+    if barrels < 6.0:
+        mult *= 0.96
+    elif barrels > 10.0:
+        mult *= 1.03
+    mult = min(mult, 1.06)
+    prob *= mult
+    return max(min(prob, 0.55), 0.05)
+
+
+class Matchup:
+    """Numbers the hot path reads from one `simulate_game(**kwargs)` argument set.
+
+    Raises what the reference would raise on the same malformed input: KeyError
+    for a pitcher without k_rate/bb_rate (fatigue_modeling.py:34-35), TypeError for a non-numeric
+    exit velocity / launch angle (bip_resolution.py:40) or hr_pa_projected=None (pa_simulator.py:46).
+    """
+
+    def __init__(self, home_lineup, away_lineup, home_pitcher, away_pitcher, env=None,
+                 home_bullpen=None, away_bullpen=None, use_noise=True, game_id=None, **_ignored):
+        env = env or {}
+        self.game_id = game_id
+        self.use_noise = bool(use_noise)
+        umpire = env.get("umpire", {}) or {}
+        # pa_simulator.py:112-114 — only read when the umpire dict is truthy; x * 1.0 is exact
+        self.k_mod = float(umpire.get("k_mod", 1.0))
+        self.bb_mod = float(umpire.get("bb_mod", 1.0))
+        self.weather_hr = env.get("weather_hr", 1.0)  # half_inning_simulator.py:186
+        # side 0 = away bats vs the home staff; side 1 = home bats vs the away staff
+        self.lineups = [list(away_lineup), list(home_lineup)]
+        self.staffs = [[home_pitcher] + list(home_bullpen or []), [away_pitcher] + list(away_bullpen or [])]
+        for s in range(2):
+            if not 1 <= len(self.lineups[s]) <= _abi.MAX_LINEUP:
+                raise ValueError(f"lineup length {len(self.lineups[s])} outside 1..{_abi.MAX_LINEUP}")
+            if len(self.staffs[s]) > _abi.MAX_PITCHERS:
+                raise ValueError(f"bullpen of {len(self.staffs[s]) - 1} exceeds {_abi.MAX_BULLPEN} relievers")
+        self.bullpen_names = [[p.get("name", "Unknown") for p in st[1:]] for st in self.staffs]  # [home, away]
+
+        L, P = _abi.MAX_LINEUP, _abi.MAX_PITCHERS
+        self.bat_k = np.zeros((2, L))
+        self.bat_bb = np.zeros((2, L))
+        self.speed = np.full((2, L), 50.0)
+        self.pit_k = np.zeros((2, P))
+        self.pit_bb = np.zeros((2, P))
+        self.pit_hr = np.zeros((2, P))
+        self.hit_prob = np.zeros((2, P, L, _abi.N_BIP))
+        for s in range(2):
+            for b, bat in enumerate(self.lineups[s]):
+                self.bat_k[s, b] = bat.get("k_rate", 0.22)      # pa_simulator.py:108
+                self.bat_bb[s, b] = bat.get("bb_rate", 0.08)    # pa_simulator.py:109
+                self.speed[s, b] = bat.get("speed", 50)         # pa_simulator.py:62
+            for p, pit in enumerate(self.staffs[s]):
+                self.pit_k[s, p] = pit["k_rate"]
+                self.pit_bb[s, p] = pit["bb_rate"]
+                hr = pit.get("hr_pa", {}).get("hr_pa_projected", 0.046) * self.weather_hr  # pa_simulator.py:46
+                self.pit_hr[s, p] = hr
+                ev = pit.get("exit_velocity_avg")
+                la = pit.get("launch_angle_avg")
+                fr = pit.get("fielder_rating", 50)
+                for b in range(len(self.lineups[s])):
+                    for t, name in enumerate(BIP_TYPES):
+                        self.hit_prob[s, p, b, t] = bip_hit_probability(name, ev, la, self.speed[s, b], fr)
+
+    @property
+    def lineup_len(self):
+        return [len(self.lineups[0]), len(self.lineups[1])]
+
+    @property
+    def bullpen_len(self):
+        return [len(self.staffs[0]) - 1, len(self.staffs[1]) - 1]
+
+
+def as_matchup(m, use_noise=True) -> Matchup:
+    if isinstance(m, Matchup):
+        return m
+    kw = dict(m)
+    kw.setdefault("use_noise", use_noise)
+    return Matchup(**kw)
+
+
+# ---------------------------------------------------------------------------------------------
+# replay parameters
+# ---------------------------------------------------------------------------------------------
+def build_params(m, use_noise=None) -> np.ndarray:
+    m = as_matchup(m) if use_noise is None else as_matchup(m, use_noise)
+    out = np.zeros((), dtype=_abi.PARAMS_DTYPE)
+    out["lineup_len"] = m.lineup_len
+    out["bullpen_len"] = m.bullpen_len
+    out["use_noise"] = int(m.use_noise if use_noise is None else use_noise)
+    out["k_mod"], out["bb_mod"] = m.k_mod, m.bb_mod
+    for f in ("bat_k", "bat_bb", "pit_k", "pit_bb", "pit_hr", "hit_prob"):
+        out[f] = getattr(m, f)
+    out["cdf_bip"], out["cdf_hit"], out["cdf_fb"] = contact_cdfs()
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# native law
+# ---------------------------------------------------------------------------------------------
+def _p_k_or_bb(k, bb, use_noise):
+    """(P(K), P(K or BB)) for effective rates k, bb (pa_simulator.py:117-124, :35-41)."""
+    pk = min(max(k, 0.0), 1.0)
+    if not use_noise:
+        return pk, max(pk, min(max(k + bb * 1.01, 0.0), 1.0))
+    # beta_noise: p <= 0 -> 0.0, p >= 1 -> 1.0, else Beta(30p, 30(1-p)) with mean p
+    if bb <= 0.0:
+        return pk, pk
+    if bb >= 1.0 or k >= 1.0:
+        return pk, 1.0  # kp + 1.01 >= 1, or kp = 1
+    if k <= 0.0:
+        # only the walk term is random: E[min(1, 1.01*Y)]
+        return 0.0, _expect_clip(None, bb)
+    sd = math.sqrt(k * (1 - k) / (NOISE_WEIGHT + 1)) + 1.01 * math.sqrt(bb * (1 - bb) / (NOISE_WEIGHT + 1))
+    if k + 1.01 * bb + 8.0 * sd < 1.0:
+        return pk, k + 1.01 * bb   # the clip at 1 has probability < 1e-14
+    return pk, _expect_clip(k, bb)
+
+
+def _expect_clip(k, bb):
+    """E[min(1, X + 1.01*Y)], X ~ Beta(30k, 30(1-k)) (or X = 0 if k is None), Y ~ Beta(30bb, 30(1-bb))."""
+    from scipy import special, stats
+
+    ay, by = NOISE_WEIGHT * bb, NOISE_WEIGHT * (1 - bb)
+    nodes, weights = np.polynomial.legendre.leggauss(400)
+    y = 0.5 * (nodes + 1.0)
+    wy = 0.5 * weights * stats.beta.pdf(y, ay, by)
+    c = 1.0 - 1.01 * y                      # X must exceed c for the clip to bite
+    if k is None:
+        excess = np.maximum(-c, 0.0)
+        mean = 1.01 * bb
+    else:
+        ax, bx = NOISE_WEIGHT * k, NOISE_WEIGHT * (1 - k)
+        cc = np.clip(c, 0.0, 1.0)
+        # E[(X - c)^+] = k * (1 - I_c(a+1, b)) - c * (1 - I_c(a, b)); for c < 0 it is k - c
+        excess = k * (1.0 - special.betainc(ax + 1, bx, cc)) - cc * (1.0 - special.betainc(ax, bx, cc))
+        excess = np.where(c < 0.0, k - c, excess)
+        mean = k + 1.01 * bb
+    return float(min(max(mean - float(np.sum(wy * excess)), 0.0), 1.0))
+
+
+def outcome_cdf(m: Matchup, side, pit, tier, slot, pitch_count=0, use_noise=None):
+    """Cumulative P over [K, BB, 1B, 2B, 3B, HR] (OUT is the remainder) for one PA context —
+    the marginal law of core/pa_simulator.py:91-143 + core/bip_resolution.py + fatigue_modeling.py."""
+    use_noise = m.use_noise if use_noise is None else use_noise
+    pen = TTO_PENALTY[tier]
+    fl = max(0, (pitch_count - FATIGUE_START) / 25)
+    ak = m.pit_k[side, pit] * (1 - pen) * (1.0 - 0.02 * fl)
+    ab = m.pit_bb[side, pit] * (1 + pen) * (1.0 + 0.03 * fl)
+    k = (m.bat_k[side, slot] + ak) / 2 * m.k_mod
+    bb = (m.bat_bb[side, slot] + ab) / 2 * m.bb_mod
+    pk, pkbb = _p_k_or_bb(k, bb, use_noise)
+    contact = 1.0 - pkbb
+    cdf_bip, cdf_hit, cdf_fb = contact_cdfs()
+    w_bip = np.diff(np.concatenate([[0.0], cdf_bip]))
+    h = np.diff(np.concatenate([[0.0], cdf_hit]))
+    f = np.diff(np.concatenate([[0.0], cdf_fb]))
+    hr = min(max(float(m.pit_hr[side, pit]), 0.0), 1.0)
+    ph = float(np.dot(w_bip, m.hit_prob[side, pit, slot]))
+    s1 = (1 - hr) * (ph * h[0] + (1 - ph) * INFIELD_FALLBACK * f[0])
+    s2 = (1 - hr) * (ph * h[1] + (1 - ph) * INFIELD_FALLBACK * f[1])
+    s3 = (1 - hr) * ph * h[2]
+    c = [pk, pkbb]
+    for share in (s1, s2, s3, hr):
+        c.append(c[-1] + contact * share)
+    return np.minimum(np.maximum.accumulate(np.asarray(c)), 1.0)
+
+
+def outcome_probabilities(m: Matchup, side, pit, tier, slot, pitch_count=0, use_noise=None):
+    """P over [K, BB, 1B, 2B, 3B, HR, OUT]."""
+    c = outcome_cdf(m, side, pit, tier, slot, pitch_count, use_noise)
+    return np.diff(np.concatenate([[0.0], c, [1.0]]))
+
+
+def _quantise(cdf):
+    q = np.floor(np.asarray(cdf) * 2147483648.0 + 0.5)
+    return np.clip(q, 0, 2147483648).astype(np.uint64)
+
+
+def build_table(m, use_noise=None) -> np.ndarray:
+    m = as_matchup(m) if use_noise is None else as_matchup(m, use_noise)
+    use_noise = m.use_noise if use_noise is None else use_noise
+    t = np.zeros((), dtype=_abi.TABLE_DTYPE)
+    t["magic"] = _abi.TABLE_MAGIC
+    t["lineup_len"] = m.lineup_len
+    t["bullpen_len"] = m.bullpen_len
+    flags = 0
+    thr = np.zeros(_abi.TABLE_DTYPE["thr"].shape, dtype=np.uint32)
+    thr[...] = 2147483648  # unused rows: everything is K (never reached)
+    slope = np.zeros(_abi.TABLE_DTYPE["slope"].shape, dtype=np.int32)
+    for s in range(2):
+        for p in range(m.bullpen_len[s] + 1):
+            for tier in range(_abi.N_TIERS):
+                for b in range(m.lineup_len[s]):
+                    q0 = _quantise(outcome_cdf(m, s, p, tier, b, 0, use_noise))
+                    thr[s, p, tier, b, :6] = q0
+                    thr[s, p, tier, b, 6:] = 2147483648
+                    if p == 0 and m.bullpen_len[s] == 0:
+                        # a starter without a bullpen is never replaced: pitch_count passes 75
+                        c1 = outcome_cdf(m, s, p, tier, b, FATIGUE_START + SLOPE_SPAN, use_noise)
+                        q1 = _quantise(c1)
+                        slope[s, tier, b, :6] = np.round((q1.astype(np.int64) - q0.astype(np.int64)) / SLOPE_SPAN)
+        if m.bullpen_len[s] == 0:
+            flags |= _abi.FLAG_FATIGUE
+    t["flags"] = flags
+    t["thr"] = thr
+    t["slope"] = slope
+    return t
+
+
+def build_tables(matchups, use_noise=True) -> np.ndarray:
+    out = np.zeros(len(matchups), dtype=_abi.TABLE_DTYPE)
+    for i, m in enumerate(matchups):
+        out[i] = build_table(m, use_noise=None if isinstance(m, Matchup) else use_noise)
+    return out

@@ -1,0 +1,267 @@
+"""TEST INFRASTRUCTURE — not product code.  Drives the UNMODIFIED reference (imported read-only
+from /root/reference, which exists only in the build container, never on the GPU box) to
+
+  * record value-level replay tapes of `simulate_game` (SURVEY.md §8(c) "Replay tape"), and
+  * batch-run seeded games over worker processes for statistical oracles,
+
+and writes the results as fixtures under tests/golden/ (see `oracle/make_golden.py`).
+
+Nothing under the product package imports this file.  Reference call sites it hooks, without
+modifying any reference file:
+  core/pa_simulator.py:32,48,54,72,74,79,122   (np.random.beta / random / choice)
+  core/bip_resolution.py:62                     (stdlib random.random)
+  core/half_inning_simulator.py:15,23,35,76,103,105,120
+  assets/bullpen_utils.py:142,144,146          (random.choice / random.choices)
+"""
+from __future__ import annotations
+
+import importlib.machinery
+import os
+import random
+import sys
+import types
+
+import numpy as np
+
+REFERENCE_ROOT = os.environ.get("MLBSIM_REFERENCE_ROOT", "/root/reference")
+OUTCOMES = ["K", "BB", "1B", "2B", "3B", "HR", "OUT"]
+
+_mods = None
+
+
+def reference_available() -> bool:
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "core"))
+
+
+def load_reference():
+    """Import the reference's hot-path modules (SURVEY.md Appendix B recipe)."""
+    global _mods
+    if _mods is not None:
+        return _mods
+    if not reference_available():
+        raise RuntimeError(f"reference checkout not found at {REFERENCE_ROOT}")
+    import pandas  # noqa: F401  must be imported before the pytz stub exists
+
+    if "pytz" not in sys.modules:
+        m = types.ModuleType("pytz")
+        m.__spec__ = importlib.machinery.ModuleSpec("pytz", None)
+        sys.modules["pytz"] = m
+    sys.dont_write_bytecode = True
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+    import core.game_simulator as gs
+    import core.pa_simulator as pa
+    import core.bip_resolution as bip
+    import core.half_inning_simulator as hi
+    import core.fatigue_modeling as fm
+    import assets.bullpen_utils as bu
+    import core.project_hr_pa as php
+
+    _mods = types.SimpleNamespace(gs=gs, pa=pa, bip=bip, hi=hi, fm=fm, bu=bu, php=php)
+    return _mods
+
+
+class _NpTape:
+    """Stands in for `np.random` inside core.pa_simulator; same stream consumption, values taped."""
+
+    def __init__(self, tape):
+        self.tape = tape
+
+    def beta(self, a, b):
+        v = np.random.beta(a, b)
+        self.tape.append(float(v))
+        return v
+
+    def random(self):
+        v = np.random.random()
+        self.tape.append(float(v))
+        return v
+
+    def choice(self, seq, p=None):
+        # legacy RandomState.choice(p=...) = one uniform + searchsorted(cdf, u, 'right')
+        u = np.random.random_sample()
+        self.tape.append(float(u))
+        cdf = np.cumsum(np.asarray(p, dtype=np.float64))
+        cdf /= cdf[-1]
+        return seq[int(np.searchsorted(cdf, u, side="right"))]
+
+
+class _PyTape:
+    """Stands in for stdlib `random` in bip_resolution / half_inning_simulator / bullpen_utils."""
+
+    def __init__(self, tape, bullpens):
+        self.tape = tape
+        self.bullpens = bullpens  # list of the full bullpen lists (to map picks to full-list index)
+
+    def random(self):
+        v = random.random()
+        self.tape.append(float(v))
+        return v
+
+    def _index(self, pick):
+        for bp in self.bullpens:
+            if bp:
+                for i, r in enumerate(bp):
+                    if r is pick:
+                        return i
+        raise RuntimeError("picked reliever not found in any bullpen")
+
+    def choice(self, seq):
+        pick = random.choice(seq)
+        self.tape.append(float(self._index(pick)))
+        return pick
+
+    def choices(self, seq, weights=None, k=1):
+        picks = random.choices(seq, weights=weights, k=k)
+        for pick in picks:
+            self.tape.append(float(self._index(pick)))
+        return picks
+
+
+def saturate_reliever_counts(matchup):
+    """Pre-set RELIEVER_USAGE_COUNTS["home"][name] = 3 so picks follow the stationary law
+    (uniform over the bullpen with replacement; assets/bullpen_utils.py:124,141-142)."""
+    ref = load_reference()
+    for key in ("home_bullpen", "away_bullpen"):
+        for rp in matchup.get(key) or []:
+            ref.bu.RELIEVER_USAGE_COUNTS["home"][rp.get("name", "Unknown")] = 3
+
+
+def reset_reliever_counts():
+    ref = load_reference()
+    ref.bu.RELIEVER_USAGE_COUNTS["home"].clear()
+    ref.bu.RELIEVER_USAGE_COUNTS["away"].clear()
+
+
+def _game_kwargs(matchup, use_noise):
+    kw = {k: matchup[k] for k in ("home_lineup", "away_lineup", "home_pitcher", "away_pitcher", "env")}
+    kw["home_bullpen"] = matchup.get("home_bullpen")
+    kw["away_bullpen"] = matchup.get("away_bullpen")
+    kw["use_noise"] = use_noise
+    return kw
+
+
+def summarize_result(result, matchup):
+    """The integer outputs replay mode must match (core/game_simulator.py:134-144)."""
+    def idx(names, bullpen):
+        lut = {r.get("name", "Unknown"): i for i, r in enumerate(bullpen or [])}
+        return [lut[n] for n in names]
+
+    innings = result["innings"]
+    return {
+        "home_score": int(result["home_score"]),
+        "away_score": int(result["away_score"]),
+        "n_innings": len(innings),
+        "away_runs": [int(i["away_runs"]) for i in innings],
+        "home_runs": [int(i["home_runs"]) for i in innings],
+        "used_home": idx(result["used_home_relievers"], matchup.get("home_bullpen")),
+        "used_away": idx(result["used_away_relievers"], matchup.get("away_bullpen")),
+        "recap": [int(result["recap"][o]) for o in OUTCOMES],
+    }
+
+
+def record_games(matchup, n_games, seed, use_noise=True, saturate=False):
+    """Run `n_games` reference games with taped RNG.  Returns (tapes, summaries, pa_recap) where
+    pa_recap[g] = per-game [AWAY[7], HOME[7]] outcome counts from PA_RECAP_LOG deltas."""
+    ref = load_reference()
+    tape: list[float] = []
+    saved = (ref.pa.np, ref.bip.random, ref.hi.random, ref.bu.random)
+    pyt = _PyTape(tape, [matchup.get("home_bullpen"), matchup.get("away_bullpen")])
+    ref.pa.np = types.SimpleNamespace(random=_NpTape(tape))
+    ref.bip.random = ref.hi.random = ref.bu.random = pyt
+    reset_reliever_counts()
+    if saturate:
+        saturate_reliever_counts(matchup)
+    random.seed(seed)
+    np.random.seed(seed)
+    tapes, sums, recaps = [], [], []
+    try:
+        for _ in range(n_games):
+            tape.clear()
+            for t in ("HOME", "AWAY"):
+                for o in OUTCOMES:
+                    ref.pa.PA_RECAP_LOG[t][o] = 0
+            res = ref.gs.simulate_game(**_game_kwargs(matchup, use_noise))
+            tapes.append(np.asarray(tape, dtype=np.float64))
+            sums.append(summarize_result(res, matchup))
+            recaps.append([[ref.pa.PA_RECAP_LOG[t][o] for o in OUTCOMES] for t in ("AWAY", "HOME")])
+    finally:
+        ref.pa.np, ref.bip.random, ref.hi.random, ref.bu.random = saved
+        reset_reliever_counts()
+    return tapes, sums, recaps
+
+
+# ---------------------------------------------------------------------------------------------
+# statistical oracle: joint (away, home) counts at caps {1,3,5,7,full} etc.
+# ---------------------------------------------------------------------------------------------
+HB = 64          # bins per team in the joint histograms (matches include/mlbsim.h MLBSIM_HIST_BINS)
+INN_BINS = 32
+
+
+def new_stats():
+    return {
+        "joint": np.zeros((5, HB, HB), dtype=np.int64),     # [cap index][away][home]
+        "innings": np.zeros(INN_BINS, dtype=np.int64),
+        "pa": np.zeros((2, 7), dtype=np.int64),             # [AWAY, HOME][outcome]
+        "rel_games": np.zeros((2, 8), dtype=np.int64),      # [away, home] sims in which reliever i appeared
+        "rel_picks": np.zeros((2, 8), dtype=np.int64),      # total picks
+        "n": 0,
+    }
+
+
+def accumulate(stats, result, matchup):
+    innings = result["innings"]
+    a = h = 0
+    caps = {}
+    for inn in innings:
+        a += inn["away_runs"]
+        h += inn["home_runs"]
+        if inn["inning"] in (1, 3, 5, 7):
+            caps[inn["inning"]] = (a, h)
+    for ci, cap in enumerate((1, 3, 5, 7)):
+        ca, ch = caps[cap]
+        stats["joint"][ci, min(ca, HB - 1), min(ch, HB - 1)] += 1
+    stats["joint"][4, min(result["away_score"], HB - 1), min(result["home_score"], HB - 1)] += 1
+    stats["innings"][min(len(innings), INN_BINS - 1)] += 1
+    for side, key, bp in ((0, "used_away_relievers", "away_bullpen"), (1, "used_home_relievers", "home_bullpen")):
+        lut = {r.get("name", "Unknown"): i for i, r in enumerate(matchup.get(bp) or [])}
+        for n in result[key]:
+            stats["rel_picks"][side, lut[n]] += 1
+        for n in set(result[key]):
+            stats["rel_games"][side, lut[n]] += 1
+    stats["n"] += 1
+
+
+def _stat_worker(args):
+    matchup, n_games, seed, use_noise = args
+    ref = load_reference()
+    reset_reliever_counts()
+    saturate_reliever_counts(matchup)
+    random.seed(seed)
+    np.random.seed(seed % (2**32))
+    for t in ("HOME", "AWAY"):
+        for o in OUTCOMES:
+            ref.pa.PA_RECAP_LOG[t][o] = 0
+    st = new_stats()
+    kw = _game_kwargs(matchup, use_noise)
+    for _ in range(n_games):
+        accumulate(st, ref.gs.simulate_game(**kw), matchup)
+    st["pa"][0] = [ref.pa.PA_RECAP_LOG["AWAY"][o] for o in OUTCOMES]
+    st["pa"][1] = [ref.pa.PA_RECAP_LOG["HOME"][o] for o in OUTCOMES]
+    return st
+
+
+def stat_batch(matchup, n_games, seed, use_noise=True, procs=None):
+    """Reference games over `procs` worker processes with distinct seeds; summed statistics."""
+    import multiprocessing as mp
+
+    procs = procs or os.cpu_count() or 1
+    per = [n_games // procs + (1 if i < n_games % procs else 0) for i in range(procs)]
+    jobs = [(matchup, per[i], seed * 1000 + i, use_noise) for i in range(procs) if per[i]]
+    with mp.get_context("fork").Pool(len(jobs)) as pool:
+        parts = pool.map(_stat_worker, jobs)
+    tot = new_stats()
+    for p in parts:
+        for k in tot:
+            tot[k] = tot[k] + p[k]
+    return tot
