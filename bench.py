@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py — simulated full games / second of the Monte Carlo game sampler on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload single|slate]
+
+One step = one pass of the hot path over one batch: `--sims` simulations (default 10 000 000) of
+every matchup of the workload PER GPU (weak scaling: rank r simulates its own slice of the sim-index
+range; histograms are combined with one NCCL all-reduce).  Default workload = BASELINE.json
+configs[1]: the single game 2025-04-04-TEX@HOU on synthetic Batters/Pitchers.csv-schema players,
+joint runs PMF at caps 1/3/5/7/full + PA outcome counters + reliever usage.  Prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "simulated_games_per_sec"
+UNIT = "games/s"
+I_ALG = 7150.0  # algorithmic thread-instructions per simulated game
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="single", choices=["single", "slate"])
+    ap.add_argument("--sims", type=int, default=None, help="sims per matchup per GPU per step")
+    ap.add_argument("--seed", type=int, default=20250404)
+    ap.add_argument("--threads-per-block", type=int, default=0)
+    ap.add_argument("--blocks-per-sm", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    return ap.parse_args()
+
+
+def workload(args):
+    from mlb_odds_engine_b200 import synth
+
+    if args.workload == "single":
+        ms = [synth.make_matchup("2025-04-04-TEX@HOU")]
+        sims = args.sims or 10_000_000
+        name = "single game 2025-04-04-TEX@HOU x 10M sims per GPU per step (BASELINE configs[1])"
+    else:
+        ms = synth.make_slate("2025-04-04", 15)
+        sims = args.sims or 1_000_000
+        name = "15-game slate x 1M sims per game per GPU per step (BASELINE configs[2])"
+    return ms, sims, name
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, power, reasons = [], [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        # "under load" = samples in the upper half of the observed power range
+        thr = (max(power) + min(power)) / 2 if len(power) > 1 else 0
+        load = [s for s, p in zip(sm, power) if p >= thr] or sm
+        return {"sm_mhz": statistics.median(load), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "power_w_max": max(power), "samples": len(sm)}
+
+
+def cpu_port_throughput(matchups, seconds, use_noise=True):
+    """The oracle's reference-grammar engine (C port of the reference algorithm incl. the Beta noise
+    draws) on all host cores, bounded to ~`seconds` of wall time."""
+    import oracle as orc
+    from mlb_odds_engine_b200 import tables
+
+    params = [tables.build_params(m, use_noise=use_noise) for m in matchups]
+    cores = orc.get_threads()
+    batch = 50_000 * max(1, cores // 2)
+    done, t0, lo = 0, time.perf_counter(), 0
+    orc.grammar(params[0], 1, 0, 20_000)  # warm-up
+    t0 = time.perf_counter()
+    i = 0
+    while True:
+        orc.grammar(params[i % len(params)], 12345, lo, lo + batch)
+        lo += batch; done += batch; i += 1
+        el = time.perf_counter() - t0
+        if el >= seconds:
+            break
+    return done / el, cores, done, el
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm for this path (oracle port: the reference is
+    Python and /root/reference does not exist on the GPU box) on all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle as orc
+    from mlb_odds_engine_b200 import tables
+
+    ms, sims, name = workload(args)
+    cores = orc.get_threads()
+    params = [tables.build_params(m) for m in ms]
+    # each step = a bounded sample of the workload: ~2 s of CPU work
+    probe_n = 20_000
+    t = time.perf_counter(); orc.grammar(params[0], 1, 0, probe_n); rate = probe_n / (time.perf_counter() - t)
+    per_step = max(10_000, int(rate * 2.0 / len(params)))
+    lo = 0
+    for _ in range(args.warmup):
+        for p in params:
+            orc.grammar(p, args.seed, lo, lo + per_step)
+        lo += per_step
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        for p in params:
+            orc.grammar(p, args.seed, lo, lo + per_step)
+        lo += per_step
+    dt = time.perf_counter() - t0
+    games = per_step * len(params) * args.steps
+    v = games / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": name, "sample_per_step": f"{per_step} games per matchup per step ({len(params)} matchups)"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{games} games: C port of the reference algorithm (oracle_grammar, Beta noise sampled), "
+                                   f"{cores} threads; the Python reference itself runs ~450 games/s/core (BASELINE.md)"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+
+    from mlb_odds_engine_b200 import _abi, tables
+    from mlb_odds_engine_b200.dist import ShardedSimulator
+
+    ms, sims_per_gpu, wname = workload(args)
+    n_m = len(ms)
+    t_build = time.perf_counter()
+    tbl = tables.build_tables(ms)
+    t_build = time.perf_counter() - t_build
+    tbl_pinned = torch.from_numpy(tbl.view(np.uint8).reshape(-1).copy()).pin_memory()
+    tbl_host = tbl_pinned.numpy().view(_abi.TABLE_DTYPE)
+
+    S = ShardedSimulator(local)
+    if args.threads_per_block or args.blocks_per_sm:
+        S.ctx.set_launch_config(args.threads_per_block, args.blocks_per_sm)
+    S.load_tables(tbl_host, ms)
+    info = S.ctx.device_info()
+
+    total_per_step = sims_per_gpu * world           # sims per matchup per step over all ranks
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    step_no = [0]
+
+    def device_step(ev=None):
+        lo = step_no[0] * total_per_step
+        step_no[0] += 1
+        if ev:
+            ev[0].record()
+        S.run_device(total_per_step, args.seed, sim_lo=lo)
+        if ev:
+            ev[1].record()
+
+    # ---------------- device-resident timing ----------------
+    for _ in range(args.warmup):
+        device_step()
+        flush.fill_(1)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = S.ctx.launch_count()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kev = []
+    t_wall = time.perf_counter()
+    for i in range(args.steps):
+        device_step(evs[i])
+        flush.fill_(i & 0xFF)   # evict the 126 MB L2 between timed iterations
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    launches = S.ctx.launch_count() - launches0
+    clocks = sampler.stop()
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    games = n_m * total_per_step * args.steps
+    value = games / (total_ms * 1e-3)
+
+    # kernel-only duration (events recorded by the library around the kernel on the same stream)
+    device_step()
+    kern_ms = S.ctx.last_kernel_ms()
+    per_gpu_rate_kernel = n_m * sims_per_gpu / (kern_ms * 1e-3)
+
+    # sanity: totals of the last step
+    hist = S.hist_dev.cpu().numpy().view(np.uint64).view(_abi.HIST_DTYPE)
+    assert int(hist["n_games"].sum()) == n_m * total_per_step, "histogram does not hold every simulated game"
+
+    # ---------------- end-to-end timing (host tables in, host histograms out) ----------------
+    for _ in range(args.warmup):
+        S.simulate(total_per_step, args.seed, sim_lo=step_no[0] * total_per_step, tables_host=tbl_host)
+        step_no[0] += 1
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = S.simulate(total_per_step, args.seed, sim_lo=step_no[0] * total_per_step, tables_host=tbl_host)
+        step_no[0] += 1
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = games / float(e2e_s.item())
+    assert int(out["n_games"].sum()) == n_m * total_per_step
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline: instruction issue (no HBM traffic, no dense contraction) ----------------
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    sm_max_mhz = float(peaks.get("sm_max_mhz") or clocks.get("sm_max_mhz") or 1965.0)
+    peak_tinst = info["sm_count"] * 4 * 32 * sm_max_mhz * 1e6 / 1e12   # thread-instr/s, all 4 schedulers issuing every cycle
+    achieved_tinst = per_gpu_rate_kernel * I_ALG / 1e12
+    hbm_bytes_per_launch = n_m * (_abi.TABLE_DTYPE.itemsize + _abi.HIST_DTYPE.itemsize)
+    roofline = {
+        "bound": "issue", "achieved": achieved_tinst, "peak": peak_tinst, "unit": "Tinst/s (thread instructions)",
+        "frac": achieved_tinst / peak_tinst, "traffic": None,
+        "kernel": "mlbsim_native_kernel", "kernel_ms": kern_ms, "games_per_launch": n_m * sims_per_gpu,
+        "i_alg_thread_instr_per_game": I_ALG,
+        "peak_source": f"{info['sm_count']} SMs x 4 schedulers x 32 lanes x {sm_max_mhz:.0f} MHz (MEASURED_PEAKS.json sm_max_mhz)",
+        "hbm": {"algorithmic_bytes_per_launch": hbm_bytes_per_launch,
+                "achieved_gbs": hbm_bytes_per_launch / (kern_ms * 1e-3) / 1e9, "peak_gbs": peaks.get("hbm_gbs"),
+                "note": "tables (18 KB/matchup) and histograms (165 KB/matchup) only; the path is not HBM-bound"},
+    }
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        v, cores, done, el = cpu_port_throughput(ms, args.cpu_seconds)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"{done} games of the same workload in {el:.1f} s: C port of the reference algorithm "
+                                  f"(oracle_grammar: reference draw grammar, Beta noise sampled) on {cores} threads; "
+                                  "the Python reference itself measured 417-485 games/s/core (BASELINE.md)"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u32", "data": "synthetic",
+        "config": {"workload": wname, "matchups": n_m, "sims_per_matchup_per_gpu_per_step": sims_per_gpu,
+                   "rng": "Philox4x32-10, one block per plate appearance, counter=(sim, pa_seq, matchup), key=seed",
+                   "parallelism": f"sim-index shards x{world}, uint64 histogram all-reduce" if world > 1 else "1 GPU",
+                   "l2": "256 MB device buffer rewritten between timed iterations (L2 flush); every step simulates a fresh sim-index range",
+                   "threads_per_block": args.threads_per_block or 512, "table_build_ms_once": 1e3 * t_build},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(tbl.nbytes),
+                "d2h_bytes_per_step": int(n_m * _abi.HIST_DTYPE.itemsize)},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+        "wall_s_timed_region": t_wall,
+        "device": info["name"],
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

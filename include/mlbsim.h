@@ -127,6 +127,9 @@ int mlbsim_init(int device, mlbsim_ctx** out);
 void mlbsim_destroy(mlbsim_ctx* ctx);
 const char* mlbsim_last_error(const mlbsim_ctx* ctx); /* ctx may be NULL: last init error */
 int mlbsim_abi_version(void);
+/* sizeof of the structs above as compiled into the library: 0 params, 1 table, 2 hist,
+ * 3 replay_game (a binding checks its own mirrors against these at load time). */
+size_t mlbsim_struct_size(int which);
 
 /* Device facts for roofline arithmetic. */
 int mlbsim_device_info(const mlbsim_ctx* ctx, int* sm_count, int* sm_clock_khz, char* name, size_t name_len);
@@ -154,6 +157,15 @@ int mlbsim_run_native(mlbsim_ctx* ctx, int matchup_lo, int matchup_hi, uint64_t 
  * histograms, run, copy to `hist_host`, synchronise. */
 int mlbsim_run_native_host(mlbsim_ctx* ctx, int matchup_lo, int matchup_hi, uint64_t sim_lo, uint64_t sim_hi,
                            uint64_t seed, mlbsim_hist* hist_host, uint32_t flags);
+
+/* Per-sim variant of native mode for small N (the compatibility path under
+ * cli/run_distribution_simulator.py:368-389, which reads result["home_score"], ["away_score"],
+ * ["innings"][i]{away_runs,home_runs}, ["used_*_relievers"]): the same law, the same Philox
+ * streams and therefore the same games as mlbsim_run_native, but one mlbsim_replay_game record
+ * per sim (tape_used = plate appearances played) written to `out_host` (sim_hi - sim_lo records).
+ * Synchronous. */
+int mlbsim_run_persim(mlbsim_ctx* ctx, int matchup, uint64_t sim_lo, uint64_t sim_hi, uint64_t seed,
+                      mlbsim_replay_game* out_host);
 
 /* Replay mode: game g consumes tape[tape_offsets[g] .. tape_offsets[g+1]) (float64 values in the
  * reference's draw order) and writes out[g].  Host pointers; synchronous.

@@ -1,0 +1,418 @@
+// mlbsim_api.cu — the C ABI declared in include/mlbsim.h: context, uploads, launches.
+// No CPU fallback: every compute entry point needs a CUDA device and fails with an error code
+// (never an exception) when something is missing.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "../../include/mlbsim.h"
+#include "native_kernel.h"
+
+struct mlbsim_ctx {
+  int device = -1;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaDeviceProp prop{};
+  mlbsim_table* tables_dev = nullptr;
+  int n_tables = 0;
+  unsigned long long* counters_dev = nullptr;
+  int counters_cap = 0;
+  mlbsim_hist* hist_scratch = nullptr;  // used by *_host entry points
+  int hist_scratch_cap = 0;
+  mlbsim_params* params_dev = nullptr;
+  int threads_per_block = 0;
+  int blocks_per_sm = 0;
+  uint64_t launches = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool timed = false;
+  std::string err;
+};
+
+static thread_local std::string g_init_error;
+
+#define CK(ctx, call)                                                                                   \
+  do {                                                                                                  \
+    cudaError_t e_ = (call);                                                                            \
+    if (e_ != cudaSuccess) {                                                                            \
+      (ctx)->err = std::string(#call) + ": " + cudaGetErrorName(e_) + " (" + cudaGetErrorString(e_) + ")"; \
+      return MLBSIM_ERR_CUDA;                                                                           \
+    }                                                                                                   \
+  } while (0)
+
+static int fail(mlbsim_ctx* ctx, int code, const char* msg) {
+  if (ctx) ctx->err = msg;
+  return code;
+}
+
+extern "C" {
+
+int mlbsim_abi_version(void) { return MLBSIM_ABI_VERSION; }
+
+size_t mlbsim_struct_size(int which) {
+  switch (which) {
+    case 0: return sizeof(mlbsim_params);
+    case 1: return sizeof(mlbsim_table);
+    case 2: return sizeof(mlbsim_hist);
+    case 3: return sizeof(mlbsim_replay_game);
+    default: return 0;
+  }
+}
+
+const char* mlbsim_last_error(const mlbsim_ctx* ctx) { return ctx ? ctx->err.c_str() : g_init_error.c_str(); }
+
+int mlbsim_init(int device, mlbsim_ctx** out) {
+  if (!out) { g_init_error = "mlbsim_init: out is NULL"; return MLBSIM_ERR_ARG; }
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    g_init_error = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    return MLBSIM_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= n) { g_init_error = "mlbsim_init: device index out of range"; return MLBSIM_ERR_ARG; }
+  mlbsim_ctx* ctx = new (std::nothrow) mlbsim_ctx();
+  if (!ctx) { g_init_error = "out of host memory"; return MLBSIM_ERR_ARG; }
+  ctx->device = device;
+  auto bail = [&](const char* what, cudaError_t ce) {
+    g_init_error = std::string(what) + ": " + cudaGetErrorString(ce);
+    delete ctx;
+    return MLBSIM_ERR_CUDA;
+  };
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+  if ((e = cudaGetDeviceProperties(&ctx->prop, device)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
+  if (ctx->prop.major != 10) {
+    g_init_error = std::string("device '") + ctx->prop.name + "' is sm_" + std::to_string(ctx->prop.major) +
+                   std::to_string(ctx->prop.minor) + "; this library is built for sm_100a only";
+    delete ctx;
+    return MLBSIM_ERR_NO_DEVICE;
+  }
+  if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  ctx->stream = ctx->own_stream;
+  if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return bail("cudaEventCreate", e);
+  if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail("cudaEventCreate", e);
+  if ((e = cudaMalloc(&ctx->params_dev, sizeof(mlbsim_params))) != cudaSuccess) return bail("cudaMalloc", e);
+  if ((e = cudaFuncSetAttribute(mlbsim_native_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)mlbsim_native_smem_bytes())) != cudaSuccess)
+    return bail("cudaFuncSetAttribute", e);
+  *out = ctx;
+  return MLBSIM_OK;
+}
+
+void mlbsim_destroy(mlbsim_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
+  cudaFree(ctx->tables_dev);
+  cudaFree(ctx->counters_dev);
+  cudaFree(ctx->hist_scratch);
+  cudaFree(ctx->params_dev);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+}
+
+int mlbsim_device_info(const mlbsim_ctx* ctx, int* sm_count, int* sm_clock_khz, char* name, size_t name_len) {
+  if (!ctx) return MLBSIM_ERR_ARG;
+  if (sm_count) *sm_count = ctx->prop.multiProcessorCount;
+  if (sm_clock_khz) *sm_clock_khz = ctx->prop.clockRate;
+  if (name && name_len) {
+    std::strncpy(name, ctx->prop.name, name_len - 1);
+    name[name_len - 1] = 0;
+  }
+  return MLBSIM_OK;
+}
+
+int mlbsim_set_stream(mlbsim_ctx* ctx, uintptr_t stream) {
+  if (!ctx) return MLBSIM_ERR_ARG;
+  ctx->stream = stream ? reinterpret_cast<cudaStream_t>(stream) : ctx->own_stream;
+  return MLBSIM_OK;
+}
+
+int mlbsim_synchronize(mlbsim_ctx* ctx) {
+  if (!ctx) return MLBSIM_ERR_ARG;
+  CK(ctx, cudaSetDevice(ctx->device));
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  return MLBSIM_OK;
+}
+
+int mlbsim_set_launch_config(mlbsim_ctx* ctx, int threads_per_block, int blocks_per_sm) {
+  if (!ctx) return MLBSIM_ERR_ARG;
+  if (threads_per_block < 0 || threads_per_block > MLBSIM_NATIVE_MAX_THREADS || (threads_per_block % 32) != 0)
+    return fail(ctx, MLBSIM_ERR_ARG, "threads_per_block must be a multiple of 32 in [0, 1024]");
+  if (blocks_per_sm < 0 || blocks_per_sm > 32) return fail(ctx, MLBSIM_ERR_ARG, "blocks_per_sm out of range");
+  ctx->threads_per_block = threads_per_block;
+  ctx->blocks_per_sm = blocks_per_sm;
+  return MLBSIM_OK;
+}
+
+uint64_t mlbsim_launch_count(const mlbsim_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int mlbsim_upload_tables(mlbsim_ctx* ctx, const mlbsim_table* tables, int n_matchups) {
+  if (!ctx) return MLBSIM_ERR_ARG;
+  if (!tables || n_matchups <= 0) return fail(ctx, MLBSIM_ERR_ARG, "mlbsim_upload_tables: no tables");
+  for (int i = 0; i < n_matchups; ++i) {
+    const mlbsim_table& t = tables[i];
+    if (t.magic != MLBSIM_TABLE_MAGIC) return fail(ctx, MLBSIM_ERR_TABLE, "table magic mismatch");
+    for (int s = 0; s < 2; ++s) {
+      if (t.lineup_len[s] < 1 || t.lineup_len[s] > MLBSIM_MAX_LINEUP) return fail(ctx, MLBSIM_ERR_TABLE, "lineup_len out of range");
+      if (t.bullpen_len[s] > MLBSIM_MAX_BULLPEN) return fail(ctx, MLBSIM_ERR_TABLE, "bullpen_len out of range");
+    }
+  }
+  CK(ctx, cudaSetDevice(ctx->device));
+  if (n_matchups > ctx->n_tables || !ctx->tables_dev) {
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->tables_dev);
+    ctx->tables_dev = nullptr;
+    CK(ctx, cudaMalloc(&ctx->tables_dev, sizeof(mlbsim_table) * (size_t)n_matchups));
+  }
+  if (n_matchups > ctx->counters_cap) {
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->counters_dev);
+    ctx->counters_dev = nullptr;
+    CK(ctx, cudaMalloc(&ctx->counters_dev, sizeof(unsigned long long) * (size_t)n_matchups));
+    ctx->counters_cap = n_matchups;
+  }
+  ctx->n_tables = n_matchups;
+  CK(ctx, cudaMemcpyAsync(ctx->tables_dev, tables, sizeof(mlbsim_table) * (size_t)n_matchups, cudaMemcpyHostToDevice, ctx->stream));
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  return MLBSIM_OK;
+}
+
+static int launch_native(mlbsim_ctx* ctx, int matchup_lo, int matchup_hi, uint64_t sim_lo, uint64_t sim_hi, uint64_t seed,
+                         mlbsim_hist* hist_dev, uint32_t flags) {
+  if (!ctx->tables_dev) return fail(ctx, MLBSIM_ERR_STATE, "mlbsim_run_native before mlbsim_upload_tables");
+  if (matchup_lo < 0 || matchup_hi > ctx->n_tables || matchup_lo >= matchup_hi) return fail(ctx, MLBSIM_ERR_ARG, "matchup range out of bounds");
+  if (sim_hi < sim_lo) return fail(ctx, MLBSIM_ERR_ARG, "sim_hi < sim_lo");
+  if (!hist_dev) return fail(ctx, MLBSIM_ERR_ARG, "hist pointer is NULL");
+  const int n_m = matchup_hi - matchup_lo;
+  const int threads = ctx->threads_per_block ? ctx->threads_per_block : 512;
+  const size_t smem = mlbsim_native_smem_bytes();
+  int occ = 0;
+  CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mlbsim_native_kernel, threads, smem));
+  if (occ < 1) return fail(ctx, MLBSIM_ERR_CUDA, "native kernel does not fit on an SM");
+  int bps = ctx->blocks_per_sm ? ctx->blocks_per_sm : occ;
+  if (bps > occ) bps = occ;
+  const int grid = ctx->prop.multiProcessorCount * bps;
+  const uint64_t total_warps = (uint64_t)grid * (threads / 32);
+
+  ctx->timed = false;
+  bool first = true;
+  // a launch covers < 2^32 sims per matchup; longer ranges are split (results are additive)
+  const uint64_t MAX_PER_LAUNCH = 0xFFFF0000ull;
+  uint64_t lo = sim_lo;
+  do {
+    const uint64_t n = (sim_hi - lo) < MAX_PER_LAUNCH ? (sim_hi - lo) : MAX_PER_LAUNCH;
+    NativeArgs a;
+    a.tables = ctx->tables_dev + matchup_lo;
+    a.hist = reinterpret_cast<unsigned long long*>(hist_dev);
+    a.counters = ctx->counters_dev;
+    a.sim_lo = lo;
+    a.n_sims = (uint32_t)n;
+    a.n_matchups = (uint32_t)n_m;
+    a.matchup_base = (uint32_t)matchup_lo;
+    // chunk: ~8 fetches per warp when all warps share one matchup, bounded to [32, 1024], multiple of 32
+    uint64_t chunk = (n * (uint64_t)n_m) / (total_warps * 8 + 1);
+    chunk = (chunk / 32) * 32;
+    if (chunk < 32) chunk = 32;
+    if (chunk > 1024) chunk = 1024;
+    a.chunk = (uint32_t)chunk;
+    a.flags = flags;
+    a.keys = philox_expand_key(seed);
+    CK(ctx, cudaMemsetAsync(ctx->counters_dev, 0, sizeof(unsigned long long) * (size_t)n_m, ctx->stream));
+    if (first) CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    if (n > 0) {
+      mlbsim_native_kernel<<<grid, threads, smem, ctx->stream>>>(a);
+      CK(ctx, cudaGetLastError());
+      ctx->launches++;
+    }
+    first = false;
+    lo += n;
+  } while (lo < sim_hi);
+  CK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  ctx->timed = true;
+  return MLBSIM_OK;
+}
+
+int mlbsim_run_native(mlbsim_ctx* ctx, int matchup_lo, int matchup_hi, uint64_t sim_lo, uint64_t sim_hi, uint64_t seed,
+                      mlbsim_hist* hist_dev, uint32_t flags) {
+  if (!ctx) return MLBSIM_ERR_ARG;
+  CK(ctx, cudaSetDevice(ctx->device));
+  return launch_native(ctx, matchup_lo, matchup_hi, sim_lo, sim_hi, seed, hist_dev, flags);
+}
+
+int mlbsim_run_native_host(mlbsim_ctx* ctx, int matchup_lo, int matchup_hi, uint64_t sim_lo, uint64_t sim_hi, uint64_t seed,
+                           mlbsim_hist* hist_host, uint32_t flags) {
+  if (!ctx) return MLBSIM_ERR_ARG;
+  if (!hist_host) return fail(ctx, MLBSIM_ERR_ARG, "hist pointer is NULL");
+  CK(ctx, cudaSetDevice(ctx->device));
+  const int n_m = matchup_hi - matchup_lo;
+  if (n_m <= 0) return fail(ctx, MLBSIM_ERR_ARG, "matchup range out of bounds");
+  if (n_m > ctx->hist_scratch_cap) {
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->hist_scratch);
+    ctx->hist_scratch = nullptr;
+    CK(ctx, cudaMalloc(&ctx->hist_scratch, sizeof(mlbsim_hist) * (size_t)n_m));
+    ctx->hist_scratch_cap = n_m;
+  }
+  CK(ctx, cudaMemsetAsync(ctx->hist_scratch, 0, sizeof(mlbsim_hist) * (size_t)n_m, ctx->stream));
+  int rc = launch_native(ctx, matchup_lo, matchup_hi, sim_lo, sim_hi, seed, ctx->hist_scratch, flags);
+  if (rc != MLBSIM_OK) return rc;
+  CK(ctx, cudaMemcpyAsync(hist_host, ctx->hist_scratch, sizeof(mlbsim_hist) * (size_t)n_m, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  return MLBSIM_OK;
+}
+
+int mlbsim_last_kernel_ms(mlbsim_ctx* ctx, float* ms) {
+  if (!ctx || !ms) return MLBSIM_ERR_ARG;
+  if (!ctx->timed) return fail(ctx, MLBSIM_ERR_STATE, "no timed launch yet");
+  CK(ctx, cudaSetDevice(ctx->device));
+  CK(ctx, cudaEventSynchronize(ctx->ev1));
+  CK(ctx, cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+  return MLBSIM_OK;
+}
+
+int mlbsim_run_replay_dev(mlbsim_ctx* ctx, const mlbsim_params* params_host, const double* tape_dev,
+                          const uint64_t* tape_offsets_dev, int64_t n_games, mlbsim_replay_game* out_dev) {
+  if (!ctx) return MLBSIM_ERR_ARG;
+  if (!params_host || !tape_offsets_dev || !out_dev || n_games < 0) return fail(ctx, MLBSIM_ERR_ARG, "mlbsim_run_replay: bad argument");
+  for (int s = 0; s < 2; ++s) {
+    if (params_host->lineup_len[s] < 1 || params_host->lineup_len[s] > MLBSIM_MAX_LINEUP) return fail(ctx, MLBSIM_ERR_ARG, "lineup_len out of range");
+    if (params_host->bullpen_len[s] < 0 || params_host->bullpen_len[s] > MLBSIM_MAX_BULLPEN) return fail(ctx, MLBSIM_ERR_ARG, "bullpen_len out of range");
+  }
+  if (n_games == 0) return MLBSIM_OK;
+  CK(ctx, cudaSetDevice(ctx->device));
+  CK(ctx, cudaMemcpyAsync(ctx->params_dev, params_host, sizeof(mlbsim_params), cudaMemcpyHostToDevice, ctx->stream));
+  ReplayArgs a{ctx->params_dev, tape_dev, tape_offsets_dev, out_dev, (long long)n_games};
+  const int threads = 128;
+  long long blocks = (n_games + threads - 1) / threads;
+  const long long cap = (long long)ctx->prop.multiProcessorCount * 16;
+  if (blocks > cap) blocks = cap;
+  CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  mlbsim_replay_kernel<<<(int)blocks, threads, 0, ctx->stream>>>(a);
+  CK(ctx, cudaGetLastError());
+  CK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  ctx->timed = true;
+  ctx->launches++;
+  // params_host may be reused by the caller right away: the H2D copy above must have landed
+  // (pageable source => the copy is already staged when cudaMemcpyAsync returns)
+  return MLBSIM_OK;
+}
+
+int mlbsim_run_replay(mlbsim_ctx* ctx, const mlbsim_params* params, const double* tape, const uint64_t* tape_offsets,
+                      int64_t n_games, mlbsim_replay_game* out) {
+  if (!ctx) return MLBSIM_ERR_ARG;
+  if (!params || !tape_offsets || !out || n_games < 0) return fail(ctx, MLBSIM_ERR_ARG, "mlbsim_run_replay: bad argument");
+  if (n_games == 0) return MLBSIM_OK;
+  CK(ctx, cudaSetDevice(ctx->device));
+  const uint64_t n_draws = tape_offsets[n_games];
+  if (n_draws && !tape) return fail(ctx, MLBSIM_ERR_ARG, "tape is NULL");
+  double* tape_dev = nullptr;
+  uint64_t* off_dev = nullptr;
+  mlbsim_replay_game* out_dev = nullptr;
+  int rc = MLBSIM_OK;
+  cudaError_t e;
+  if ((e = cudaMalloc(&tape_dev, sizeof(double) * (size_t)(n_draws ? n_draws : 1))) != cudaSuccess ||
+      (e = cudaMalloc(&off_dev, sizeof(uint64_t) * (size_t)(n_games + 1))) != cudaSuccess ||
+      (e = cudaMalloc(&out_dev, sizeof(mlbsim_replay_game) * (size_t)n_games)) != cudaSuccess) {
+    ctx->err = std::string("cudaMalloc: ") + cudaGetErrorString(e);
+    rc = MLBSIM_ERR_CUDA;
+  }
+  if (rc == MLBSIM_OK) {
+    if ((e = cudaMemcpyAsync(tape_dev, tape, sizeof(double) * (size_t)n_draws, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(off_dev, tape_offsets, sizeof(uint64_t) * (size_t)(n_games + 1), cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) {
+      ctx->err = std::string("cudaMemcpyAsync: ") + cudaGetErrorString(e);
+      rc = MLBSIM_ERR_CUDA;
+    }
+  }
+  if (rc == MLBSIM_OK) rc = mlbsim_run_replay_dev(ctx, params, tape_dev, off_dev, n_games, out_dev);
+  if (rc == MLBSIM_OK) {
+    if ((e = cudaMemcpyAsync(out, out_dev, sizeof(mlbsim_replay_game) * (size_t)n_games, cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess ||
+        (e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) {
+      ctx->err = std::string("replay copy-back: ") + cudaGetErrorString(e);
+      rc = MLBSIM_ERR_CUDA;
+    }
+  } else {
+    cudaStreamSynchronize(ctx->stream);
+  }
+  cudaFree(tape_dev);
+  cudaFree(off_dev);
+  cudaFree(out_dev);
+  return rc;
+}
+
+int mlbsim_run_persim(mlbsim_ctx* ctx, int matchup, uint64_t sim_lo, uint64_t sim_hi, uint64_t seed, mlbsim_replay_game* out_host) {
+  if (!ctx) return MLBSIM_ERR_ARG;
+  if (!ctx->tables_dev) return fail(ctx, MLBSIM_ERR_STATE, "mlbsim_run_persim before mlbsim_upload_tables");
+  if (matchup < 0 || matchup >= ctx->n_tables) return fail(ctx, MLBSIM_ERR_ARG, "matchup out of range");
+  if (sim_hi < sim_lo || !out_host) return fail(ctx, MLBSIM_ERR_ARG, "mlbsim_run_persim: bad argument");
+  const uint64_t n = sim_hi - sim_lo;
+  if (n == 0) return MLBSIM_OK;
+  CK(ctx, cudaSetDevice(ctx->device));
+  mlbsim_replay_game* out_dev = nullptr;
+  CK(ctx, cudaMalloc(&out_dev, sizeof(mlbsim_replay_game) * (size_t)n));
+  PersimArgs a;
+  a.table = ctx->tables_dev + matchup;
+  a.out = out_dev;
+  a.sim_lo = sim_lo;
+  a.n_sims = n;
+  a.matchup_id = (uint32_t)matchup;
+  a.keys = philox_expand_key(seed);
+  const int threads = 128;
+  uint64_t blocks = (n + threads - 1) / threads;
+  const uint64_t cap = (uint64_t)ctx->prop.multiProcessorCount * 16;
+  if (blocks > cap) blocks = cap;
+  mlbsim_persim_kernel<<<(int)blocks, threads, 0, ctx->stream>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out_host, out_dev, sizeof(mlbsim_replay_game) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(out_dev);
+  ctx->launches++;
+  if (e != cudaSuccess) {
+    ctx->err = std::string("mlbsim_run_persim: ") + cudaGetErrorString(e);
+    return MLBSIM_ERR_CUDA;
+  }
+  return MLBSIM_OK;
+}
+
+int mlbsim_malloc(mlbsim_ctx* ctx, size_t bytes, void** dev_ptr) {
+  if (!ctx || !dev_ptr) return MLBSIM_ERR_ARG;
+  CK(ctx, cudaSetDevice(ctx->device));
+  CK(ctx, cudaMalloc(dev_ptr, bytes ? bytes : 1));
+  return MLBSIM_OK;
+}
+
+int mlbsim_free(mlbsim_ctx* ctx, void* dev_ptr) {
+  if (!ctx) return MLBSIM_ERR_ARG;
+  CK(ctx, cudaSetDevice(ctx->device));
+  CK(ctx, cudaFree(dev_ptr));
+  return MLBSIM_OK;
+}
+
+int mlbsim_memset(mlbsim_ctx* ctx, void* dev_ptr, int value, size_t bytes) {
+  if (!ctx || !dev_ptr) return MLBSIM_ERR_ARG;
+  CK(ctx, cudaSetDevice(ctx->device));
+  CK(ctx, cudaMemsetAsync(dev_ptr, value, bytes, ctx->stream));
+  return MLBSIM_OK;
+}
+
+int mlbsim_memcpy_h2d(mlbsim_ctx* ctx, void* dev_dst, const void* host_src, size_t bytes) {
+  if (!ctx || !dev_dst || !host_src) return MLBSIM_ERR_ARG;
+  CK(ctx, cudaSetDevice(ctx->device));
+  CK(ctx, cudaMemcpyAsync(dev_dst, host_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  return MLBSIM_OK;
+}
+
+int mlbsim_memcpy_d2h(mlbsim_ctx* ctx, void* host_dst, const void* dev_src, size_t bytes) {
+  if (!ctx || !host_dst || !dev_src) return MLBSIM_ERR_ARG;
+  CK(ctx, cudaSetDevice(ctx->device));
+  CK(ctx, cudaMemcpyAsync(host_dst, dev_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  return MLBSIM_OK;
+}
+
+}  // extern "C"

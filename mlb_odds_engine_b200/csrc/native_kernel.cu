@@ -1,0 +1,451 @@
+// native_kernel.cu — native-RNG Monte Carlo game sampler for sm_100a.
+//
+// Replaces the serial loop of cli/run_distribution_simulator.py:368-382 over
+// core/game_simulator.py:14-156 -> core/half_inning_simulator.py:138-258 -> core/pa_simulator.py:91-143
+// (+ bip_resolution, fatigue_modeling, bullpen_utils.simulate_reliever_chain).
+//
+// Execution model
+//   * one thread = one game at a time, a register-resident state machine; one loop iteration =
+//     one plate appearance for every live lane of the warp (flat loop: half-inning, inning and
+//     game boundaries are predicated blocks inside the iteration, so lanes never wait for each
+//     other at those boundaries);
+//   * a lane that finishes a game immediately starts the next unassigned sim of its warp's
+//     chunk (warp-ballot prefix, no atomics); warps pull chunks of the matchup's sim range
+//     from a global counter.  Sim i draws Philox4x32-10 blocks with counter (i_lo, i_hi, pa_seq,
+//     matchup) and key = seed, so which lane / block / GPU runs it is irrelevant to its result;
+//   * the per-matchup threshold table (16 KB), the transition LUT (2.6 KB) and the five joint
+//     (away, home) histograms (20 KB of u32 bins) live in shared memory; histograms are flushed
+//     to the uint64 device totals once per (block, matchup);
+//   * no tensor cores: there is no dense contraction in this path.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mlbsim.h"
+#include "native_kernel.h"
+#include "philox.cuh"
+
+namespace {
+
+// ---- model constants (reference file:line) ----------------------------------------------------
+constexpr uint32_t T_DP = 601295421u;        // 0.14 * 2^32   half_inning_simulator.py:76
+constexpr uint32_t T_040 = 1717986918u;      // 0.40 * 2^32   :103 (1B: runner on 2B scores), :120 (2B: runner on 1B scores)
+constexpr uint32_t T_046 = 1975684956u;      // 0.40 + 0.60*0.10: :103 combined with the two-out rule :28-39
+constexpr uint32_t T_080 = 3435973837u;      // 0.80 * 2^32   :105 (1B: runner on 1B takes second)
+constexpr uint32_t T_END_BOTH = 472446u;     // 0.011*0.01        misc run AND ghost run  :12-25
+constexpr uint32_t T_END_ANY = 89721867u;    // 1-0.989*0.99      misc run OR ghost run
+constexpr uint32_t T_END_GHOST = 42949673u;  // 0.01              ghost run only (inning already scored)
+constexpr int MAX_PA_PER_HALF = 30;          // half_inning_simulator.py:160
+constexpr int PITCH_LIMIT = 90;              // game_simulator.py:8
+constexpr int FATIGUE_START = 75;            // fatigue_modeling.py:38
+
+// ---- shared-memory layout ---------------------------------------------------------------------
+constexpr int SB = 32;                                    // smem joint-histogram bins per team
+constexpr int THR_WORDS = 2 * MLBSIM_MAX_PITCHERS * MLBSIM_N_TIERS * MLBSIM_MAX_LINEUP * MLBSIM_ROW_WORDS;  // 4032
+constexpr int SLOPE_WORDS = 2 * MLBSIM_N_TIERS * MLBSIM_MAX_LINEUP * MLBSIM_ROW_WORDS;                      // 576
+constexpr int LUT_WORDS = 7 * 4 * 24;                                                                       // 672
+constexpr int JOINT_WORDS = MLBSIM_N_CAPS * SB * SB;                                                        // 5120
+
+struct __align__(16) Smem {
+  uint32_t thr[THR_WORDS];
+  int32_t slope[SLOPE_WORDS];
+  uint32_t lut[LUT_WORDS];
+  uint32_t joint[JOINT_WORDS];
+  uint32_t innings[MLBSIM_INN_BINS];
+  uint32_t rel_games[16];
+  uint32_t rel_picks[16];
+  uint32_t n_games;
+  uint32_t hdr_flags, L0, L1, nb0, nb1;
+  uint32_t go;  // block-uniform "this matchup still has work"
+};
+
+// ---- per-side context word --------------------------------------------------------------------
+// slot[3:0] | tier[5:4] | pit[8:6] | pitch_count[19:9] | score[31:20]   (side = batting side)
+constexpr uint32_t CX_SLOT = 0xFu;
+constexpr uint32_t CX_TIER_ONE = 1u << 4;
+constexpr uint32_t CX_TIER_MASK = 3u << 4;
+constexpr int CX_T_SHIFT = 4;  // (ctx >> 4) & 31 = pit*4 + tier
+constexpr int CX_PIT_SHIFT = 6;
+constexpr int CX_PC_SHIFT = 9;
+constexpr uint32_t CX_PC_ONE = 1u << 9;
+constexpr uint32_t CX_PC_MASK = 0x7FFu;
+constexpr int CX_SCORE_SHIFT = 20;
+constexpr uint32_t CX_STAFF_MASK = 0x000FFFF0u;  // tier | pit | pitch_count
+
+// ---- half-inning state word -------------------------------------------------------------------
+// ob[4:0] = outs*8 + bases | n_pa[13:8] | runs[21:16] | reached_count[29:24]
+constexpr uint32_t HS_OB = 31u;
+constexpr uint32_t HS_NPA_ONE = 1u << 8;
+constexpr uint32_t HS_NPA_MASK = 0x3Fu << 8;
+
+// LUT entry: new_ob | runs << 16 | reached << 24, so that  hs' = (hs & ~31) + 256 + entry.
+__device__ uint32_t transition_entry(int o, int dA, int dB, int outs, int bases) {
+  int nb = bases, r = 0, oa = 0;
+  const int on1 = bases & 1, on2 = (bases >> 1) & 1, on3 = (bases >> 2) & 1;
+  if (o == MLBSIM_K || o == MLBSIM_OUT) {  // half_inning_simulator.py:73-82
+    if (on1 && outs < 2 && dA) { nb = bases & 6; oa = 2; } else { oa = 1; }
+  } else if (o == MLBSIM_BB) {             // :84-94
+    r = (bases == 7);
+    nb = 1 | (on1 << 1) | ((on2 | on3) << 2);  // runner on 2B always goes to 3B; 3B holds unless forced
+  } else if (o == MLBSIM_1B) {             // :97-109 (+ :28-39 folded into dA at two outs)
+    r = on3 + (on2 & dA);
+    nb = 1 | ((on1 & dB) << 1) | ((on2 & (dA ^ 1)) << 2);
+  } else if (o == MLBSIM_2B) {             // :112-123
+    r = on3 + on2 + (on1 & dA);
+    nb = 2 | ((on1 & (dA ^ 1)) << 2);
+  } else if (o == MLBSIM_3B) {             // :126-129
+    r = on1 + on2 + on3; nb = 4;
+  } else {                                 // HR :132-136
+    r = on1 + on2 + on3 + 1; nb = 0;
+  }
+  int no = outs + oa;
+  if (no > 3) no = 3;
+  const int reached = (r > 0) || (nb != 0);
+  return (uint32_t)(no * 8 + nb) | ((uint32_t)r << 16) | ((uint32_t)reached << 24);
+}
+
+__device__ __forceinline__ uint32_t lanemask_lt() {
+  uint32_t m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+
+}  // namespace
+
+extern "C" __global__ void __launch_bounds__(MLBSIM_NATIVE_MAX_THREADS, 1)
+mlbsim_native_kernel(const NativeArgs args) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem& S = *reinterpret_cast<Smem*>(smem_raw);
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const uint32_t n_sims = args.n_sims;
+
+  // transition LUT: derived once per block from the branchy semantics above
+  for (int i = tid; i < LUT_WORDS; i += blockDim.x) {
+    const int ob = i % 24, sel = i / 24;
+    S.lut[i] = transition_entry(sel >> 2, (sel >> 1) & 1, sel & 1, ob >> 3, ob & 7);
+  }
+
+  for (uint32_t step = 0; step < args.n_matchups; ++step) {
+    const uint32_t m = (blockIdx.x + step) % args.n_matchups;
+    __syncthreads();  // previous matchup fully flushed; S.go free for reuse
+    if (tid == 0) S.go = (*(volatile unsigned long long*)&args.counters[m] < (unsigned long long)n_sims) ? 1u : 0u;
+    __syncthreads();
+    if (!S.go) continue;
+
+    // ---- stage this matchup's table; clear block-local accumulators ----
+    {
+      const mlbsim_table* T = args.tables + m;
+      const uint4* src = reinterpret_cast<const uint4*>(T->thr);
+      uint4* dst = reinterpret_cast<uint4*>(S.thr);
+      for (int i = tid; i < THR_WORDS / 4; i += blockDim.x) dst[i] = __ldg(src + i);
+      const int4* ssrc = reinterpret_cast<const int4*>(T->slope);
+      int4* sdst = reinterpret_cast<int4*>(S.slope);
+      for (int i = tid; i < SLOPE_WORDS / 4; i += blockDim.x) sdst[i] = __ldg(ssrc + i);
+      for (int i = tid; i < JOINT_WORDS; i += blockDim.x) S.joint[i] = 0;
+      if (tid < MLBSIM_INN_BINS) S.innings[tid] = 0;
+      if (tid < 16) { S.rel_games[tid] = 0; S.rel_picks[tid] = 0; }
+      if (tid == 0) {
+        S.n_games = 0;
+        S.hdr_flags = T->flags; S.L0 = T->lineup_len[0]; S.L1 = T->lineup_len[1];
+        S.nb0 = T->bullpen_len[0]; S.nb1 = T->bullpen_len[1];
+      }
+    }
+    __syncthreads();
+
+    const bool fatigue = (S.hdr_flags & MLBSIM_FLAG_FATIGUE) != 0;
+    const bool count_pa = (args.flags & 1u) == 0;
+    const uint32_t L0 = S.L0, L1 = S.L1, nb0 = S.nb0, nb1 = S.nb1;
+    const uint32_t c3 = args.matchup_base + m;
+    unsigned long long* const H = args.hist + (size_t)m * MLBSIM_HIST_WORDS;
+    unsigned long long* const counter = args.counters + m;
+    // word offsets inside mlbsim_hist
+    constexpr size_t H_INN = (size_t)MLBSIM_N_CAPS * MLBSIM_HIST_BINS * MLBSIM_HIST_BINS;
+    constexpr size_t H_PA = H_INN + MLBSIM_INN_BINS;
+    constexpr size_t H_RELG = H_PA + 16;
+    constexpr size_t H_RELP = H_RELG + 16;
+    constexpr size_t H_N = H_RELP + 16;
+
+    // ---- warp-uniform work state ----
+    uint32_t chunk_next = 0, chunk_end = 0;
+    bool exhausted = false;
+
+    // ---- lane state ----
+    bool alive = false;
+    uint32_t c0 = 0, c1 = 0, seq = 0;
+    uint32_t cA = 0, cB = 0, cur = 0;  // side contexts (A: away bats, B: home bats), cur = live copy
+    uint32_t hs = 0;                   // half-inning state
+    uint32_t side = 0, inning = 1;
+    uint32_t capA = 0, capH = 0;       // scores after innings 1,3,5,7 (8 bits each)
+    uint32_t used = 0;                 // reliever bitmasks: home staff bits 0-7, away staff 8-15
+    unsigned long long pa0 = 0, pa1 = 0;  // packed 8-bit outcome counters per side
+    int flush_in = 255;
+
+    for (;;) {
+      // ---------------- refill / termination (warp-synchronous) ----------------
+      const uint32_t need = __ballot_sync(0xffffffffu, !alive);
+      if (need) {
+        if (chunk_next >= chunk_end && !exhausted) {
+          unsigned long long base = 0;
+          if (lane == 0) base = atomicAdd(counter, (unsigned long long)args.chunk);
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (base >= (unsigned long long)n_sims) {
+            exhausted = true;
+          } else {
+            chunk_next = (uint32_t)base;
+            const unsigned long long e = base + args.chunk;
+            chunk_end = e < (unsigned long long)n_sims ? (uint32_t)e : n_sims;
+          }
+        }
+        const uint32_t avail = chunk_end - chunk_next;
+        const uint32_t rank = __popc(need & lanemask_lt());
+        if (!alive && rank < avail) {
+          const unsigned long long sim = (unsigned long long)args.sim_lo + (chunk_next + rank);
+          c0 = (uint32_t)sim; c1 = (uint32_t)(sim >> 32); seq = 0;
+          cA = 0; cB = 0; cur = 0; hs = 0; side = 0; inning = 1; capA = 0; capH = 0; used = 0;
+          alive = true;
+        }
+        const uint32_t want = __popc(need);
+        chunk_next += want < avail ? want : avail;
+        if (exhausted && __ballot_sync(0xffffffffu, alive) == 0) break;
+      }
+
+      if (alive) {
+        // ---------------- one plate appearance ----------------
+        uint32_t w0, w1, w2, w3;
+        philox4x32_10(c0, c1, seq, c3, args.keys, w0, w1, w2, w3);
+        ++seq;
+
+        const uint32_t slot = cur & CX_SLOT;
+        // TTO: half_inning_simulator.py:177-178 — bump when the lineup wraps inside or across halves,
+        // but not when a half starts at slot 0 of a fresh walk (n_pa == 0)
+        if (slot == 0 && (hs & HS_NPA_MASK) != 0 && (cur & CX_TIER_MASK) != CX_TIER_MASK) cur += CX_TIER_ONE;
+        const uint32_t T = (cur >> CX_T_SHIFT) & 31u;  // pit*4 + tier
+        const uint32_t row = (side * (MLBSIM_MAX_PITCHERS * MLBSIM_N_TIERS) + T) * MLBSIM_MAX_LINEUP + slot;
+        const uint4 ta = *reinterpret_cast<const uint4*>(&S.thr[row * MLBSIM_ROW_WORDS]);
+        const uint2 tb = *reinterpret_cast<const uint2*>(&S.thr[row * MLBSIM_ROW_WORDS + 4]);
+        uint32_t t0 = ta.x, t1 = ta.y, t2 = ta.z, t3 = ta.w, t4 = tb.x, t5 = tb.y;
+        if (fatigue) {
+          const uint32_t pc = (cur >> CX_PC_SHIFT) & CX_PC_MASK;
+          if (T < 4u && pc > (uint32_t)FATIGUE_START) {  // starter (pit == 0) past 75 pitches
+            const uint32_t e = pc - FATIGUE_START;
+            const uint32_t srow = (side * MLBSIM_N_TIERS + T) * MLBSIM_MAX_LINEUP + slot;
+            const int4 sa = *reinterpret_cast<const int4*>(&S.slope[srow * MLBSIM_ROW_WORDS]);
+            const int2 sb = *reinterpret_cast<const int2*>(&S.slope[srow * MLBSIM_ROW_WORDS + 4]);
+            t0 += e * (uint32_t)sa.x; t1 += e * (uint32_t)sa.y; t2 += e * (uint32_t)sa.z;
+            t3 += e * (uint32_t)sa.w; t4 += e * (uint32_t)sb.x; t5 += e * (uint32_t)sb.y;
+          }
+        }
+        const uint32_t u = w0 >> 1;
+        const uint32_t o = (u >= t0) + (u >= t1) + (u >= t2) + (u >= t3) + (u >= t4) + (u >= t5);
+
+        const uint32_t ob = hs & HS_OB;
+        uint32_t tA = T_DP;
+        if (o == MLBSIM_1B) tA = (ob >= 16u) ? T_046 : T_040;
+        if (o == MLBSIM_2B) tA = T_040;
+        const uint32_t sel = o * 4u + (w1 < tA ? 2u : 0u) + (w2 < T_080 ? 1u : 0u);
+        const uint32_t ent = S.lut[sel * 24u + ob];
+        hs = (hs & ~HS_OB) + HS_NPA_ONE + ent;
+
+        if (count_pa) {
+          const unsigned long long inc = 1ull << (o * 8u);
+          if (side) pa1 += inc; else pa0 += inc;
+        }
+
+        // next batter, one more pitch (pitch_count counts PAs: half_inning_simulator.py:218-220)
+        cur += CX_PC_ONE + 1u;
+        if ((cur & CX_SLOT) == (side ? L1 : L0)) cur -= (side ? L1 : L0);
+
+        // ---------------- end of half inning ----------------
+        if ((hs & HS_OB) >= 24u || ((hs >> 8) & 63u) >= (uint32_t)MAX_PA_PER_HALF) {
+          uint32_t runs = (hs >> 16) & 63u;
+          if ((hs >> 24) != 0u) {  // runner_reached
+            runs += (runs == 0u) ? (uint32_t)(w3 < T_END_BOTH) + (uint32_t)(w3 < T_END_ANY) : (uint32_t)(w3 < T_END_GHOST);
+          }
+          cur += runs << CX_SCORE_SHIFT;
+          if (side) cB = cur; else cA = cur;
+          const uint32_t sa = cA >> CX_SCORE_SHIFT, sh = cB >> CX_SCORE_SHIFT;
+          bool over = false;
+          if (side == 0) {
+            if (inning == 9 && sh > sa) over = true;  // game_simulator.py:72 — bottom of the 9th skipped
+            else side = 1;
+          } else {
+            if (inning <= 7 && (inning & 1u)) {       // run_distribution_simulator.py:414-424 caps
+              const uint32_t sft = (inning >> 1) * 8u;
+              capA |= (sa < 255u ? sa : 255u) << sft;
+              capH |= (sh < 255u ? sh : 255u) << sft;
+            }
+            if (inning >= 9 && sa != sh) over = true; // game_simulator.py:110-111
+            else { side = 0; ++inning; }
+          }
+          if (!over) {
+            cur = side ? cB : cA;
+            hs = 0;
+            // should_replace_pitcher (game_simulator.py:8-12) for the staff that now takes the mound
+            const uint32_t nb = side ? nb1 : nb0;
+            const uint32_t pc = (cur >> CX_PC_SHIFT) & CX_PC_MASK;
+            if (nb != 0u && (pc > (uint32_t)PITCH_LIMIT || (cur & CX_TIER_MASK) >= (2u << 4))) {
+              const uint32_t idx = __umulhi(w2, nb);  // stationary law of simulate_reliever_chain: uniform, with replacement
+              cur = (cur & ~CX_STAFF_MASK) | ((idx + 1u) << CX_PIT_SHIFT);
+              used |= 1u << (idx + side * 8u);
+              atomicAdd(&S.rel_picks[side * 8u + idx], 1u);
+            }
+          } else {
+            // ---------------- game over: commit ----------------
+            const uint32_t a4[5] = {capA & 255u, (capA >> 8) & 255u, (capA >> 16) & 255u, capA >> 24, sa};
+            const uint32_t h4[5] = {capH & 255u, (capH >> 8) & 255u, (capH >> 16) & 255u, capH >> 24, sh};
+#pragma unroll
+            for (int c = 0; c < MLBSIM_N_CAPS; ++c) {
+              const uint32_t a = a4[c], h = h4[c];
+              if ((a | h) < (uint32_t)SB) {
+                atomicAdd(&S.joint[c * SB * SB + a * SB + h], 1u);
+              } else {
+                const uint32_t ac = a < MLBSIM_HIST_BINS - 1 ? a : MLBSIM_HIST_BINS - 1;
+                const uint32_t hc = h < MLBSIM_HIST_BINS - 1 ? h : MLBSIM_HIST_BINS - 1;
+                atomicAdd(&H[((size_t)c * MLBSIM_HIST_BINS + ac) * MLBSIM_HIST_BINS + hc], 1ull);
+              }
+            }
+            atomicAdd(&S.innings[inning < MLBSIM_INN_BINS - 1 ? inning : MLBSIM_INN_BINS - 1], 1u);
+            uint32_t um = used;
+            while (um) {
+              const int b = __ffs(um) - 1;
+              um &= um - 1;
+              atomicAdd(&S.rel_games[b], 1u);
+            }
+            atomicAdd(&S.n_games, 1u);
+            alive = false;
+          }
+        }
+      }
+
+      // ---------------- periodic flush of the packed PA counters ----------------
+      if (count_pa && --flush_in == 0) {
+        flush_in = 255;
+#pragma unroll
+        for (int o = 0; o < MLBSIM_N_OUTCOMES; ++o) {
+          const uint32_t v0 = __reduce_add_sync(0xffffffffu, (uint32_t)(pa0 >> (8 * o)) & 255u);
+          const uint32_t v1 = __reduce_add_sync(0xffffffffu, (uint32_t)(pa1 >> (8 * o)) & 255u);
+          if (lane == 0) {
+            if (v0) atomicAdd(&H[H_PA + o], (unsigned long long)v0);
+            if (v1) atomicAdd(&H[H_PA + 8 + o], (unsigned long long)v1);
+          }
+        }
+        pa0 = 0; pa1 = 0;
+      }
+    }
+
+    // ---- final PA counter flush for this warp ----
+    if (count_pa) {
+#pragma unroll
+      for (int o = 0; o < MLBSIM_N_OUTCOMES; ++o) {
+        const uint32_t v0 = __reduce_add_sync(0xffffffffu, (uint32_t)(pa0 >> (8 * o)) & 255u);
+        const uint32_t v1 = __reduce_add_sync(0xffffffffu, (uint32_t)(pa1 >> (8 * o)) & 255u);
+        if (lane == 0) {
+          if (v0) atomicAdd(&H[H_PA + o], (unsigned long long)v0);
+          if (v1) atomicAdd(&H[H_PA + 8 + o], (unsigned long long)v1);
+        }
+      }
+    }
+
+    // ---- block flush: shared u32 bins -> device u64 totals ----
+    __syncthreads();
+    for (int i = tid; i < JOINT_WORDS; i += blockDim.x) {
+      const uint32_t v = S.joint[i];
+      if (v) {
+        const int c = i / (SB * SB), a = (i / SB) % SB, h = i % SB;
+        atomicAdd(&H[((size_t)c * MLBSIM_HIST_BINS + a) * MLBSIM_HIST_BINS + h], (unsigned long long)v);
+      }
+    }
+    if (tid < MLBSIM_INN_BINS && S.innings[tid]) atomicAdd(&H[H_INN + tid], (unsigned long long)S.innings[tid]);
+    if (tid < 16) {
+      if (S.rel_games[tid]) atomicAdd(&H[H_RELG + tid], (unsigned long long)S.rel_games[tid]);
+      if (S.rel_picks[tid]) atomicAdd(&H[H_RELP + tid], (unsigned long long)S.rel_picks[tid]);
+    }
+    if (tid == 0 && S.n_games) atomicAdd(&H[H_N], (unsigned long long)S.n_games);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per-sim variant (small N compatibility path and cross-check of the flat kernel): one thread
+// plays one game with plain nested loops, reads thresholds straight from global memory and
+// writes a full mlbsim_replay_game record.  Same law, same Philox streams => the same games as
+// mlbsim_native_kernel.
+// ---------------------------------------------------------------------------------------------
+extern "C" __global__ void __launch_bounds__(128)
+mlbsim_persim_kernel(const PersimArgs args) {
+  const mlbsim_table* __restrict__ T = args.table;
+  for (unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; g < args.n_sims;
+       g += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned long long sim = args.sim_lo + g;
+    const uint32_t c0 = (uint32_t)sim, c1 = (uint32_t)(sim >> 32);
+    uint32_t seq = 0, w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+    __align__(16) mlbsim_replay_game R;
+    {
+      uint32_t* z = reinterpret_cast<uint32_t*>(&R);
+#pragma unroll 1
+      for (int i = 0; i < (int)(sizeof(R) / 4); ++i) z[i] = 0;
+    }
+    int score[2] = {0, 0}, slot[2] = {0, 0}, n_used[2] = {0, 0};
+    int pc[2] = {0, 0}, tto[2] = {1, 1}, pit[2] = {0, 0};
+    int inning = 1;
+    for (;;) {
+      int rr[2] = {0, 0};
+      for (int side = 0; side < 2; ++side) {
+        if (side == 1 && inning == 9 && score[1] > score[0]) break;
+        const uint32_t nbp = T->bullpen_len[side];
+        if ((pc[side] > PITCH_LIMIT || tto[side] >= 3) && nbp > 0) {
+          const uint32_t idx = __umulhi(w2, nbp);
+          pit[side] = 1 + (int)idx; pc[side] = 0; tto[side] = 1;
+          uint8_t* used = side == 0 ? R.used_home : R.used_away;
+          if (n_used[side] < MLBSIM_REPLAY_MAX_USED) used[n_used[side]] = (uint8_t)idx;
+          else R.status |= MLBSIM_ST_USED_OVERFLOW;
+          n_used[side]++;
+        }
+        const int L = (int)T->lineup_len[side];
+        int outs = 0, bases = 0, runs = 0, n = 0, sl = slot[side];
+        bool reached = false;
+        while (outs < 3 && n < MAX_PA_PER_HALF) {
+          philox4x32_10(c0, c1, seq, args.matchup_id, args.keys, w0, w1, w2, w3);
+          ++seq;
+          if (sl == 0 && n > 0) tto[side] += 1;
+          const int tier = (tto[side] >= 4 ? 4 : tto[side]) - 1;
+          const uint32_t* row = T->thr[side][pit[side]][tier][sl];
+          const int32_t* sp = T->slope[side][tier][sl];
+          const uint32_t e = (pit[side] == 0 && pc[side] > FATIGUE_START) ? (uint32_t)(pc[side] - FATIGUE_START) : 0u;
+          const uint32_t u = w0 >> 1;
+          int o = 0;
+#pragma unroll
+          for (int j = 0; j < 6; ++j) o += (u >= row[j] + e * (uint32_t)sp[j]) ? 1 : 0;
+          const uint32_t tA = (o == MLBSIM_1B) ? (outs == 2 ? T_046 : T_040) : (o == MLBSIM_2B) ? T_040 : T_DP;
+          const uint32_t ent = transition_entry(o, w1 < tA, w2 < T_080, outs, bases);
+          const int r = (ent >> 16) & 7;
+          outs = (ent & 31u) >> 3; bases = ent & 7u; runs += r;
+          if ((ent >> 24) & 1u) reached = true;
+          R.pa[side][o] += 1;
+          pc[side] += 1; n += 1; sl = (sl + 1 == L) ? 0 : sl + 1;
+        }
+        if (reached) runs += (runs == 0) ? (int)(w3 < T_END_BOTH) + (int)(w3 < T_END_ANY) : (int)(w3 < T_END_GHOST);
+        slot[side] = sl;
+        score[side] += runs;
+        rr[side] = runs;
+      }
+      if (inning <= MLBSIM_REPLAY_MAX_INNINGS) {
+        R.away_runs[inning - 1] = (uint8_t)(rr[0] > 255 ? 255 : rr[0]);
+        R.home_runs[inning - 1] = (uint8_t)(rr[1] > 255 ? 255 : rr[1]);
+      } else {
+        R.status |= MLBSIM_ST_INNINGS_OVERFLOW;
+      }
+      if (inning >= 9 && score[0] != score[1]) break;
+      inning += 1;
+    }
+    R.home_score = score[1]; R.away_score = score[0]; R.n_innings = inning;
+    R.tape_used = (int32_t)seq;
+    R.n_used[0] = n_used[0]; R.n_used[1] = n_used[1];
+    const uint4* s4 = reinterpret_cast<const uint4*>(&R);
+    uint4* d4 = reinterpret_cast<uint4*>(args.out + g);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(R) / 16); ++i) d4[i] = s4[i];
+  }
+}
+
+size_t mlbsim_native_smem_bytes() { return sizeof(Smem); }

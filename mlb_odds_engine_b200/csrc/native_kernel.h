@@ -1,0 +1,46 @@
+// Launch interface between the C-ABI translation unit and the kernels (internal, not exported).
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/mlbsim.h"
+#include "philox.cuh"
+
+#define MLBSIM_NATIVE_MAX_THREADS 1024
+
+struct NativeArgs {
+  const mlbsim_table* tables;    // device, n_matchups entries (already offset to matchup_lo)
+  unsigned long long* hist;      // device, n_matchups * MLBSIM_HIST_WORDS uint64 counters
+  unsigned long long* counters;  // device, n_matchups work counters, zero at launch
+  uint64_t sim_lo;               // first sim index of this launch
+  uint32_t n_sims;               // sims per matchup in this launch (< 2^32)
+  uint32_t n_matchups;
+  uint32_t matchup_base;         // global id of tables[0] (Philox counter word 3)
+  uint32_t chunk;                // sims a warp takes per fetch
+  uint32_t flags;                // bit 0: skip PA outcome counters
+  PhiloxKeys keys;
+};
+
+struct ReplayArgs {
+  const mlbsim_params* params;  // device
+  const double* tape;           // device
+  const uint64_t* offsets;      // device, n_games + 1
+  mlbsim_replay_game* out;      // device
+  long long n_games;
+};
+
+struct PersimArgs {
+  const mlbsim_table* table;  // device, one matchup
+  mlbsim_replay_game* out;    // device, n_sims records
+  unsigned long long sim_lo;
+  unsigned long long n_sims;
+  uint32_t matchup_id;        // Philox counter word 3
+  PhiloxKeys keys;
+};
+
+#ifdef __CUDACC__
+extern "C" __global__ void mlbsim_persim_kernel(const PersimArgs args);
+extern "C" __global__ void mlbsim_native_kernel(const NativeArgs args);
+extern "C" __global__ void mlbsim_replay_kernel(const ReplayArgs args);
+#endif
+size_t mlbsim_native_smem_bytes();

@@ -327,6 +327,7 @@ static void engine_game(const mlbsim_params* P, source* src, mlbsim_replay_game*
     }
     if (res && inning <= 7 && (inning & 1)) { res->cap_a[inning >> 1] = score[0]; res->cap_h[inning >> 1] = score[1]; }
     if (inning >= 9 && score[0] != score[1]) break;                            /* :110-111 */
+    if (src->underrun && inning >= 200) break; /* a dry tape (all 0.5) may never break a tie */
     inning += 1;
   }
   if (out) {
@@ -470,76 +471,116 @@ static uint32_t native_transition(int o, int dA, int dB, int outs, int bases) {
   return (uint32_t)nb | (uint32_t)r << 3 | (uint32_t)oa << 6;
 }
 
-typedef struct { const mlbsim_table* T; uint32_t matchup; uint64_t seed; mlbsim_hist* hist; uint32_t flags; } native_args;
-static void native_range(int64_t lo, int64_t hi, void* argp) {
-  native_args* a = (native_args*)argp;
-  const mlbsim_table* T = a->T;
-  const uint32_t matchup = a->matchup;
-  const uint32_t key[2] = {(uint32_t)a->seed, (uint32_t)(a->seed >> 32)};
-  const int count_pa = !(a->flags & 1u);
-  mlbsim_hist* local = (mlbsim_hist*)calloc(1, sizeof(mlbsim_hist));
-  for (uint64_t sim = (uint64_t)lo; sim < (uint64_t)hi; ++sim) {
-    uint32_t ctr[4] = {(uint32_t)sim, (uint32_t)(sim >> 32), 0u, matchup};
-    uint32_t w[4] = {0, 0, 0, 0};
-    int score[2] = {0, 0}, slot[2] = {0, 0};
-    staff_state st[2] = {{0, 1, 0}, {0, 1, 0}};
-    int cap_a[4] = {0, 0, 0, 0}, cap_h[4] = {0, 0, 0, 0};
-    uint32_t used_mask[2] = {0, 0};
-    int inning = 1;
-    for (;;) {
-      for (int side = 0; side < 2; ++side) {
-        if (side == 1 && inning == 9 && score[1] > score[0]) break;
-        int nbp = (int)T->bullpen_len[side];
-        if ((st[side].pc > 90 || st[side].tto >= 3) && nbp > 0) {
-          int idx = (int)(((uint64_t)w[2] * (uint64_t)nbp) >> 32); /* w2 of the game's latest PA */
-          st[side].pit = 1 + idx; st[side].pc = 0; st[side].tto = 1;
-          used_mask[side] |= 1u << idx;
-          local->rel_picks[side][idx]++;
+/* one game of the native law; adds to `local` (if not NULL) and fills `rg` (if not NULL) */
+static void native_game(const mlbsim_table* T, uint32_t matchup, const uint32_t key[2], uint64_t sim, int count_pa,
+                        mlbsim_hist* local, mlbsim_replay_game* rg) {
+  uint32_t ctr[4] = {(uint32_t)sim, (uint32_t)(sim >> 32), 0u, matchup};
+  uint32_t w[4] = {0, 0, 0, 0};
+  int score[2] = {0, 0}, slot[2] = {0, 0};
+  staff_state st[2] = {{0, 1, 0}, {0, 1, 0}};
+  int cap_a[4] = {0, 0, 0, 0}, cap_h[4] = {0, 0, 0, 0};
+  uint32_t used_mask[2] = {0, 0};
+  int n_used[2] = {0, 0};
+  int inning = 1;
+  if (rg) memset(rg, 0, sizeof(*rg));
+  for (;;) {
+    int rr[2] = {0, 0};
+    for (int side = 0; side < 2; ++side) {
+      if (side == 1 && inning == 9 && score[1] > score[0]) break;
+      int nbp = (int)T->bullpen_len[side];
+      if ((st[side].pc > 90 || st[side].tto >= 3) && nbp > 0) {
+        int idx = (int)(((uint64_t)w[2] * (uint64_t)nbp) >> 32); /* w2 of the game's latest PA */
+        st[side].pit = 1 + idx; st[side].pc = 0; st[side].tto = 1;
+        used_mask[side] |= 1u << idx;
+        if (local) local->rel_picks[side][idx]++;
+        if (rg) {
+          uint8_t* used = side == 0 ? rg->used_home : rg->used_away;
+          if (n_used[side] < MLBSIM_REPLAY_MAX_USED) used[n_used[side]] = (uint8_t)idx;
+          else rg->status |= MLBSIM_ST_USED_OVERFLOW;
         }
-        int L = (int)T->lineup_len[side];
-        int outs = 0, runs = 0, n = 0, bases = 0, reached = 0, sl = slot[side];
-        while (outs < 3 && n < 30) {
-          oracle_philox4x32_10(ctr, key, w);
-          ctr[2]++;
-          if (sl == 0 && n > 0) st[side].tto += 1;
-          int tier = (st[side].tto >= 4 ? 4 : st[side].tto) - 1;
-          const uint32_t* row = T->thr[side][st[side].pit][tier][sl];
-          uint32_t e = (st[side].pit == 0 && st[side].pc > 75) ? (uint32_t)(st[side].pc - 75) : 0u;
-          const int32_t* sp = T->slope[side][tier][sl];
-          uint32_t u = w[0] >> 1;
-          int o = 0;
-          for (int j = 0; j < 6; ++j) o += (u >= row[j] + e * (uint32_t)sp[j]);
-          uint32_t tA = (o == MLBSIM_1B) ? (outs == 2 ? T_046 : T_040) : (o == MLBSIM_2B) ? T_040 : T_DP;
-          int dA = w[1] < tA, dB = w[2] < T_080;
-          uint32_t t = native_transition(o, dA, dB, outs, bases);
-          int r = (t >> 3) & 7;
-          bases = t & 7; outs += t >> 6; runs += r;
-          if (r > 0 || bases != 0) reached = 1;
-          if (count_pa) local->pa[side][o]++;
-          st[side].pc += 1; n += 1; sl = (sl + 1 == L) ? 0 : sl + 1;
-        }
-        if (reached) runs += (runs == 0) ? (w[3] < T_END_BOTH) + (w[3] < T_END_ANY) : (w[3] < T_END_GHOST);
-        slot[side] = sl;
-        score[side] += runs;
+        n_used[side]++;
       }
-      if (inning <= 7 && (inning & 1)) { cap_a[inning >> 1] = score[0]; cap_h[inning >> 1] = score[1]; }
-      if (inning >= 9 && score[0] != score[1]) break;
-      inning += 1;
+      int L = (int)T->lineup_len[side];
+      int outs = 0, runs = 0, n = 0, bases = 0, reached = 0, sl = slot[side];
+      while (outs < 3 && n < 30) {
+        oracle_philox4x32_10(ctr, key, w);
+        ctr[2]++;
+        if (sl == 0 && n > 0) st[side].tto += 1;
+        int tier = (st[side].tto >= 4 ? 4 : st[side].tto) - 1;
+        const uint32_t* row = T->thr[side][st[side].pit][tier][sl];
+        uint32_t e = (st[side].pit == 0 && st[side].pc > 75) ? (uint32_t)(st[side].pc - 75) : 0u;
+        const int32_t* sp = T->slope[side][tier][sl];
+        uint32_t u = w[0] >> 1;
+        int o = 0;
+        for (int j = 0; j < 6; ++j) o += (u >= row[j] + e * (uint32_t)sp[j]);
+        uint32_t tA = (o == MLBSIM_1B) ? (outs == 2 ? T_046 : T_040) : (o == MLBSIM_2B) ? T_040 : T_DP;
+        int dA = w[1] < tA, dB = w[2] < T_080;
+        uint32_t t = native_transition(o, dA, dB, outs, bases);
+        int r = (t >> 3) & 7;
+        bases = t & 7; outs += t >> 6; runs += r;
+        if (r > 0 || bases != 0) reached = 1;
+        if (count_pa && local) local->pa[side][o]++;
+        if (rg) rg->pa[side][o]++;
+        st[side].pc += 1; n += 1; sl = (sl + 1 == L) ? 0 : sl + 1;
+      }
+      if (reached) runs += (runs == 0) ? (w[3] < T_END_BOTH) + (w[3] < T_END_ANY) : (w[3] < T_END_GHOST);
+      slot[side] = sl;
+      score[side] += runs;
+      rr[side] = runs;
     }
+    if (rg) {
+      if (inning <= MLBSIM_REPLAY_MAX_INNINGS) {
+        rg->away_runs[inning - 1] = (uint8_t)(rr[0] > 255 ? 255 : rr[0]);
+        rg->home_runs[inning - 1] = (uint8_t)(rr[1] > 255 ? 255 : rr[1]);
+      } else rg->status |= MLBSIM_ST_INNINGS_OVERFLOW;
+    }
+    if (inning <= 7 && (inning & 1)) { cap_a[inning >> 1] = score[0]; cap_h[inning >> 1] = score[1]; }
+    if (inning >= 9 && score[0] != score[1]) break;
+    inning += 1;
+  }
+  if (local) {
     hist_add_game(local, cap_a, cap_h, score[0], score[1], inning);
     for (int s = 0; s < 2; ++s)
       for (int i = 0; i < 8; ++i) if (used_mask[s] >> i & 1) local->rel_games[s][i]++;
   }
-  pthread_mutex_lock(&g_merge_lock);
-  hist_merge(a->hist, local);
-  pthread_mutex_unlock(&g_merge_lock);
-  free(local);
+  if (rg) {
+    rg->home_score = score[1]; rg->away_score = score[0]; rg->n_innings = inning;
+    rg->tape_used = (int32_t)ctr[2]; /* Philox blocks (= PAs) consumed */
+    rg->n_used[0] = n_used[0]; rg->n_used[1] = n_used[1];
+  }
+}
+
+typedef struct {
+  const mlbsim_table* T; uint32_t matchup; uint64_t seed; mlbsim_hist* hist; uint32_t flags;
+  mlbsim_replay_game* games; uint64_t sim_lo;
+} native_args;
+static void native_range(int64_t lo, int64_t hi, void* argp) {
+  native_args* a = (native_args*)argp;
+  const uint32_t key[2] = {(uint32_t)a->seed, (uint32_t)(a->seed >> 32)};
+  const int count_pa = !(a->flags & 1u);
+  mlbsim_hist* local = a->hist ? (mlbsim_hist*)calloc(1, sizeof(mlbsim_hist)) : NULL;
+  for (uint64_t sim = (uint64_t)lo; sim < (uint64_t)hi; ++sim)
+    native_game(a->T, a->matchup, key, sim, count_pa, local, a->games ? &a->games[sim - a->sim_lo] : NULL);
+  if (local) {
+    pthread_mutex_lock(&g_merge_lock);
+    hist_merge(a->hist, local);
+    pthread_mutex_unlock(&g_merge_lock);
+    free(local);
+  }
 }
 /* sim indices must stay below 2^63 (they are split over threads as int64 ranges) */
 int oracle_native(const mlbsim_table* T, uint32_t matchup, uint64_t sim_lo, uint64_t sim_hi, uint64_t seed,
                   mlbsim_hist* hist, uint32_t flags) {
   if (T->magic != MLBSIM_TABLE_MAGIC) return MLBSIM_ERR_TABLE;
-  native_args a = {T, matchup, seed, hist, flags};
+  native_args a = {T, matchup, seed, hist, flags, NULL, sim_lo};
+  parallel_ranges((int64_t)sim_lo, (int64_t)sim_hi, native_range, &a);
+  return 0;
+}
+/* per-sim records of the native law (scores, per-inning runs, relievers, outcome counts) */
+int oracle_native_persim(const mlbsim_table* T, uint32_t matchup, uint64_t sim_lo, uint64_t sim_hi, uint64_t seed,
+                         mlbsim_replay_game* games) {
+  if (T->magic != MLBSIM_TABLE_MAGIC) return MLBSIM_ERR_TABLE;
+  native_args a = {T, matchup, seed, NULL, 0, games, sim_lo};
   parallel_ranges((int64_t)sim_lo, (int64_t)sim_hi, native_range, &a);
   return 0;
 }

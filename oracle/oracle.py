@@ -40,6 +40,8 @@ def lib():
         L.oracle_grammar.restype = ctypes.c_int
         L.oracle_native.argtypes = [vp, u32, u64, u64, u64, vp, u32]
         L.oracle_native.restype = ctypes.c_int
+        L.oracle_native_persim.argtypes = [vp, u32, u64, u64, u64, vp]
+        L.oracle_native_persim.restype = ctypes.c_int
         L.oracle_philox4x32_10.argtypes = [vp, vp, vp]
         L.oracle_philox4x32_10.restype = None
         L.oracle_set_threads.argtypes = [ctypes.c_int]
@@ -122,3 +124,14 @@ def native(table: np.ndarray, matchup: int, sim_lo: int, sim_hi: int, seed: int,
     if rc != 0:
         raise RuntimeError(f"oracle_native failed with code {rc}")
     return hist
+
+
+def native_persim(table: np.ndarray, matchup: int, sim_lo: int, sim_hi: int, seed: int) -> np.ndarray:
+    from mlb_odds_engine_b200 import _abi
+
+    out = np.zeros(sim_hi - sim_lo, dtype=_abi.REPLAY_GAME_DTYPE)
+    t = np.ascontiguousarray(table)
+    rc = lib().oracle_native_persim(_ptr(t), matchup, sim_lo, sim_hi, seed, _ptr(out))
+    if rc != 0:
+        raise RuntimeError(f"oracle_native_persim failed with code {rc}")
+    return out
