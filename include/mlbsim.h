@@ -135,7 +135,8 @@ size_t mlbsim_struct_size(int which);
 int mlbsim_device_info(const mlbsim_ctx* ctx, int* sm_count, int* sm_clock_khz, char* name, size_t name_len);
 
 /* Uses an externally owned stream (e.g. torch's current stream) for all later calls; 0 restores
- * the context's own stream.  `stream` is a cudaStream_t passed as an integer. */
+ * the context's own stream.  `stream` is a cudaStream_t passed as an integer; pass 1
+ * (cudaStreamLegacy) to name the legacy default stream, whose handle is otherwise 0. */
 int mlbsim_set_stream(mlbsim_ctx* ctx, uintptr_t stream);
 int mlbsim_synchronize(mlbsim_ctx* ctx);
 

@@ -50,13 +50,18 @@ class ShardedSimulator:
         torch.cuda.set_device(self.device)
         self.sim = GpuSimulator(self.device)
         self.ctx = self.sim.ctx
-        self.ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+        self._bind_stream()
         self.hist_dev = None
         self.hist_pinned = None
         self.n_matchups = 0
 
     def close(self):
         self.sim.close()
+
+    def _bind_stream(self):
+        # torch's default stream has handle 0, which mlbsim_set_stream reads as "own stream":
+        # name the legacy default stream explicitly (cudaStreamLegacy == 1)
+        self.ctx.set_stream(self.torch.cuda.current_stream().cuda_stream or 1)
 
     def _ensure(self, n_matchups: int):
         torch = self.torch
@@ -80,7 +85,7 @@ class ShardedSimulator:
     # ---- device-resident step: tables already in HBM, result stays in HBM ----
     def run_device(self, n_sims_total: int, seed: int, sim_lo: int = 0, count_pa: bool = True):
         """Zero the device histograms, simulate this rank's shard, all-reduce.  Asynchronous."""
-        self.ctx.set_stream(self.torch.cuda.current_stream().cuda_stream)
+        self._bind_stream()
         lo, hi = shard_range(sim_lo, n_sims_total, self.rank, self.world)
         self.hist_dev.zero_()
         self.ctx.run_native(0, self.n_matchups, lo, hi, seed, self.hist_dev.data_ptr(), 0 if count_pa else 1)

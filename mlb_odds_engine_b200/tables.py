@@ -185,10 +185,20 @@ def _p_k_or_bb(k, bb, use_noise):
     if k <= 0.0:
         # only the walk term is random: E[min(1, 1.01*Y)]
         return 0.0, _expect_clip(None, bb)
-    sd = math.sqrt(k * (1 - k) / (NOISE_WEIGHT + 1)) + 1.01 * math.sqrt(bb * (1 - bb) / (NOISE_WEIGHT + 1))
-    if k + 1.01 * bb + 8.0 * sd < 1.0:
-        return pk, k + 1.01 * bb   # the clip at 1 has probability < 1e-14
+    # E[min(1, X + 1.01 Y)]: for realistic rates the clip term is < 1e-12 and the quadrature
+    # returns k + 1.01*bb to the last bit; for extreme grid points (k = 0.5, bb = 0.3: ~5 %) it matters
     return pk, _expect_clip(k, bb)
+
+
+_GL = None
+
+
+def _gauss_legendre_01():
+    global _GL
+    if _GL is None:
+        nodes, weights = np.polynomial.legendre.leggauss(400)
+        _GL = (0.5 * (nodes + 1.0), 0.5 * weights)
+    return _GL
 
 
 def _expect_clip(k, bb):
@@ -196,20 +206,19 @@ def _expect_clip(k, bb):
     from scipy import special, stats
 
     ay, by = NOISE_WEIGHT * bb, NOISE_WEIGHT * (1 - bb)
-    nodes, weights = np.polynomial.legendre.leggauss(400)
-    y = 0.5 * (nodes + 1.0)
-    wy = 0.5 * weights * stats.beta.pdf(y, ay, by)
+    mean = (0.0 if k is None else k) + 1.01 * bb
+    y, w = _gauss_legendre_01()
+    # the clip needs X > 1 - 1.01*y: only the upper part of Y's range can contribute
+    wy = w * stats.beta.pdf(y, ay, by)
     c = 1.0 - 1.01 * y                      # X must exceed c for the clip to bite
     if k is None:
         excess = np.maximum(-c, 0.0)
-        mean = 1.01 * bb
     else:
         ax, bx = NOISE_WEIGHT * k, NOISE_WEIGHT * (1 - k)
         cc = np.clip(c, 0.0, 1.0)
         # E[(X - c)^+] = k * (1 - I_c(a+1, b)) - c * (1 - I_c(a, b)); for c < 0 it is k - c
         excess = k * (1.0 - special.betainc(ax + 1, bx, cc)) - cc * (1.0 - special.betainc(ax, bx, cc))
         excess = np.where(c < 0.0, k - c, excess)
-        mean = k + 1.01 * bb
     return float(min(max(mean - float(np.sum(wy * excess)), 0.0), 1.0))
 
 

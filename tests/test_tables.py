@@ -1,0 +1,133 @@
+"""CPU: host-side table builders against the reference's documented behaviour."""
+import copy
+
+import numpy as np
+import pytest
+
+import oracle as orc
+from helpers import load_replay
+from mlb_odds_engine_b200 import _abi, synth, tables
+
+
+def test_contact_cdfs_are_numpys_own_doubles():
+    cdf_bip, cdf_hit, cdf_fb = tables.contact_cdfs()
+    assert cdf_bip.tolist() == [0.27999999999999997, 0.6, 0.8999999999999999, 1.0]      # SURVEY §8(a) A6 [probe]
+    assert cdf_hit.tolist() == [0.7618102421595871, 0.9801508535132989, 1.0]
+    assert cdf_fb.tolist() == [0.9207292905271502, 1.0]
+
+
+def test_bip_hit_probability_literals():
+    f = tables.bip_hit_probability
+    assert f("LD", None, None, 50, 50) == 0.55                      # 0.65 * 1.03 clamped to 0.55
+    assert f("POP", 88, 8.0, 50, 50) == 0.05                        # floor
+    assert f("GB", 88, 8.0, 50, 50) == 0.305
+    assert f("GB", 96, 12, 70, 30) == 0.305 * 1.025 * 1.03 * min(1.03 * 1.03, 1.06)
+    assert f("FB", 84, 5.0, 30, 65) == 0.10 * 0.97 * 0.97 * (0.97 * 0.96)
+    with pytest.raises(TypeError):
+        f("GB", "N/A", 12, 50, 50)                                  # un-enriched starter: bip_resolution.py:40
+
+
+def test_reference_error_behaviour():
+    m = synth.make_matchup()
+    bad = copy.deepcopy(m); del bad["home_pitcher"]["k_rate"]
+    with pytest.raises(KeyError):
+        tables.build_table(bad)
+    bad = copy.deepcopy(m); bad["away_pitcher"]["hr_pa"]["hr_pa_projected"] = None
+    with pytest.raises(TypeError):
+        tables.build_table(bad)
+    bad = copy.deepcopy(m); bad["home_bullpen"] = bad["home_bullpen"] + bad["away_bullpen"]
+    with pytest.raises(ValueError):
+        tables.build_table(bad)
+
+
+def test_inert_inputs_do_not_change_the_table():
+    """env multipliers under the driver's key names, ISO/AVG/wOBA, Stuff+ ... are unread by the hot path (A7)."""
+    m = synth.make_matchup()
+    t0 = tables.build_table(m)
+    m2 = copy.deepcopy(m)
+    m2["env"].update({"park_hr_mult": 1.3, "weather_hr_mult": 1.2, "adi_mult": 0.9, "single_mult": 1.1})
+    m2["env"]["umpire"] = {"K": 1.2, "BB": 0.8}
+    for b in m2["home_lineup"]:
+        b.update({"iso": 0.3, "avg": 0.33, "woba": 0.44})
+    m2["home_pitcher"].update({"stuff_plus": 140, "hr_fb_rate": 0.3, "iso_allowed": 0.3})
+    assert tables.build_table(m2).tobytes() == t0.tobytes()
+    m3 = copy.deepcopy(m)
+    m3["env"]["weather_hr"] = 1.2          # the key the hot path does read (half_inning_simulator.py:186)
+    assert tables.build_table(m3).tobytes() != t0.tobytes()
+
+
+def test_outcome_law_matches_survey_probe():
+    """A9: probabilities sum to 1, thresholds are monotone, tiers shift K down / BB up."""
+    m = tables.as_matchup(synth.make_matchup())
+    for side in range(2):
+        for tier in range(4):
+            p = tables.outcome_probabilities(m, side, 0, tier, 3)
+            assert abs(p.sum() - 1.0) < 1e-12 and (p >= 0).all()
+    p1 = tables.outcome_probabilities(m, 0, 0, 0, 0)
+    p4 = tables.outcome_probabilities(m, 0, 0, 3, 0)
+    assert p4[0] < p1[0] and p4[1] > p1[1]
+    k = (m.bat_k[0, 0] + m.pit_k[0, 0]) / 2
+    bb = (m.bat_bb[0, 0] + m.pit_bb[0, 0]) / 2
+    assert abs(p1[0] - k) < 1e-15 and abs(p1[1] - 1.01 * bb) < 1e-9   # clip term of the Beta noise ~4e-11
+    t = tables.build_table(m)
+    thr = t["thr"][:, :, :, :, :6].astype(np.int64)
+    assert (np.diff(thr, axis=-1) >= 0).all() and thr.max() <= 2**31
+
+
+def test_noise_clip_quadrature_against_sampling():
+    """Appendix A caveat: E[min(1, X + 1.01 Y)] must be integrated when k + 1.01 bb is near 1."""
+    rng = np.random.default_rng(0)
+    k, bb = 0.5, 0.3
+    x = rng.beta(30 * k, 30 * (1 - k), 2_000_000)
+    y = rng.beta(30 * bb, 30 * (1 - bb), 2_000_000)
+    mc = np.minimum(1.0, x + 1.01 * y).mean()
+    pk, pkbb = tables._p_k_or_bb(k, bb, True)
+    assert pk == k and abs(pkbb - mc) < 3e-4 and pkbb < k + 1.01 * bb - 0.002
+    assert abs(tables._p_k_or_bb(0.22, 0.08, True)[1] - (0.22 + 1.01 * 0.08)) < 1e-9
+    assert tables._p_k_or_bb(0.9, 0.3, False) == (0.9, 1.0)
+    assert tables._p_k_or_bb(1.2, 0.1, True) == (1.0, 1.0)
+    assert tables._p_k_or_bb(0.3, -0.1, True) == (0.3, 0.3)
+
+
+def test_fatigue_slope_reproduces_exact_law():
+    """thr + (pc - 75) * slope tracks the exactly recomputed CDF to < 2^-24 over a starter's range."""
+    m = synth.make_matchup(bullpens=False)
+    mm = tables.as_matchup(m)
+    t = tables.build_table(m)
+    assert t["flags"] & _abi.FLAG_FATIGUE
+    for pc in (76, 90, 120, 175):
+        for tier in (0, 3):
+            exact = tables.outcome_cdf(mm, 1, 0, tier, 4, pitch_count=pc)
+            approx = (t["thr"][1, 0, tier, 4, :6].astype(np.int64) + (pc - 75) * t["slope"][1, tier, 4, :6].astype(np.int64)) / 2.0**31
+            assert np.abs(exact - approx).max() < 2.0**-24
+    t2 = tables.build_table(synth.make_matchup())
+    assert not (t2["flags"] & _abi.FLAG_FATIGUE) and not t2["slope"].any()
+
+
+def test_oracle_twin_pa_mix_matches_table_law():
+    """The integer twin's outcome frequencies converge to the analytic per-PA law (neutral game)."""
+    m = synth.neutral_calibration_matchup()
+    mm = tables.as_matchup(m)
+    t = tables.build_table(m)
+    n = 200_000
+    h = orc.native(t, 0, 0, n, 3)
+    per_game = orc.native_persim(t, 0, 0, 2000, 3)
+    assert int(h["n_games"]) == n
+    # first-time-through, fresh starter: every batter identical => tier-1 law for the first 9 PAs
+    p = tables.outcome_probabilities(mm, 0, 0, 0, 0)
+    assert abs(p[0] - 0.225) < 1e-12
+    tot = h["pa"][:, :7].sum()
+    mix = h["pa"][:, :7].sum(axis=0) / tot
+    published = np.array([22.23, 8.36, 19.58, 4.77, 0.40, 2.52, 42.14]) / 100   # logs/calibration_outcomes.csv
+    assert np.abs(mix - published).max() < 0.002
+    assert abs(tot / n - 81.38) < 0.2
+    assert (per_game["pa"][:, :, :7].sum(axis=(1, 2)) == per_game["tape_used"]).all()
+
+
+def test_params_roundtrip_fields():
+    g = load_replay("odd_onesided")
+    p = tables.build_params(g["matchup"], use_noise=True)
+    assert p["k_mod"] == 1.04 and p["bb_mod"] == 0.95
+    assert p["bullpen_len"].tolist() == [3, 0] and p["lineup_len"].tolist() == [9, 9]
+    hr = g["matchup"]["home_pitcher"]["hr_pa"]["hr_pa_projected"] * 1.12
+    assert p["pit_hr"][0, 0] == hr
