@@ -128,6 +128,6 @@ def test_params_roundtrip_fields():
     g = load_replay("odd_onesided")
     p = tables.build_params(g["matchup"], use_noise=True)
     assert p["k_mod"] == 1.04 and p["bb_mod"] == 0.95
-    assert p["bullpen_len"].tolist() == [3, 0] and p["lineup_len"].tolist() == [9, 9]
+    assert p["bullpen_len"].tolist() == [5, 0] and p["lineup_len"].tolist() == [9, 9]
     hr = g["matchup"]["home_pitcher"]["hr_pa"]["hr_pa_projected"] * 1.12
     assert p["pit_hr"][0, 0] == hr
