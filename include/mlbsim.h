@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define MLBSIM_ABI_VERSION 1
+#define MLBSIM_ABI_VERSION 2
 
 /* ---- model dimensions ------------------------------------------------------------------- */
 #define MLBSIM_MAX_LINEUP 9   /* len(lineup); 9 in every caller (half_inning_simulator.py:175) */
@@ -74,11 +74,14 @@ typedef struct mlbsim_replay_game {
   uint16_t pa[2][8]; /* [side][outcome] per-game PA_RECAP_LOG deltas; [7] unused */
 } mlbsim_replay_game;
 
-/* ---- native mode: per-matchup integer threshold table --------------------------------------
- * One PA consumes one Philox4x32-10 block (w0..w3).  u = w0 >> 1 (31 bits); the outcome is the
- * number of thresholds thr[..][j] (j = 0..5, cumulative over K BB 1B 2B 3B HR) with u >= thr,
- * so OUT = 6.  thr = round(cdf * 2^31) in [0, 2^31].  For pitch counts above 75
- * (fatigue_modeling.py:38) starters use thr + (pitch_count - 75) * slope.                      */
+/* ---- native mode: per-matchup integer sampling table -----------------------------------------
+ * One PA consumes one Philox4x32-10 block (w0..w3).  The outcome over K BB 1B 2B 3B HR OUT is
+ * drawn from w0 with Walker's alias method on 8 columns (column 7 has no mass of its own):
+ *     col = w0 >> 29;  e = alias[side][pit][tier][slot][col];
+ *     outcome = ((w0 & 0x1FFFFFFF) < (e >> 3)) ? col : (e & 7)
+ * i.e. one table word per PA.  Starters past 75 pitches (fatigue_modeling.py:38; only possible
+ * for a staff without a bullpen, MLBSIM_FLAG_FATIGUE) use cumulative 31-bit thresholds instead:
+ *     u = w0 >> 1;  outcome = #{ j < 6 : u >= fthr[..][j] + (pitch_count - 75) * fslope[..][j] }   */
 #define MLBSIM_TABLE_MAGIC 0x4d4c4254u /* "MLBT" */
 #define MLBSIM_ROW_WORDS 8
 #define MLBSIM_FLAG_FATIGUE 1u /* some staff has no bullpen: pitch_count can exceed 75 */
@@ -89,8 +92,9 @@ typedef struct mlbsim_table {
   uint32_t lineup_len[2];
   uint32_t bullpen_len[2];
   uint32_t reserved[2];
-  uint32_t thr[2][MLBSIM_MAX_PITCHERS][MLBSIM_N_TIERS][MLBSIM_MAX_LINEUP][MLBSIM_ROW_WORDS];
-  int32_t slope[2][MLBSIM_N_TIERS][MLBSIM_MAX_LINEUP][MLBSIM_ROW_WORDS]; /* starters only */
+  uint32_t alias[2][MLBSIM_MAX_PITCHERS][MLBSIM_N_TIERS][MLBSIM_MAX_LINEUP][MLBSIM_ROW_WORDS];
+  uint32_t fthr[2][MLBSIM_N_TIERS][MLBSIM_MAX_LINEUP][MLBSIM_ROW_WORDS];  /* starters, at pitch_count 75 */
+  int32_t fslope[2][MLBSIM_N_TIERS][MLBSIM_MAX_LINEUP][MLBSIM_ROW_WORDS]; /* per pitch above 75 */
 } mlbsim_table;
 
 /* ---- native mode: per-matchup output, all uint64 counters ---------------------------------- */

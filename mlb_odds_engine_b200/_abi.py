@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import numpy as np
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 MAX_LINEUP = 9
 MAX_BULLPEN = 6
@@ -78,8 +78,9 @@ TABLE_DTYPE = np.dtype(
         ("lineup_len", "<u4", (2,)),
         ("bullpen_len", "<u4", (2,)),
         ("reserved", "<u4", (2,)),
-        ("thr", "<u4", (2, MAX_PITCHERS, N_TIERS, MAX_LINEUP, ROW_WORDS)),
-        ("slope", "<i4", (2, N_TIERS, MAX_LINEUP, ROW_WORDS)),
+        ("alias", "<u4", (2, MAX_PITCHERS, N_TIERS, MAX_LINEUP, ROW_WORDS)),
+        ("fthr", "<u4", (2, N_TIERS, MAX_LINEUP, ROW_WORDS)),
+        ("fslope", "<i4", (2, N_TIERS, MAX_LINEUP, ROW_WORDS)),
     ],
     align=True,
 )

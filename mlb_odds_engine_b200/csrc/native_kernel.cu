@@ -13,9 +13,9 @@
 //     chunk (warp-ballot prefix, no atomics); warps pull chunks of the matchup's sim range
 //     from a global counter.  Sim i draws Philox4x32-10 blocks with counter (i_lo, i_hi, pa_seq,
 //     matchup) and key = seed, so which lane / block / GPU runs it is irrelevant to its result;
-//   * the per-matchup threshold table (16 KB), the transition LUT (2.6 KB) and the five joint
-//     (away, home) histograms (20 KB of u32 bins) live in shared memory; histograms are flushed
-//     to the uint64 device totals once per (block, matchup);
+//   * the per-matchup alias table (16 KB, one word read per PA), the transition LUT (2.6 KB) and
+//     the five joint (away, home) histograms (20 KB of u32 bins) live in shared memory; histograms
+//     are flushed to the uint64 device totals once per (block, matchup);
 //   * no tensor cores: there is no dense contraction in this path.
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -40,15 +40,17 @@ constexpr int FATIGUE_START = 75;            // fatigue_modeling.py:38
 
 // ---- shared-memory layout ---------------------------------------------------------------------
 constexpr int SB = 32;                                    // smem joint-histogram bins per team
-constexpr int THR_WORDS = 2 * MLBSIM_MAX_PITCHERS * MLBSIM_N_TIERS * MLBSIM_MAX_LINEUP * MLBSIM_ROW_WORDS;  // 4032
-constexpr int SLOPE_WORDS = 2 * MLBSIM_N_TIERS * MLBSIM_MAX_LINEUP * MLBSIM_ROW_WORDS;                      // 576
-constexpr int LUT_WORDS = 7 * 4 * 24;                                                                       // 672
-constexpr int JOINT_WORDS = MLBSIM_N_CAPS * SB * SB;                                                        // 5120
+constexpr int ALIAS_WORDS = 2 * MLBSIM_MAX_PITCHERS * MLBSIM_N_TIERS * MLBSIM_MAX_LINEUP * MLBSIM_ROW_WORDS;  // 4032
+constexpr int FAT_WORDS = 2 * MLBSIM_N_TIERS * MLBSIM_MAX_LINEUP * MLBSIM_ROW_WORDS;                          // 576
+constexpr int LUT_WORDS = 7 * 4 * 24;                                                                         // 672
+constexpr int JOINT_WORDS = MLBSIM_N_CAPS * SB * SB;                                                          // 5120
 
 struct __align__(16) Smem {
-  uint32_t thr[THR_WORDS];
-  int32_t slope[SLOPE_WORDS];
+  uint32_t alias[ALIAS_WORDS];
+  uint32_t fthr[FAT_WORDS];
+  int32_t fslope[FAT_WORDS];
   uint32_t lut[LUT_WORDS];
+  uint32_t tA[16];  // sub-draw A threshold by outcome*2 + (outs == 2)
   uint32_t joint[JOINT_WORDS];
   uint32_t innings[MLBSIM_INN_BINS];
   uint32_t rel_games[16];
@@ -58,18 +60,17 @@ struct __align__(16) Smem {
   uint32_t go;  // block-uniform "this matchup still has work"
 };
 
-// ---- per-side context word --------------------------------------------------------------------
-// slot[3:0] | tier[5:4] | pit[8:6] | pitch_count[19:9] | score[31:20]   (side = batting side)
+// ---- per-side context word (one per batting side; `cur` = side at bat, `oth` = the other) -------
+// slot[3:0] | tier[5:4] | pit[8:6] | pitch_count[31:9]      pitch_count is the top field, so
+// "pitch_count > n" is a plain unsigned compare of the whole word against ((n + 1) << 9).
 constexpr uint32_t CX_SLOT = 0xFu;
 constexpr uint32_t CX_TIER_ONE = 1u << 4;
 constexpr uint32_t CX_TIER_MASK = 3u << 4;
+constexpr uint32_t CX_TIER_GE2 = 2u << 4;
 constexpr int CX_T_SHIFT = 4;  // (ctx >> 4) & 31 = pit*4 + tier
 constexpr int CX_PIT_SHIFT = 6;
 constexpr int CX_PC_SHIFT = 9;
-constexpr uint32_t CX_PC_ONE = 1u << 9;
-constexpr uint32_t CX_PC_MASK = 0x7FFu;
-constexpr int CX_SCORE_SHIFT = 20;
-constexpr uint32_t CX_STAFF_MASK = 0x000FFFF0u;  // tier | pit | pitch_count
+constexpr uint32_t CX_NEXT_PA = (1u << CX_PC_SHIFT) + 1u;  // one more pitch, next batter
 
 // ---- half-inning state word -------------------------------------------------------------------
 // ob[4:0] = outs*8 + bases | n_pa[13:8] | runs[21:16] | reached_count[29:24]
@@ -103,10 +104,49 @@ __device__ uint32_t transition_entry(int o, int dA, int dB, int outs, int bases)
   return (uint32_t)(no * 8 + nb) | ((uint32_t)r << 16) | ((uint32_t)reached << 24);
 }
 
+// threshold of sub-draw A: double play (K/OUT), runner on 2B scores on a single (0.46 with two
+// outs: 0.4 + 0.6*0.1), runner on 1B scores on a double
+__device__ uint32_t subdraw_a_threshold(int o, int two_outs) {
+  if (o == MLBSIM_1B) return two_outs ? T_046 : T_040;
+  if (o == MLBSIM_2B) return T_040;
+  return T_DP;
+}
+
 __device__ __forceinline__ uint32_t lanemask_lt() {
   uint32_t m;
   asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
   return m;
+}
+
+// joint-histogram commit: shared u32 bin when both scores fit the 32x32 window, else the global
+// u64 bin directly (a team scoring >= 32 runs: ~never, but exact)
+__device__ __forceinline__ void commit_joint(uint32_t* sj, unsigned long long* H, uint32_t c, uint32_t a, uint32_t h) {
+  if ((a | h) < (uint32_t)SB) {
+    atomicAdd(&sj[c * (SB * SB) + a * SB + h], 1u);
+  } else {
+    const uint32_t ac = a < MLBSIM_HIST_BINS - 1 ? a : MLBSIM_HIST_BINS - 1;
+    const uint32_t hc = h < MLBSIM_HIST_BINS - 1 ? h : MLBSIM_HIST_BINS - 1;
+    atomicAdd(&H[((size_t)c * MLBSIM_HIST_BINS + ac) * MLBSIM_HIST_BINS + hc], 1ull);
+  }
+}
+
+// warp-wide flush of the packed 8-bit PA counters (pc* = side at bat, po* = other side)
+__device__ __forceinline__ void flush_pa(unsigned long long* Hpa, uint32_t side, uint32_t& pc_lo, uint32_t& pc_hi,
+                                         uint32_t& po_lo, uint32_t& po_hi, int lane) {
+  const uint32_t s0_lo = side ? po_lo : pc_lo, s0_hi = side ? po_hi : pc_hi;
+  const uint32_t s1_lo = side ? pc_lo : po_lo, s1_hi = side ? pc_hi : po_hi;
+#pragma unroll
+  for (int o = 0; o < MLBSIM_N_OUTCOMES; ++o) {
+    const uint32_t f0 = ((o < 4 ? s0_lo : s0_hi) >> (8 * (o & 3))) & 255u;
+    const uint32_t f1 = ((o < 4 ? s1_lo : s1_hi) >> (8 * (o & 3))) & 255u;
+    const uint32_t v0 = __reduce_add_sync(0xffffffffu, f0);
+    const uint32_t v1 = __reduce_add_sync(0xffffffffu, f1);
+    if (lane == 0) {
+      if (v0) atomicAdd(&Hpa[o], (unsigned long long)v0);
+      if (v1) atomicAdd(&Hpa[8 + o], (unsigned long long)v1);
+    }
+  }
+  pc_lo = pc_hi = po_lo = po_hi = 0;
 }
 
 }  // namespace
@@ -120,11 +160,12 @@ mlbsim_native_kernel(const NativeArgs args) {
   const int lane = tid & 31;
   const uint32_t n_sims = args.n_sims;
 
-  // transition LUT: derived once per block from the branchy semantics above
+  // transition LUT + sub-draw thresholds: derived once per block from the branchy semantics above
   for (int i = tid; i < LUT_WORDS; i += blockDim.x) {
     const int ob = i % 24, sel = i / 24;
     S.lut[i] = transition_entry(sel >> 2, (sel >> 1) & 1, sel & 1, ob >> 3, ob & 7);
   }
+  if (tid < 16) S.tA[tid] = subdraw_a_threshold(tid >> 1, tid & 1);
 
   for (uint32_t step = 0; step < args.n_matchups; ++step) {
     const uint32_t m = (blockIdx.x + step) % args.n_matchups;
@@ -136,12 +177,14 @@ mlbsim_native_kernel(const NativeArgs args) {
     // ---- stage this matchup's table; clear block-local accumulators ----
     {
       const mlbsim_table* T = args.tables + m;
-      const uint4* src = reinterpret_cast<const uint4*>(T->thr);
-      uint4* dst = reinterpret_cast<uint4*>(S.thr);
-      for (int i = tid; i < THR_WORDS / 4; i += blockDim.x) dst[i] = __ldg(src + i);
-      const int4* ssrc = reinterpret_cast<const int4*>(T->slope);
-      int4* sdst = reinterpret_cast<int4*>(S.slope);
-      for (int i = tid; i < SLOPE_WORDS / 4; i += blockDim.x) sdst[i] = __ldg(ssrc + i);
+      const uint4* src = reinterpret_cast<const uint4*>(T->alias);
+      uint4* dst = reinterpret_cast<uint4*>(S.alias);
+      for (int i = tid; i < ALIAS_WORDS / 4; i += blockDim.x) dst[i] = __ldg(src + i);
+      if (T->flags & MLBSIM_FLAG_FATIGUE) {
+        const uint4* fsrc = reinterpret_cast<const uint4*>(T->fthr);
+        uint4* fdst = reinterpret_cast<uint4*>(S.fthr);
+        for (int i = tid; i < 2 * FAT_WORDS / 4; i += blockDim.x) fdst[i] = __ldg(fsrc + i);  // fthr then fslope
+      }
       for (int i = tid; i < JOINT_WORDS; i += blockDim.x) S.joint[i] = 0;
       if (tid < MLBSIM_INN_BINS) S.innings[tid] = 0;
       if (tid < 16) { S.rel_games[tid] = 0; S.rel_picks[tid] = 0; }
@@ -173,12 +216,12 @@ mlbsim_native_kernel(const NativeArgs args) {
     // ---- lane state ----
     bool alive = false;
     uint32_t c0 = 0, c1 = 0, seq = 0;
-    uint32_t cA = 0, cB = 0, cur = 0;  // side contexts (A: away bats, B: home bats), cur = live copy
+    uint32_t cur = 0, oth = 0;         // side contexts: cur = side at bat
+    uint32_t sc = 0;                   // away | home << 16
+    uint32_t hidx = 0;                 // half-inning index: side = hidx & 1, inning = (hidx >> 1) + 1
     uint32_t hs = 0;                   // half-inning state
-    uint32_t side = 0, inning = 1;
-    uint32_t capA = 0, capH = 0;       // scores after innings 1,3,5,7 (8 bits each)
     uint32_t used = 0;                 // reliever bitmasks: home staff bits 0-7, away staff 8-15
-    unsigned long long pa0 = 0, pa1 = 0;  // packed 8-bit outcome counters per side
+    uint32_t pc_lo = 0, pc_hi = 0, po_lo = 0, po_hi = 0;  // packed 8-bit outcome counters (at bat / other)
     int flush_in = 255;
 
     for (;;) {
@@ -202,7 +245,7 @@ mlbsim_native_kernel(const NativeArgs args) {
         if (!alive && rank < avail) {
           const unsigned long long sim = (unsigned long long)args.sim_lo + (chunk_next + rank);
           c0 = (uint32_t)sim; c1 = (uint32_t)(sim >> 32); seq = 0;
-          cA = 0; cB = 0; cur = 0; hs = 0; side = 0; inning = 1; capA = 0; capH = 0; used = 0;
+          cur = 0; oth = 0; sc = 0; hidx = 0; hs = 0; used = 0;
           alive = true;
         }
         const uint32_t want = __popc(need);
@@ -216,96 +259,79 @@ mlbsim_native_kernel(const NativeArgs args) {
         philox4x32_10(c0, c1, seq, c3, args.keys, w0, w1, w2, w3);
         ++seq;
 
+        const uint32_t side = hidx & 1u;
         const uint32_t slot = cur & CX_SLOT;
-        // TTO: half_inning_simulator.py:177-178 — bump when the lineup wraps inside or across halves,
-        // but not when a half starts at slot 0 of a fresh walk (n_pa == 0)
+        // TTO: half_inning_simulator.py:177-178 — bump when the lineup wraps, except at the very
+        // first PA of a half that starts at slot 0
         if (slot == 0 && (hs & HS_NPA_MASK) != 0 && (cur & CX_TIER_MASK) != CX_TIER_MASK) cur += CX_TIER_ONE;
         const uint32_t T = (cur >> CX_T_SHIFT) & 31u;  // pit*4 + tier
         const uint32_t row = (side * (MLBSIM_MAX_PITCHERS * MLBSIM_N_TIERS) + T) * MLBSIM_MAX_LINEUP + slot;
-        const uint4 ta = *reinterpret_cast<const uint4*>(&S.thr[row * MLBSIM_ROW_WORDS]);
-        const uint2 tb = *reinterpret_cast<const uint2*>(&S.thr[row * MLBSIM_ROW_WORDS + 4]);
-        uint32_t t0 = ta.x, t1 = ta.y, t2 = ta.z, t3 = ta.w, t4 = tb.x, t5 = tb.y;
+        // Walker alias draw: one shared-memory word per PA
+        const uint32_t col = w0 >> 29;
+        const uint32_t e = S.alias[row * MLBSIM_ROW_WORDS + col];
+        uint32_t o = ((w0 & 0x1FFFFFFFu) < (e >> 3)) ? col : (e & 7u);
         if (fatigue) {
-          const uint32_t pc = (cur >> CX_PC_SHIFT) & CX_PC_MASK;
-          if (T < 4u && pc > (uint32_t)FATIGUE_START) {  // starter (pit == 0) past 75 pitches
-            const uint32_t e = pc - FATIGUE_START;
-            const uint32_t srow = (side * MLBSIM_N_TIERS + T) * MLBSIM_MAX_LINEUP + slot;
-            const int4 sa = *reinterpret_cast<const int4*>(&S.slope[srow * MLBSIM_ROW_WORDS]);
-            const int2 sb = *reinterpret_cast<const int2*>(&S.slope[srow * MLBSIM_ROW_WORDS + 4]);
-            t0 += e * (uint32_t)sa.x; t1 += e * (uint32_t)sa.y; t2 += e * (uint32_t)sa.z;
-            t3 += e * (uint32_t)sa.w; t4 += e * (uint32_t)sb.x; t5 += e * (uint32_t)sb.y;
+          if (T < 4u && cur >= ((uint32_t)(FATIGUE_START + 1) << CX_PC_SHIFT)) {  // starter past 75 pitches
+            const uint32_t ex = (cur >> CX_PC_SHIFT) - FATIGUE_START;
+            const uint32_t srow = ((side * MLBSIM_N_TIERS + T) * MLBSIM_MAX_LINEUP + slot) * MLBSIM_ROW_WORDS;
+            const uint4 ta = *reinterpret_cast<const uint4*>(&S.fthr[srow]);
+            const uint2 tb = *reinterpret_cast<const uint2*>(&S.fthr[srow + 4]);
+            const int4 sa = *reinterpret_cast<const int4*>(&S.fslope[srow]);
+            const int2 sb = *reinterpret_cast<const int2*>(&S.fslope[srow + 4]);
+            const uint32_t u = w0 >> 1;
+            o = (u >= ta.x + ex * (uint32_t)sa.x) + (u >= ta.y + ex * (uint32_t)sa.y) + (u >= ta.z + ex * (uint32_t)sa.z) +
+                (u >= ta.w + ex * (uint32_t)sa.w) + (u >= tb.x + ex * (uint32_t)sb.x) + (u >= tb.y + ex * (uint32_t)sb.y);
           }
         }
-        const uint32_t u = w0 >> 1;
-        const uint32_t o = (u >= t0) + (u >= t1) + (u >= t2) + (u >= t3) + (u >= t4) + (u >= t5);
 
         const uint32_t ob = hs & HS_OB;
-        uint32_t tA = T_DP;
-        if (o == MLBSIM_1B) tA = (ob >= 16u) ? T_046 : T_040;
-        if (o == MLBSIM_2B) tA = T_040;
+        const uint32_t tA = S.tA[o * 2u + (ob >> 4)];
         const uint32_t sel = o * 4u + (w1 < tA ? 2u : 0u) + (w2 < T_080 ? 1u : 0u);
         const uint32_t ent = S.lut[sel * 24u + ob];
         hs = (hs & ~HS_OB) + HS_NPA_ONE + ent;
 
         if (count_pa) {
-          const unsigned long long inc = 1ull << (o * 8u);
-          if (side) pa1 += inc; else pa0 += inc;
+          const uint32_t inc = 1u << ((o & 3u) * 8u);
+          if (o < 4u) pc_lo += inc; else pc_hi += inc;
         }
 
         // next batter, one more pitch (pitch_count counts PAs: half_inning_simulator.py:218-220)
-        cur += CX_PC_ONE + 1u;
-        if ((cur & CX_SLOT) == (side ? L1 : L0)) cur -= (side ? L1 : L0);
+        cur += CX_NEXT_PA;
+        const uint32_t L = side ? L1 : L0;
+        if ((cur & CX_SLOT) == L) cur -= L;
 
         // ---------------- end of half inning ----------------
-        if ((hs & HS_OB) >= 24u || ((hs >> 8) & 63u) >= (uint32_t)MAX_PA_PER_HALF) {
+        if ((hs & HS_OB) >= 24u || (hs & HS_NPA_MASK) >= ((uint32_t)MAX_PA_PER_HALF << 8)) {
           uint32_t runs = (hs >> 16) & 63u;
-          if ((hs >> 24) != 0u) {  // runner_reached
+          if (hs >= (1u << 24)) {  // runner_reached
             runs += (runs == 0u) ? (uint32_t)(w3 < T_END_BOTH) + (uint32_t)(w3 < T_END_ANY) : (uint32_t)(w3 < T_END_GHOST);
           }
-          cur += runs << CX_SCORE_SHIFT;
-          if (side) cB = cur; else cA = cur;
-          const uint32_t sa = cA >> CX_SCORE_SHIFT, sh = cB >> CX_SCORE_SHIFT;
-          bool over = false;
-          if (side == 0) {
-            if (inning == 9 && sh > sa) over = true;  // game_simulator.py:72 — bottom of the 9th skipped
-            else side = 1;
-          } else {
-            if (inning <= 7 && (inning & 1u)) {       // run_distribution_simulator.py:414-424 caps
-              const uint32_t sft = (inning >> 1) * 8u;
-              capA |= (sa < 255u ? sa : 255u) << sft;
-              capH |= (sh < 255u ? sh : 255u) << sft;
-            }
-            if (inning >= 9 && sa != sh) over = true; // game_simulator.py:110-111
-            else { side = 0; ++inning; }
-          }
+          sc += runs << (side * 16u);
+          const uint32_t a = sc & 0xFFFFu, h = sc >> 16;
+          // first 1/3/5/7 innings: committed when the bottom half of that inning ends (hidx = 1, 5, 9, 13)
+          if ((hidx & 3u) == 1u && hidx < 16u) commit_joint(S.joint, H, hidx >> 2, a, h);
+          // game_simulator.py:72 (bottom of the 9th skipped when the home team leads) and :110-111
+          const bool over = side ? (hidx >= 17u && a != h) : (hidx == 16u && h > a);
           if (!over) {
-            cur = side ? cB : cA;
+            ++hidx;
             hs = 0;
+            uint32_t t = cur; cur = oth; oth = t;
+            t = pc_lo; pc_lo = po_lo; po_lo = t;
+            t = pc_hi; pc_hi = po_hi; po_hi = t;
             // should_replace_pitcher (game_simulator.py:8-12) for the staff that now takes the mound
-            const uint32_t nb = side ? nb1 : nb0;
-            const uint32_t pc = (cur >> CX_PC_SHIFT) & CX_PC_MASK;
-            if (nb != 0u && (pc > (uint32_t)PITCH_LIMIT || (cur & CX_TIER_MASK) >= (2u << 4))) {
+            const uint32_t nb = side ? nb0 : nb1;  // `side` is the half that just ended
+            if (nb != 0u && ((cur & CX_TIER_GE2) != 0u || cur >= ((uint32_t)(PITCH_LIMIT + 1) << CX_PC_SHIFT))) {
               const uint32_t idx = __umulhi(w2, nb);  // stationary law of simulate_reliever_chain: uniform, with replacement
-              cur = (cur & ~CX_STAFF_MASK) | ((idx + 1u) << CX_PIT_SHIFT);
-              used |= 1u << (idx + side * 8u);
-              atomicAdd(&S.rel_picks[side * 8u + idx], 1u);
+              cur = (cur & CX_SLOT) | ((idx + 1u) << CX_PIT_SHIFT);
+              const uint32_t bit = idx + (side ? 0u : 8u);
+              used |= 1u << bit;
+              atomicAdd(&S.rel_picks[bit], 1u);
             }
           } else {
             // ---------------- game over: commit ----------------
-            const uint32_t a4[5] = {capA & 255u, (capA >> 8) & 255u, (capA >> 16) & 255u, capA >> 24, sa};
-            const uint32_t h4[5] = {capH & 255u, (capH >> 8) & 255u, (capH >> 16) & 255u, capH >> 24, sh};
-#pragma unroll
-            for (int c = 0; c < MLBSIM_N_CAPS; ++c) {
-              const uint32_t a = a4[c], h = h4[c];
-              if ((a | h) < (uint32_t)SB) {
-                atomicAdd(&S.joint[c * SB * SB + a * SB + h], 1u);
-              } else {
-                const uint32_t ac = a < MLBSIM_HIST_BINS - 1 ? a : MLBSIM_HIST_BINS - 1;
-                const uint32_t hc = h < MLBSIM_HIST_BINS - 1 ? h : MLBSIM_HIST_BINS - 1;
-                atomicAdd(&H[((size_t)c * MLBSIM_HIST_BINS + ac) * MLBSIM_HIST_BINS + hc], 1ull);
-              }
-            }
-            atomicAdd(&S.innings[inning < MLBSIM_INN_BINS - 1 ? inning : MLBSIM_INN_BINS - 1], 1u);
+            commit_joint(S.joint, H, 4u, a, h);
+            const uint32_t inn = (hidx >> 1) + 1u;
+            atomicAdd(&S.innings[inn < MLBSIM_INN_BINS - 1 ? inn : MLBSIM_INN_BINS - 1], 1u);
             uint32_t um = used;
             while (um) {
               const int b = __ffs(um) - 1;
@@ -313,6 +339,11 @@ mlbsim_native_kernel(const NativeArgs args) {
               atomicAdd(&S.rel_games[b], 1u);
             }
             atomicAdd(&S.n_games, 1u);
+            if (side) {  // next game starts with side 0 at bat: keep (pc_*, po_*) = (side 0, side 1)
+              uint32_t t = pc_lo; pc_lo = po_lo; po_lo = t;
+              t = pc_hi; pc_hi = po_hi; po_hi = t;
+            }
+            hidx = 0;
             alive = false;
           }
         }
@@ -321,31 +352,11 @@ mlbsim_native_kernel(const NativeArgs args) {
       // ---------------- periodic flush of the packed PA counters ----------------
       if (count_pa && --flush_in == 0) {
         flush_in = 255;
-#pragma unroll
-        for (int o = 0; o < MLBSIM_N_OUTCOMES; ++o) {
-          const uint32_t v0 = __reduce_add_sync(0xffffffffu, (uint32_t)(pa0 >> (8 * o)) & 255u);
-          const uint32_t v1 = __reduce_add_sync(0xffffffffu, (uint32_t)(pa1 >> (8 * o)) & 255u);
-          if (lane == 0) {
-            if (v0) atomicAdd(&H[H_PA + o], (unsigned long long)v0);
-            if (v1) atomicAdd(&H[H_PA + 8 + o], (unsigned long long)v1);
-          }
-        }
-        pa0 = 0; pa1 = 0;
+        flush_pa(H + H_PA, hidx & 1u, pc_lo, pc_hi, po_lo, po_hi, lane);
       }
     }
 
-    // ---- final PA counter flush for this warp ----
-    if (count_pa) {
-#pragma unroll
-      for (int o = 0; o < MLBSIM_N_OUTCOMES; ++o) {
-        const uint32_t v0 = __reduce_add_sync(0xffffffffu, (uint32_t)(pa0 >> (8 * o)) & 255u);
-        const uint32_t v1 = __reduce_add_sync(0xffffffffu, (uint32_t)(pa1 >> (8 * o)) & 255u);
-        if (lane == 0) {
-          if (v0) atomicAdd(&H[H_PA + o], (unsigned long long)v0);
-          if (v1) atomicAdd(&H[H_PA + 8 + o], (unsigned long long)v1);
-        }
-      }
-    }
+    if (count_pa) flush_pa(H + H_PA, hidx & 1u, pc_lo, pc_hi, po_lo, po_hi, lane);
 
     // ---- block flush: shared u32 bins -> device u64 totals ----
     __syncthreads();
@@ -409,14 +420,21 @@ mlbsim_persim_kernel(const PersimArgs args) {
           ++seq;
           if (sl == 0 && n > 0) tto[side] += 1;
           const int tier = (tto[side] >= 4 ? 4 : tto[side]) - 1;
-          const uint32_t* row = T->thr[side][pit[side]][tier][sl];
-          const int32_t* sp = T->slope[side][tier][sl];
-          const uint32_t e = (pit[side] == 0 && pc[side] > FATIGUE_START) ? (uint32_t)(pc[side] - FATIGUE_START) : 0u;
-          const uint32_t u = w0 >> 1;
-          int o = 0;
+          int o;
+          if ((T->flags & MLBSIM_FLAG_FATIGUE) && pit[side] == 0 && pc[side] > FATIGUE_START) {
+            const uint32_t* row = T->fthr[side][tier][sl];
+            const int32_t* sp = T->fslope[side][tier][sl];
+            const uint32_t e = (uint32_t)(pc[side] - FATIGUE_START);
+            const uint32_t u = w0 >> 1;
+            o = 0;
 #pragma unroll
-          for (int j = 0; j < 6; ++j) o += (u >= row[j] + e * (uint32_t)sp[j]) ? 1 : 0;
-          const uint32_t tA = (o == MLBSIM_1B) ? (outs == 2 ? T_046 : T_040) : (o == MLBSIM_2B) ? T_040 : T_DP;
+            for (int j = 0; j < 6; ++j) o += (u >= row[j] + e * (uint32_t)sp[j]) ? 1 : 0;
+          } else {
+            const uint32_t col = w0 >> 29;
+            const uint32_t e = T->alias[side][pit[side]][tier][sl][col];
+            o = ((w0 & 0x1FFFFFFFu) < (e >> 3)) ? (int)col : (int)(e & 7u);
+          }
+          const uint32_t tA = subdraw_a_threshold(o, outs == 2);
           const uint32_t ent = transition_entry(o, w1 < tA, w2 < T_080, outs, bases);
           const int r = (ent >> 16) & 7;
           outs = (ent & 31u) >> 3; bases = ent & 7u; runs += r;

@@ -7,11 +7,11 @@ products per matchup:
   reference computes per PA from dict values is either copied verbatim or precomputed here with
   the same float64 operation order, so the device compares the same doubles
   (core/bip_resolution.py:20-57, core/pa_simulator.py:46,54,68-79).
-* `build_table`   -> `mlbsim_table`   31-bit integer outcome thresholds for NATIVE mode: the
-  per-PA law of core/pa_simulator.py:91-143 with the Beta(30p, 30(1-p)) noise of :23-32
-  integrated out (it is redrawn independently every PA and only the outcome is consumed), the
-  TTO tiers of core/fatigue_modeling.py:25-35 tabulated and the pitch-count ramp of :38-43 kept
-  as an integer slope per pitch above 75.
+* `build_table`   -> `mlbsim_table`   integer sampling tables for NATIVE mode: the per-PA law of
+  core/pa_simulator.py:91-143 with the Beta(30p, 30(1-p)) noise of :23-32 integrated out (it is
+  redrawn independently every PA and only the outcome is consumed), one Walker alias row per
+  (side, pitcher, TTO tier of core/fatigue_modeling.py:25-35, batter), and for starters without
+  a bullpen 31-bit cumulative thresholds with an integer slope per pitch above 75 (:38-43).
 
 Only keys the reference's hot path reads are used; everything else in the
 dicts (iso, avg, woba, stuff_plus, park multipliers, ...) is inert there and therefore here.
@@ -260,6 +260,55 @@ def _quantise(cdf):
     return np.clip(q, 0, 2147483648).astype(np.uint64)
 
 
+ALIAS_COLS = 8
+ALIAS_FRAC_BITS = 29
+
+
+def alias_row(p) -> np.ndarray:
+    """Walker/Vose alias table for the 7 outcome probabilities `p` on 8 columns (column 7 carries
+    no mass of its own).  Entry = cut << 3 | alias with cut in [0, 2^29): a draw w0 picks column
+    w0 >> 29 and keeps the column's own outcome iff (w0 & (2^29 - 1)) < cut.  Deterministic."""
+    q = np.zeros(ALIAS_COLS)
+    q[:7] = np.asarray(p, dtype=np.float64) * ALIAS_COLS / float(np.sum(p))
+    cut = np.ones(ALIAS_COLS)
+    alias = np.arange(ALIAS_COLS)
+    small = [i for i in range(ALIAS_COLS) if q[i] < 1.0]
+    large = [i for i in range(ALIAS_COLS) if q[i] >= 1.0]
+    while small and large:
+        s = small.pop()
+        g = large.pop()
+        cut[s] = q[s]
+        alias[s] = g
+        q[g] = q[g] - (1.0 - q[s])
+        (small if q[g] < 1.0 else large).append(g)
+    for i in small + large:      # leftovers are full columns up to rounding
+        cut[i] = 1.0
+        alias[i] = i if i < 7 else int(np.argmax(p))
+    one = 1 << ALIAS_FRAC_BITS
+    out = np.zeros(ALIAS_COLS, dtype=np.uint32)
+    for i in range(ALIAS_COLS):
+        c = int(math.floor(cut[i] * one + 0.5))
+        a = int(alias[i])
+        if c >= one:             # full column: encode as "always alias" with alias = own outcome
+            c, a = 0, (i if i < 7 else a)
+        if i == 7:
+            c = 0
+        c = max(c, 0)
+        out[i] = (c << 3) | a
+    return out
+
+
+def alias_probabilities(row) -> np.ndarray:
+    """Exact outcome probabilities an alias row encodes (for tests)."""
+    one = float(1 << ALIAS_FRAC_BITS)
+    p = np.zeros(8)
+    for col in range(ALIAS_COLS):
+        c, a = int(row[col]) >> 3, int(row[col]) & 7
+        p[col] += c / one / ALIAS_COLS
+        p[a] += (1.0 - c / one) / ALIAS_COLS
+    return p[:7]
+
+
 def build_table(m, use_noise=None) -> np.ndarray:
     m = as_matchup(m) if use_noise is None else as_matchup(m, use_noise)
     use_noise = m.use_noise if use_noise is None else use_noise
@@ -268,26 +317,28 @@ def build_table(m, use_noise=None) -> np.ndarray:
     t["lineup_len"] = m.lineup_len
     t["bullpen_len"] = m.bullpen_len
     flags = 0
-    thr = np.zeros(_abi.TABLE_DTYPE["thr"].shape, dtype=np.uint32)
-    thr[...] = 2147483648  # unused rows: everything is K (never reached)
-    slope = np.zeros(_abi.TABLE_DTYPE["slope"].shape, dtype=np.int32)
+    alias = np.zeros(_abi.TABLE_DTYPE["alias"].shape, dtype=np.uint32)   # unused rows: always K (never reached)
+    fthr = np.zeros(_abi.TABLE_DTYPE["fthr"].shape, dtype=np.uint32)
+    fthr[...] = 2147483648
+    fslope = np.zeros(_abi.TABLE_DTYPE["fslope"].shape, dtype=np.int32)
     for s in range(2):
         for p in range(m.bullpen_len[s] + 1):
             for tier in range(_abi.N_TIERS):
                 for b in range(m.lineup_len[s]):
-                    q0 = _quantise(outcome_cdf(m, s, p, tier, b, 0, use_noise))
-                    thr[s, p, tier, b, :6] = q0
-                    thr[s, p, tier, b, 6:] = 2147483648
+                    c0 = outcome_cdf(m, s, p, tier, b, 0, use_noise)
+                    alias[s, p, tier, b] = alias_row(np.diff(np.concatenate([[0.0], c0, [1.0]])))
                     if p == 0 and m.bullpen_len[s] == 0:
                         # a starter without a bullpen is never replaced: pitch_count passes 75
-                        c1 = outcome_cdf(m, s, p, tier, b, FATIGUE_START + SLOPE_SPAN, use_noise)
-                        q1 = _quantise(c1)
-                        slope[s, tier, b, :6] = np.round((q1.astype(np.int64) - q0.astype(np.int64)) / SLOPE_SPAN)
+                        q0 = _quantise(c0)
+                        q1 = _quantise(outcome_cdf(m, s, p, tier, b, FATIGUE_START + SLOPE_SPAN, use_noise))
+                        fthr[s, tier, b, :6] = q0
+                        fslope[s, tier, b, :6] = np.round((q1.astype(np.int64) - q0.astype(np.int64)) / SLOPE_SPAN)
         if m.bullpen_len[s] == 0:
             flags |= _abi.FLAG_FATIGUE
     t["flags"] = flags
-    t["thr"] = thr
-    t["slope"] = slope
+    t["alias"] = alias
+    t["fthr"] = fthr
+    t["fslope"] = fslope
     return t
 
 

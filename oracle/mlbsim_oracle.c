@@ -507,12 +507,21 @@ static void native_game(const mlbsim_table* T, uint32_t matchup, const uint32_t 
         ctr[2]++;
         if (sl == 0 && n > 0) st[side].tto += 1;
         int tier = (st[side].tto >= 4 ? 4 : st[side].tto) - 1;
-        const uint32_t* row = T->thr[side][st[side].pit][tier][sl];
-        uint32_t e = (st[side].pit == 0 && st[side].pc > 75) ? (uint32_t)(st[side].pc - 75) : 0u;
-        const int32_t* sp = T->slope[side][tier][sl];
-        uint32_t u = w[0] >> 1;
-        int o = 0;
-        for (int j = 0; j < 6; ++j) o += (u >= row[j] + e * (uint32_t)sp[j]);
+        int o;
+        if ((T->flags & MLBSIM_FLAG_FATIGUE) && st[side].pit == 0 && st[side].pc > 75) {
+          /* starter past 75 pitches: cumulative thresholds + per-pitch slope */
+          const uint32_t* row = T->fthr[side][tier][sl];
+          const int32_t* sp = T->fslope[side][tier][sl];
+          uint32_t e = (uint32_t)(st[side].pc - 75);
+          uint32_t u = w[0] >> 1;
+          o = 0;
+          for (int j = 0; j < 6; ++j) o += (u >= row[j] + e * (uint32_t)sp[j]);
+        } else {
+          /* Walker alias draw: one table word per PA */
+          uint32_t col = w[0] >> 29;
+          uint32_t e = T->alias[side][st[side].pit][tier][sl][col];
+          o = ((w[0] & 0x1FFFFFFFu) < (e >> 3)) ? (int)col : (int)(e & 7u);
+        }
         uint32_t tA = (o == MLBSIM_1B) ? (outs == 2 ? T_046 : T_040) : (o == MLBSIM_2B) ? T_040 : T_DP;
         int dA = w[1] < tA, dB = w[2] < T_080;
         uint32_t t = native_transition(o, dA, dB, outs, bases);

@@ -70,8 +70,21 @@ def test_outcome_law_matches_survey_probe():
     bb = (m.bat_bb[0, 0] + m.pit_bb[0, 0]) / 2
     assert abs(p1[0] - k) < 1e-15 and abs(p1[1] - 1.01 * bb) < 1e-9   # clip term of the Beta noise ~4e-11
     t = tables.build_table(m)
-    thr = t["thr"][:, :, :, :, :6].astype(np.int64)
-    assert (np.diff(thr, axis=-1) >= 0).all() and thr.max() <= 2**31
+    # every alias row encodes its target law to within the 2^-32 quantisation of the cuts
+    for side, pit, tier, slot in ((0, 0, 0, 0), (1, 3, 2, 8), (0, 6, 3, 4), (1, 0, 1, 5)):
+        want = tables.outcome_probabilities(m, side, pit, tier, slot)
+        got = tables.alias_probabilities(t["alias"][side, pit, tier, slot])
+        assert np.abs(got - want).max() < 2.0**-31
+        assert (t["alias"][side, pit, tier, slot] & 7).max() <= 6
+
+
+def test_alias_rows_degenerate_and_uniform():
+    for p in ([1, 0, 0, 0, 0, 0, 0], [0, 0, 0, 0, 0, 1, 0], [0, 1, 0, 0, 0, 0, 0]):
+        row = tables.alias_row(p)
+        assert tables.alias_probabilities(row).tolist() == [float(x) for x in p]   # exactly, no 2^-32 leak
+    row = tables.alias_row([1 / 7] * 7)
+    assert np.abs(tables.alias_probabilities(row) - 1 / 7).max() < 2.0**-31
+    assert (row >> 3).max() < 2**29 and (row[7] >> 3) == 0
 
 
 def test_noise_clip_quadrature_against_sampling():
@@ -98,10 +111,10 @@ def test_fatigue_slope_reproduces_exact_law():
     for pc in (76, 90, 120, 175):
         for tier in (0, 3):
             exact = tables.outcome_cdf(mm, 1, 0, tier, 4, pitch_count=pc)
-            approx = (t["thr"][1, 0, tier, 4, :6].astype(np.int64) + (pc - 75) * t["slope"][1, tier, 4, :6].astype(np.int64)) / 2.0**31
+            approx = (t["fthr"][1, tier, 4, :6].astype(np.int64) + (pc - 75) * t["fslope"][1, tier, 4, :6].astype(np.int64)) / 2.0**31
             assert np.abs(exact - approx).max() < 2.0**-24
     t2 = tables.build_table(synth.make_matchup())
-    assert not (t2["flags"] & _abi.FLAG_FATIGUE) and not t2["slope"].any()
+    assert not (t2["flags"] & _abi.FLAG_FATIGUE) and not t2["fslope"].any()
 
 
 def test_oracle_twin_pa_mix_matches_table_law():
