@@ -95,7 +95,7 @@ int mlbsim_init(int device, mlbsim_ctx** out) {
   if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail("cudaEventCreate", e);
   if ((e = cudaMalloc(&ctx->params_dev, sizeof(mlbsim_params))) != cudaSuccess) return bail("cudaMalloc", e);
   if ((e = cudaFuncSetAttribute(mlbsim_native_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)mlbsim_native_smem_bytes())) != cudaSuccess)
+                                (int)mlbsim_native_smem_bytes(MLBSIM_NATIVE_MAX_THREADS))) != cudaSuccess)
     return bail("cudaFuncSetAttribute", e);
   *out = ctx;
   return MLBSIM_OK;
@@ -187,10 +187,12 @@ static int launch_native(mlbsim_ctx* ctx, int matchup_lo, int matchup_hi, uint64
   if (!ctx->tables_dev) return fail(ctx, MLBSIM_ERR_STATE, "mlbsim_run_native before mlbsim_upload_tables");
   if (matchup_lo < 0 || matchup_hi > ctx->n_tables || matchup_lo >= matchup_hi) return fail(ctx, MLBSIM_ERR_ARG, "matchup range out of bounds");
   if (sim_hi < sim_lo) return fail(ctx, MLBSIM_ERR_ARG, "sim_hi < sim_lo");
+  if (sim_hi > RNG_MAX_SIM_INDEX) return fail(ctx, MLBSIM_ERR_ARG, "sim index beyond 2^38 (Philox counter field)");
+  if ((unsigned)matchup_hi > RNG_MAX_MATCHUPS) return fail(ctx, MLBSIM_ERR_ARG, "more than 4096 matchups (Philox counter field)");
   if (!hist_dev) return fail(ctx, MLBSIM_ERR_ARG, "hist pointer is NULL");
   const int n_m = matchup_hi - matchup_lo;
   const int threads = ctx->threads_per_block ? ctx->threads_per_block : 512;
-  const size_t smem = mlbsim_native_smem_bytes();
+  const size_t smem = mlbsim_native_smem_bytes(threads);
   int occ = 0;
   CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mlbsim_native_kernel, threads, smem));
   if (occ < 1) return fail(ctx, MLBSIM_ERR_CUDA, "native kernel does not fit on an SM");
@@ -221,7 +223,7 @@ static int launch_native(mlbsim_ctx* ctx, int matchup_lo, int matchup_hi, uint64
     if (chunk > 1024) chunk = 1024;
     a.chunk = (uint32_t)chunk;
     a.flags = flags;
-    a.keys = philox_expand_key(seed);
+    a.keys = philox2_keys_from_seed(seed);
     CK(ctx, cudaMemsetAsync(ctx->counters_dev, 0, sizeof(unsigned long long) * (size_t)n_m, ctx->stream));
     if (first) CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     if (n > 0) {
@@ -349,6 +351,7 @@ int mlbsim_run_persim(mlbsim_ctx* ctx, int matchup, uint64_t sim_lo, uint64_t si
   if (!ctx->tables_dev) return fail(ctx, MLBSIM_ERR_STATE, "mlbsim_run_persim before mlbsim_upload_tables");
   if (matchup < 0 || matchup >= ctx->n_tables) return fail(ctx, MLBSIM_ERR_ARG, "matchup out of range");
   if (sim_hi < sim_lo || !out_host) return fail(ctx, MLBSIM_ERR_ARG, "mlbsim_run_persim: bad argument");
+  if (sim_hi > RNG_MAX_SIM_INDEX || (unsigned)matchup >= RNG_MAX_MATCHUPS) return fail(ctx, MLBSIM_ERR_ARG, "sim or matchup index beyond the Philox counter fields");
   const uint64_t n = sim_hi - sim_lo;
   if (n == 0) return MLBSIM_OK;
   CK(ctx, cudaSetDevice(ctx->device));
@@ -360,7 +363,7 @@ int mlbsim_run_persim(mlbsim_ctx* ctx, int matchup, uint64_t sim_lo, uint64_t si
   a.sim_lo = sim_lo;
   a.n_sims = n;
   a.matchup_id = (uint32_t)matchup;
-  a.keys = philox_expand_key(seed);
+  a.keys = philox2_keys_from_seed(seed);
   const int threads = 128;
   uint64_t blocks = (n + threads - 1) / threads;
   const uint64_t cap = (uint64_t)ctx->prop.multiProcessorCount * 16;

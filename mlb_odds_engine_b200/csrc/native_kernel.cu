@@ -11,8 +11,9 @@
 //     other at those boundaries);
 //   * a lane that finishes a game immediately starts the next unassigned sim of its warp's
 //     chunk (warp-ballot prefix, no atomics); warps pull chunks of the matchup's sim range
-//     from a global counter.  Sim i draws Philox4x32-10 blocks with counter (i_lo, i_hi, pa_seq,
-//     matchup) and key = seed, so which lane / block / GPU runs it is irrelevant to its result;
+//     from a global counter.  Sim i draws Philox2x32-10 blocks with counter (i, draw number,
+//     kind, matchup) and a key derived from the seed (philox.cuh), so which lane / block / GPU
+//     runs it is irrelevant to its result;
 //   * the per-matchup alias table (16 KB, one word read per PA), the transition LUT (2.6 KB) and
 //     the five joint (away, home) histograms (20 KB of u32 bins) live in shared memory; histograms
 //     are flushed to the uint64 device totals once per (block, matchup);
@@ -30,7 +31,7 @@ namespace {
 constexpr uint32_t T_DP = 601295421u;        // 0.14 * 2^32   half_inning_simulator.py:76
 constexpr uint32_t T_040 = 1717986918u;      // 0.40 * 2^32   :103 (1B: runner on 2B scores), :120 (2B: runner on 1B scores)
 constexpr uint32_t T_046 = 1975684956u;      // 0.40 + 0.60*0.10: :103 combined with the two-out rule :28-39
-constexpr uint32_t T_080 = 3435973837u;      // 0.80 * 2^32   :105 (1B: runner on 1B takes second)
+constexpr uint32_t T_080_16 = 52429u;         // 0.80 * 2^16   :105 (1B: runner on 1B takes second; low half of w1)
 constexpr uint32_t T_END_BOTH = 472446u;     // 0.011*0.01        misc run AND ghost run  :12-25
 constexpr uint32_t T_END_ANY = 89721867u;    // 1-0.989*0.99      misc run OR ghost run
 constexpr uint32_t T_END_GHOST = 42949673u;  // 0.01              ghost run only (inning already scored)
@@ -58,7 +59,10 @@ struct __align__(16) Smem {
   uint32_t n_games;
   uint32_t hdr_flags, L0, L1, nb0, nb1;
   uint32_t go;  // block-uniform "this matchup still has work"
+  // followed in dynamic shared memory by pa[14][blockDim.x]: per-thread PA outcome counters
+  // (column = thread: bank = lane, so the read-modify-write below is conflict-free)
 };
+constexpr int PA_FIELDS = 14;  // [side][outcome]
 
 // ---- per-side context word (one per batting side; `cur` = side at bat, `oth` = the other) -------
 // slot[3:0] | tier[5:4] | pit[8:6] | pitch_count[31:9]      pitch_count is the top field, so
@@ -130,31 +134,13 @@ __device__ __forceinline__ void commit_joint(uint32_t* sj, unsigned long long* H
   }
 }
 
-// warp-wide flush of the packed 8-bit PA counters (pc* = side at bat, po* = other side)
-__device__ __forceinline__ void flush_pa(unsigned long long* Hpa, uint32_t side, uint32_t& pc_lo, uint32_t& pc_hi,
-                                         uint32_t& po_lo, uint32_t& po_hi, int lane) {
-  const uint32_t s0_lo = side ? po_lo : pc_lo, s0_hi = side ? po_hi : pc_hi;
-  const uint32_t s1_lo = side ? pc_lo : po_lo, s1_hi = side ? pc_hi : po_hi;
-#pragma unroll
-  for (int o = 0; o < MLBSIM_N_OUTCOMES; ++o) {
-    const uint32_t f0 = ((o < 4 ? s0_lo : s0_hi) >> (8 * (o & 3))) & 255u;
-    const uint32_t f1 = ((o < 4 ? s1_lo : s1_hi) >> (8 * (o & 3))) & 255u;
-    const uint32_t v0 = __reduce_add_sync(0xffffffffu, f0);
-    const uint32_t v1 = __reduce_add_sync(0xffffffffu, f1);
-    if (lane == 0) {
-      if (v0) atomicAdd(&Hpa[o], (unsigned long long)v0);
-      if (v1) atomicAdd(&Hpa[8 + o], (unsigned long long)v1);
-    }
-  }
-  pc_lo = pc_hi = po_lo = po_hi = 0;
-}
-
 }  // namespace
 
 extern "C" __global__ void __launch_bounds__(MLBSIM_NATIVE_MAX_THREADS, 1)
 mlbsim_native_kernel(const NativeArgs args) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& S = *reinterpret_cast<Smem*>(smem_raw);
+  uint32_t* const S_pa = reinterpret_cast<uint32_t*>(smem_raw + sizeof(Smem));
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -199,7 +185,7 @@ mlbsim_native_kernel(const NativeArgs args) {
     const bool fatigue = (S.hdr_flags & MLBSIM_FLAG_FATIGUE) != 0;
     const bool count_pa = (args.flags & 1u) == 0;
     const uint32_t L0 = S.L0, L1 = S.L1, nb0 = S.nb0, nb1 = S.nb1;
-    const uint32_t c3 = args.matchup_base + m;
+    const uint32_t rng_matchup = (args.matchup_base + m) << RNG_MATCHUP_SHIFT;
     unsigned long long* const H = args.hist + (size_t)m * MLBSIM_HIST_WORDS;
     unsigned long long* const counter = args.counters + m;
     // word offsets inside mlbsim_hist
@@ -209,20 +195,28 @@ mlbsim_native_kernel(const NativeArgs args) {
     constexpr size_t H_RELP = H_RELG + 16;
     constexpr size_t H_N = H_RELP + 16;
 
+    // per-thread PA counters: pa[f][tid], f = side*7 + outcome
+    const uint32_t pa_stride = blockDim.x * 4u;               // bytes between fields
+    const uint32_t pa_side = 7u * pa_stride;                   // bytes between sides
+    unsigned char* const pa_mine = reinterpret_cast<unsigned char*>(S_pa) + tid * 4u;
+    if (count_pa) {
+#pragma unroll
+      for (int f = 0; f < PA_FIELDS; ++f) *reinterpret_cast<uint32_t*>(pa_mine + f * pa_stride) = 0u;
+    }
+
     // ---- warp-uniform work state ----
     uint32_t chunk_next = 0, chunk_end = 0;
     bool exhausted = false;
 
     // ---- lane state ----
     bool alive = false;
-    uint32_t c0 = 0, c1 = 0, seq = 0;
+    uint32_t c0 = 0, c1 = 0;           // Philox counter: c0 = sim_lo, c1 = draw number | matchup | sim_hi
     uint32_t cur = 0, oth = 0;         // side contexts: cur = side at bat
     uint32_t sc = 0;                   // away | home << 16
     uint32_t hidx = 0;                 // half-inning index: side = hidx & 1, inning = (hidx >> 1) + 1
     uint32_t hs = 0;                   // half-inning state
     uint32_t used = 0;                 // reliever bitmasks: home staff bits 0-7, away staff 8-15
-    uint32_t pc_lo = 0, pc_hi = 0, po_lo = 0, po_hi = 0;  // packed 8-bit outcome counters (at bat / other)
-    int flush_in = 255;
+    uint32_t w1_first = 0;             // w1 of the current half's first PA (end-of-half draw)
 
     for (;;) {
       // ---------------- refill / termination (warp-synchronous) ----------------
@@ -244,7 +238,8 @@ mlbsim_native_kernel(const NativeArgs args) {
         const uint32_t rank = __popc(need & lanemask_lt());
         if (!alive && rank < avail) {
           const unsigned long long sim = (unsigned long long)args.sim_lo + (chunk_next + rank);
-          c0 = (uint32_t)sim; c1 = (uint32_t)(sim >> 32); seq = 0;
+          c0 = (uint32_t)sim;
+          c1 = ((uint32_t)(sim >> 32) << RNG_SIMHI_SHIFT) | rng_matchup;
           cur = 0; oth = 0; sc = 0; hidx = 0; hs = 0; used = 0;
           alive = true;
         }
@@ -255,15 +250,18 @@ mlbsim_native_kernel(const NativeArgs args) {
 
       if (alive) {
         // ---------------- one plate appearance ----------------
-        uint32_t w0, w1, w2, w3;
-        philox4x32_10(c0, c1, seq, c3, args.keys, w0, w1, w2, w3);
-        ++seq;
+        uint32_t w0, w1;
+        philox2x32_10(c0, c1, args.keys, w0, w1);
 
         const uint32_t side = hidx & 1u;
         const uint32_t slot = cur & CX_SLOT;
+        const bool first_pa = (hs & HS_NPA_MASK) == 0;
+        // The first PA of a half has empty bases, so its w1 never reaches the transition: keep it
+        // as this half's end-of-inning (misc / ghost run) draw.
+        if (first_pa) w1_first = w1;
         // TTO: half_inning_simulator.py:177-178 — bump when the lineup wraps, except at the very
         // first PA of a half that starts at slot 0
-        if (slot == 0 && (hs & HS_NPA_MASK) != 0 && (cur & CX_TIER_MASK) != CX_TIER_MASK) cur += CX_TIER_ONE;
+        if (slot == 0 && !first_pa && (cur & CX_TIER_MASK) != CX_TIER_MASK) cur += CX_TIER_ONE;
         const uint32_t T = (cur >> CX_T_SHIFT) & 31u;  // pit*4 + tier
         const uint32_t row = (side * (MLBSIM_MAX_PITCHERS * MLBSIM_N_TIERS) + T) * MLBSIM_MAX_LINEUP + slot;
         // Walker alias draw: one shared-memory word per PA
@@ -284,15 +282,16 @@ mlbsim_native_kernel(const NativeArgs args) {
           }
         }
 
+        // base-running sub-draws from w1: A = full 32-bit compare, B = its low 16 bits
         const uint32_t ob = hs & HS_OB;
         const uint32_t tA = S.tA[o * 2u + (ob >> 4)];
-        const uint32_t sel = o * 4u + (w1 < tA ? 2u : 0u) + (w2 < T_080 ? 1u : 0u);
+        const uint32_t sel = o * 4u + (w1 < tA ? 2u : 0u) + ((w1 & 0xFFFFu) < T_080_16 ? 1u : 0u);
         const uint32_t ent = S.lut[sel * 24u + ob];
         hs = (hs & ~HS_OB) + HS_NPA_ONE + ent;
 
         if (count_pa) {
-          const uint32_t inc = 1u << ((o & 3u) * 8u);
-          if (o < 4u) pc_lo += inc; else pc_hi += inc;
+          uint32_t* p = reinterpret_cast<uint32_t*>(pa_mine + (side ? pa_side : 0u) + o * pa_stride);
+          *p += 1u;
         }
 
         // next batter, one more pitch (pitch_count counts PAs: half_inning_simulator.py:218-220)
@@ -303,25 +302,26 @@ mlbsim_native_kernel(const NativeArgs args) {
         // ---------------- end of half inning ----------------
         if ((hs & HS_OB) >= 24u || (hs & HS_NPA_MASK) >= ((uint32_t)MAX_PA_PER_HALF << 8)) {
           uint32_t runs = (hs >> 16) & 63u;
-          if (hs >= (1u << 24)) {  // runner_reached
-            runs += (runs == 0u) ? (uint32_t)(w3 < T_END_BOTH) + (uint32_t)(w3 < T_END_ANY) : (uint32_t)(w3 < T_END_GHOST);
-          }
+          const uint32_t x2 = (uint32_t)(w1_first < T_END_BOTH) + (uint32_t)(w1_first < T_END_ANY);
+          const uint32_t x1 = (uint32_t)(w1_first < T_END_GHOST);
+          const uint32_t extra = (runs == 0u) ? x2 : x1;
+          runs += (hs >= (1u << 24)) ? extra : 0u;  // only if a runner reached
           sc += runs << (side * 16u);
           const uint32_t a = sc & 0xFFFFu, h = sc >> 16;
           // first 1/3/5/7 innings: committed when the bottom half of that inning ends (hidx = 1, 5, 9, 13)
           if ((hidx & 3u) == 1u && hidx < 16u) commit_joint(S.joint, H, hidx >> 2, a, h);
           // game_simulator.py:72 (bottom of the 9th skipped when the home team leads) and :110-111
-          const bool over = side ? (hidx >= 17u && a != h) : (hidx == 16u && h > a);
+          const bool over = ((side != 0u) & (hidx >= 17u) & (a != h)) | ((hidx == 16u) & (h > a));
+          hs = 0;
           if (!over) {
             ++hidx;
-            hs = 0;
-            uint32_t t = cur; cur = oth; oth = t;
-            t = pc_lo; pc_lo = po_lo; po_lo = t;
-            t = pc_hi; pc_hi = po_hi; po_hi = t;
+            const uint32_t t = cur; cur = oth; oth = t;
             // should_replace_pitcher (game_simulator.py:8-12) for the staff that now takes the mound
             const uint32_t nb = side ? nb0 : nb1;  // `side` is the half that just ended
             if (nb != 0u && ((cur & CX_TIER_GE2) != 0u || cur >= ((uint32_t)(PITCH_LIMIT + 1) << CX_PC_SHIFT))) {
-              const uint32_t idx = __umulhi(w2, nb);  // stationary law of simulate_reliever_chain: uniform, with replacement
+              // stationary law of simulate_reliever_chain: uniform, with replacement.  The half ended on
+              // an out, whose transition ignores the low half of w1 (only singles read it).
+              const uint32_t idx = ((w1 & 0xFFFFu) * nb) >> 16;
               cur = (cur & CX_SLOT) | ((idx + 1u) << CX_PIT_SHIFT);
               const uint32_t bit = idx + (side ? 0u : 8u);
               used |= 1u << bit;
@@ -339,26 +339,22 @@ mlbsim_native_kernel(const NativeArgs args) {
               atomicAdd(&S.rel_games[b], 1u);
             }
             atomicAdd(&S.n_games, 1u);
-            if (side) {  // next game starts with side 0 at bat: keep (pc_*, po_*) = (side 0, side 1)
-              uint32_t t = pc_lo; pc_lo = po_lo; po_lo = t;
-              t = pc_hi; pc_hi = po_hi; po_hi = t;
-            }
             hidx = 0;
             alive = false;
           }
         }
-      }
-
-      // ---------------- periodic flush of the packed PA counters ----------------
-      if (count_pa && --flush_in == 0) {
-        flush_in = 255;
-        flush_pa(H + H_PA, hidx & 1u, pc_lo, pc_hi, po_lo, po_hi, lane);
+        ++c1;  // next draw number
       }
     }
 
-    if (count_pa) flush_pa(H + H_PA, hidx & 1u, pc_lo, pc_hi, po_lo, po_hi, lane);
-
-    // ---- block flush: shared u32 bins -> device u64 totals ----
+    // ---- block flush: shared u32 bins / per-thread counters -> device u64 totals ----
+    if (count_pa) {
+#pragma unroll
+      for (int f = 0; f < PA_FIELDS; ++f) {
+        const uint32_t v = __reduce_add_sync(0xffffffffu, *reinterpret_cast<uint32_t*>(pa_mine + f * pa_stride));
+        if (lane == 0 && v) atomicAdd(&H[H_PA + (f / 7) * 8 + (f % 7)], (unsigned long long)v);
+      }
+    }
     __syncthreads();
     for (int i = tid; i < JOINT_WORDS; i += blockDim.x) {
       const uint32_t v = S.joint[i];
@@ -388,8 +384,9 @@ mlbsim_persim_kernel(const PersimArgs args) {
   for (unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; g < args.n_sims;
        g += (unsigned long long)gridDim.x * blockDim.x) {
     const unsigned long long sim = args.sim_lo + g;
-    const uint32_t c0 = (uint32_t)sim, c1 = (uint32_t)(sim >> 32);
-    uint32_t seq = 0, w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+    const uint32_t c0 = (uint32_t)sim;
+    const uint32_t c1base = ((uint32_t)(sim >> 32) << RNG_SIMHI_SHIFT) | (args.matchup_id << RNG_MATCHUP_SHIFT);
+    uint32_t seq = 0, w0 = 0, w1 = 0, w1_first = 0;
     __align__(16) mlbsim_replay_game R;
     {
       uint32_t* z = reinterpret_cast<uint32_t*>(&R);
@@ -405,7 +402,7 @@ mlbsim_persim_kernel(const PersimArgs args) {
         if (side == 1 && inning == 9 && score[1] > score[0]) break;
         const uint32_t nbp = T->bullpen_len[side];
         if ((pc[side] > PITCH_LIMIT || tto[side] >= 3) && nbp > 0) {
-          const uint32_t idx = __umulhi(w2, nbp);
+          const uint32_t idx = ((w1 & 0xFFFFu) * nbp) >> 16;  // low half of the game's latest w1
           pit[side] = 1 + (int)idx; pc[side] = 0; tto[side] = 1;
           uint8_t* used = side == 0 ? R.used_home : R.used_away;
           if (n_used[side] < MLBSIM_REPLAY_MAX_USED) used[n_used[side]] = (uint8_t)idx;
@@ -416,8 +413,8 @@ mlbsim_persim_kernel(const PersimArgs args) {
         int outs = 0, bases = 0, runs = 0, n = 0, sl = slot[side];
         bool reached = false;
         while (outs < 3 && n < MAX_PA_PER_HALF) {
-          philox4x32_10(c0, c1, seq, args.matchup_id, args.keys, w0, w1, w2, w3);
-          ++seq;
+          philox2x32_10(c0, c1base + seq, args.keys, w0, w1);
+          if (n == 0) w1_first = w1;
           if (sl == 0 && n > 0) tto[side] += 1;
           const int tier = (tto[side] >= 4 ? 4 : tto[side]) - 1;
           int o;
@@ -435,14 +432,15 @@ mlbsim_persim_kernel(const PersimArgs args) {
             o = ((w0 & 0x1FFFFFFFu) < (e >> 3)) ? (int)col : (int)(e & 7u);
           }
           const uint32_t tA = subdraw_a_threshold(o, outs == 2);
-          const uint32_t ent = transition_entry(o, w1 < tA, w2 < T_080, outs, bases);
+          const uint32_t ent = transition_entry(o, w1 < tA, (w1 & 0xFFFFu) < T_080_16, outs, bases);
           const int r = (ent >> 16) & 7;
           outs = (ent & 31u) >> 3; bases = ent & 7u; runs += r;
           if ((ent >> 24) & 1u) reached = true;
           R.pa[side][o] += 1;
           pc[side] += 1; n += 1; sl = (sl + 1 == L) ? 0 : sl + 1;
+          ++seq;
         }
-        if (reached) runs += (runs == 0) ? (int)(w3 < T_END_BOTH) + (int)(w3 < T_END_ANY) : (int)(w3 < T_END_GHOST);
+        if (reached) runs += (runs == 0) ? (int)(w1_first < T_END_BOTH) + (int)(w1_first < T_END_ANY) : (int)(w1_first < T_END_GHOST);
         slot[side] = sl;
         score[side] += runs;
         rr[side] = runs;
@@ -466,4 +464,4 @@ mlbsim_persim_kernel(const PersimArgs args) {
   }
 }
 
-size_t mlbsim_native_smem_bytes() { return sizeof(Smem); }
+size_t mlbsim_native_smem_bytes(int threads_per_block) { return sizeof(Smem) + (size_t)PA_FIELDS * 4u * (size_t)threads_per_block; }

@@ -15,10 +15,10 @@ struct NativeArgs {
   uint64_t sim_lo;               // first sim index of this launch
   uint32_t n_sims;               // sims per matchup in this launch (< 2^32)
   uint32_t n_matchups;
-  uint32_t matchup_base;         // global id of tables[0] (Philox counter word 3)
+  uint32_t matchup_base;         // global id of tables[0] (Philox counter field)
   uint32_t chunk;                // sims a warp takes per fetch
   uint32_t flags;                // bit 0: skip PA outcome counters
-  PhiloxKeys keys;
+  Philox2Keys keys;
 };
 
 struct ReplayArgs {
@@ -34,8 +34,8 @@ struct PersimArgs {
   mlbsim_replay_game* out;    // device, n_sims records
   unsigned long long sim_lo;
   unsigned long long n_sims;
-  uint32_t matchup_id;        // Philox counter word 3
-  PhiloxKeys keys;
+  uint32_t matchup_id;        // Philox counter field
+  Philox2Keys keys;
 };
 
 #ifdef __CUDACC__
@@ -43,4 +43,4 @@ extern "C" __global__ void mlbsim_persim_kernel(const PersimArgs args);
 extern "C" __global__ void mlbsim_native_kernel(const NativeArgs args);
 extern "C" __global__ void mlbsim_replay_kernel(const ReplayArgs args);
 #endif
-size_t mlbsim_native_smem_bytes();
+size_t mlbsim_native_smem_bytes(int threads_per_block);

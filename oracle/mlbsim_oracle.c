@@ -86,6 +86,31 @@ void oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
+/* Philox2x32-10 (same paper): the generator of the native law */
+#define PHILOX2_M 0xD256D193u
+void oracle_philox2x32_10(const uint32_t ctr[2], uint32_t key, uint32_t out[2]) {
+  uint32_t c0 = ctr[0], c1 = ctr[1], k = key;
+  for (int r = 0; r < 10; ++r) {
+    uint64_t p = (uint64_t)PHILOX2_M * c0;
+    c0 = (uint32_t)(p >> 32) ^ k ^ c1;
+    c1 = (uint32_t)p;
+    k += PHILOX_W0;
+  }
+  out[0] = c0; out[1] = c1;
+}
+/* 64-bit seed -> 32-bit Philox2x32 key: word 0 of Philox4x32-10 over a fixed domain-separation counter */
+uint32_t oracle_native_key(uint64_t seed) {
+  const uint32_t ctr[4] = {0x6d6c6273u, 0x696d3278u, 0u, 0u};
+  const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+  uint32_t out[4];
+  oracle_philox4x32_10(ctr, key, out);
+  return out[0];
+}
+/* counter word 1: draw number [12:0] | kind [13] | matchup [25:14] | sim bits 37..32 [31:26] */
+#define RNG_KIND_HALF_END (1u << 13)
+#define RNG_MATCHUP_SHIFT 14
+#define RNG_SIMHI_SHIFT 26
+
 /* ------------------------------------------------------------------------------------------ */
 /* draw sources for the float64 engine                                                        */
 /* ------------------------------------------------------------------------------------------ */
@@ -441,7 +466,7 @@ int oracle_grammar(const mlbsim_params* P, uint64_t seed, int64_t game_lo, int64
 static const uint32_t T_DP = 601295421u;      /* round(0.14 * 2^32)   half_inning_simulator.py:76 */
 static const uint32_t T_040 = 1717986918u;    /* round(0.40 * 2^32)   :103, :120 */
 static const uint32_t T_046 = 1975684956u;    /* round(0.46 * 2^32) = 0.4 + 0.6*0.10  :103 + :28-39 (two outs) */
-static const uint32_t T_080 = 3435973837u;    /* round(0.80 * 2^32)   :105 */
+static const uint32_t T_080_16 = 52429u;      /* round(0.80 * 2^16)   :105 (low half of w1) */
 static const uint32_t T_END_BOTH = 472446u;   /* round(0.011*0.01 * 2^32)          misc AND ghost  :12-25 */
 static const uint32_t T_END_ANY = 89721867u;  /* round((1-0.989*0.99) * 2^32)      misc OR ghost */
 static const uint32_t T_END_GHOST = 42949673u;/* round(0.01 * 2^32)                ghost only (runs > 0) */
@@ -472,10 +497,12 @@ static uint32_t native_transition(int o, int dA, int dB, int outs, int bases) {
 }
 
 /* one game of the native law; adds to `local` (if not NULL) and fills `rg` (if not NULL) */
-static void native_game(const mlbsim_table* T, uint32_t matchup, const uint32_t key[2], uint64_t sim, int count_pa,
+static void native_game(const mlbsim_table* T, uint32_t matchup, uint32_t key, uint64_t sim, int count_pa,
                         mlbsim_hist* local, mlbsim_replay_game* rg) {
-  uint32_t ctr[4] = {(uint32_t)sim, (uint32_t)(sim >> 32), 0u, matchup};
-  uint32_t w[4] = {0, 0, 0, 0};
+  const uint32_t c0 = (uint32_t)sim;
+  const uint32_t c1base = ((uint32_t)(sim >> 32) << RNG_SIMHI_SHIFT) | (matchup << RNG_MATCHUP_SHIFT);
+  uint32_t seq = 0;
+  uint32_t w[2] = {0, 0}, w1_first = 0;
   int score[2] = {0, 0}, slot[2] = {0, 0};
   staff_state st[2] = {{0, 1, 0}, {0, 1, 0}};
   int cap_a[4] = {0, 0, 0, 0}, cap_h[4] = {0, 0, 0, 0};
@@ -489,7 +516,7 @@ static void native_game(const mlbsim_table* T, uint32_t matchup, const uint32_t 
       if (side == 1 && inning == 9 && score[1] > score[0]) break;
       int nbp = (int)T->bullpen_len[side];
       if ((st[side].pc > 90 || st[side].tto >= 3) && nbp > 0) {
-        int idx = (int)(((uint64_t)w[2] * (uint64_t)nbp) >> 32); /* w2 of the game's latest PA */
+        int idx = (int)(((w[1] & 0xFFFFu) * (uint32_t)nbp) >> 16); /* low half of the game's latest w1 (an out ignores it) */
         st[side].pit = 1 + idx; st[side].pc = 0; st[side].tto = 1;
         used_mask[side] |= 1u << idx;
         if (local) local->rel_picks[side][idx]++;
@@ -503,8 +530,9 @@ static void native_game(const mlbsim_table* T, uint32_t matchup, const uint32_t 
       int L = (int)T->lineup_len[side];
       int outs = 0, runs = 0, n = 0, bases = 0, reached = 0, sl = slot[side];
       while (outs < 3 && n < 30) {
-        oracle_philox4x32_10(ctr, key, w);
-        ctr[2]++;
+        const uint32_t ctr[2] = {c0, c1base + seq};
+        oracle_philox2x32_10(ctr, key, w);
+        if (n == 0) w1_first = w[1]; /* bases empty: this w1 never reaches the transition -> end-of-half draw */
         if (sl == 0 && n > 0) st[side].tto += 1;
         int tier = (st[side].tto >= 4 ? 4 : st[side].tto) - 1;
         int o;
@@ -523,7 +551,7 @@ static void native_game(const mlbsim_table* T, uint32_t matchup, const uint32_t 
           o = ((w[0] & 0x1FFFFFFFu) < (e >> 3)) ? (int)col : (int)(e & 7u);
         }
         uint32_t tA = (o == MLBSIM_1B) ? (outs == 2 ? T_046 : T_040) : (o == MLBSIM_2B) ? T_040 : T_DP;
-        int dA = w[1] < tA, dB = w[2] < T_080;
+        int dA = w[1] < tA, dB = (w[1] & 0xFFFFu) < T_080_16;
         uint32_t t = native_transition(o, dA, dB, outs, bases);
         int r = (t >> 3) & 7;
         bases = t & 7; outs += t >> 6; runs += r;
@@ -531,8 +559,9 @@ static void native_game(const mlbsim_table* T, uint32_t matchup, const uint32_t 
         if (count_pa && local) local->pa[side][o]++;
         if (rg) rg->pa[side][o]++;
         st[side].pc += 1; n += 1; sl = (sl + 1 == L) ? 0 : sl + 1;
+        seq += 1;
       }
-      if (reached) runs += (runs == 0) ? (w[3] < T_END_BOTH) + (w[3] < T_END_ANY) : (w[3] < T_END_GHOST);
+      if (reached) runs += (runs == 0) ? (w1_first < T_END_BOTH) + (w1_first < T_END_ANY) : (w1_first < T_END_GHOST);
       slot[side] = sl;
       score[side] += runs;
       rr[side] = runs;
@@ -554,7 +583,7 @@ static void native_game(const mlbsim_table* T, uint32_t matchup, const uint32_t 
   }
   if (rg) {
     rg->home_score = score[1]; rg->away_score = score[0]; rg->n_innings = inning;
-    rg->tape_used = (int32_t)ctr[2]; /* Philox blocks (= PAs) consumed */
+    rg->tape_used = (int32_t)seq; /* Philox PA blocks (= PAs) consumed */
     rg->n_used[0] = n_used[0]; rg->n_used[1] = n_used[1];
   }
 }
@@ -565,7 +594,7 @@ typedef struct {
 } native_args;
 static void native_range(int64_t lo, int64_t hi, void* argp) {
   native_args* a = (native_args*)argp;
-  const uint32_t key[2] = {(uint32_t)a->seed, (uint32_t)(a->seed >> 32)};
+  const uint32_t key = oracle_native_key(a->seed);
   const int count_pa = !(a->flags & 1u);
   mlbsim_hist* local = a->hist ? (mlbsim_hist*)calloc(1, sizeof(mlbsim_hist)) : NULL;
   for (uint64_t sim = (uint64_t)lo; sim < (uint64_t)hi; ++sim)

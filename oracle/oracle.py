@@ -44,6 +44,10 @@ def lib():
         L.oracle_native_persim.restype = ctypes.c_int
         L.oracle_philox4x32_10.argtypes = [vp, vp, vp]
         L.oracle_philox4x32_10.restype = None
+        L.oracle_philox2x32_10.argtypes = [vp, u32, vp]
+        L.oracle_philox2x32_10.restype = None
+        L.oracle_native_key.argtypes = [u64]
+        L.oracle_native_key.restype = u32
         L.oracle_set_threads.argtypes = [ctypes.c_int]
         L.oracle_get_threads.restype = ctypes.c_int
         for f in ("params", "table", "hist", "replay_game"):
@@ -74,6 +78,17 @@ def philox4x32_10(ctr, key):
     out = np.zeros(4, dtype=np.uint32)
     lib().oracle_philox4x32_10(_ptr(c), _ptr(k), _ptr(out))
     return out
+
+
+def philox2x32_10(ctr, key):
+    c = np.asarray(ctr, dtype=np.uint32)
+    out = np.zeros(2, dtype=np.uint32)
+    lib().oracle_philox2x32_10(_ptr(c), int(key), _ptr(out))
+    return out
+
+
+def native_key(seed: int) -> int:
+    return int(lib().oracle_native_key(int(seed)))
 
 
 def pack_tapes(tapes):

@@ -39,3 +39,15 @@ def test_philox_known_answers():
     for ctr, key, want in kat:
         got = orc.philox4x32_10(ctr, key)
         assert [int(x) for x in got] == want
+
+
+def test_philox2x32_known_answers():
+    # Random123 known-answer vectors for philox2x32-10
+    kat = [
+        ([0, 0], 0, [0xFF1DAE59, 0x6CD10DF2]),
+        ([0xFFFFFFFF, 0xFFFFFFFF], 0xFFFFFFFF, [0x2C3F628B, 0xAB4FD7AD]),
+        ([0x243F6A88, 0x85A308D3], 0x13198A2E, [0xDD7CE038, 0xF62A4C12]),
+    ]
+    for ctr, key, want in kat:
+        got = orc.philox2x32_10(ctr, key)
+        assert [int(x) for x in got] == want
