@@ -174,20 +174,31 @@ def build_params(m, use_noise=None) -> np.ndarray:
 # ---------------------------------------------------------------------------------------------
 def _p_k_or_bb(k, bb, use_noise):
     """(P(K), P(K or BB)) for effective rates k, bb (pa_simulator.py:117-124, :35-41)."""
-    pk = min(max(k, 0.0), 1.0)
+    pk, pkbb = _p_k_or_bb_batch(np.array([k], dtype=np.float64), np.array([bb], dtype=np.float64), use_noise)
+    return float(pk[0]), float(pkbb[0])
+
+
+def _p_k_or_bb_batch(k, bb, use_noise):
+    """Vectorised over rows.  With noise the reference draws kp ~ Beta(30k, 30(1-k)) (0.0 / 1.0 without
+    a draw when k <= 0 / k >= 1), bp likewise, then bp *= 1.01, and compares one uniform u:
+    K iff u < kp, BB iff kp <= u < kp + bp.  Hence P(K) = E[kp] and P(K or BB) = E[min(1, kp + bp)]."""
+    k = np.asarray(k, dtype=np.float64)
+    bb = np.asarray(bb, dtype=np.float64)
+    pk = np.clip(k, 0.0, 1.0)
     if not use_noise:
-        return pk, max(pk, min(max(k + bb * 1.01, 0.0), 1.0))
-    # beta_noise: p <= 0 -> 0.0, p >= 1 -> 1.0, else Beta(30p, 30(1-p)) with mean p
-    if bb <= 0.0:
-        return pk, pk
-    if bb >= 1.0 or k >= 1.0:
-        return pk, 1.0  # kp + 1.01 >= 1, or kp = 1
-    if k <= 0.0:
-        # only the walk term is random: E[min(1, 1.01*Y)]
-        return 0.0, _expect_clip(None, bb)
-    # E[min(1, X + 1.01 Y)]: for realistic rates the clip term is < 1e-12 and the quadrature
-    # returns k + 1.01*bb to the last bit; for extreme grid points (k = 0.5, bb = 0.3: ~5 %) it matters
-    return pk, _expect_clip(k, bb)
+        return pk, np.maximum(pk, np.clip(k + bb * 1.01, 0.0, 1.0))
+    pkbb = np.empty_like(pk)
+    no_walk = bb <= 0.0
+    sure = (~no_walk) & ((bb >= 1.0) | (k >= 1.0))        # kp + 1.01 >= 1, or kp = 1
+    no_k = (~no_walk) & (~sure) & (k <= 0.0)               # only the walk term is random
+    both = ~(no_walk | sure | no_k)
+    pkbb[no_walk] = pk[no_walk]
+    pkbb[sure] = 1.0
+    if no_k.any():
+        pkbb[no_k] = _expect_clip(None, bb[no_k])
+    if both.any():
+        pkbb[both] = _expect_clip(k[both], bb[both])
+    return pk, pkbb
 
 
 _GL = None
@@ -196,57 +207,68 @@ _GL = None
 def _gauss_legendre_01():
     global _GL
     if _GL is None:
-        nodes, weights = np.polynomial.legendre.leggauss(400)
+        nodes, weights = np.polynomial.legendre.leggauss(96)   # 64 nodes already agree with 400 to 4e-15
         _GL = (0.5 * (nodes + 1.0), 0.5 * weights)
     return _GL
 
 
 def _expect_clip(k, bb):
-    """E[min(1, X + 1.01*Y)], X ~ Beta(30k, 30(1-k)) (or X = 0 if k is None), Y ~ Beta(30bb, 30(1-bb))."""
+    """E[min(1, X + 1.01*Y)] for arrays k, bb: X ~ Beta(30k, 30(1-k)) (X = 0 if k is None),
+    Y ~ Beta(30bb, 30(1-bb)).  For realistic rates the clip term is ~1e-11 and the result equals
+    k + 1.01*bb to ten digits; for extreme grid points (k = 0.5, bb = 0.3: 0.4 %) it matters
+    (SURVEY.md Appendix A caveat).  Gauss-Legendre over y, closed form in x."""
     from scipy import special, stats
 
-    ay, by = NOISE_WEIGHT * bb, NOISE_WEIGHT * (1 - bb)
-    mean = (0.0 if k is None else k) + 1.01 * bb
+    bb = np.atleast_1d(np.asarray(bb, dtype=np.float64))
     y, w = _gauss_legendre_01()
-    # the clip needs X > 1 - 1.01*y: only the upper part of Y's range can contribute
-    wy = w * stats.beta.pdf(y, ay, by)
-    c = 1.0 - 1.01 * y                      # X must exceed c for the clip to bite
+    ay, by = (NOISE_WEIGHT * bb)[:, None], (NOISE_WEIGHT * (1 - bb))[:, None]
+    wy = w[None, :] * stats.beta.pdf(y[None, :], ay, by)
+    c = (1.0 - 1.01 * y)[None, :]            # X must exceed c for the clip to bite
     if k is None:
         excess = np.maximum(-c, 0.0)
+        mean = 1.01 * bb
     else:
-        ax, bx = NOISE_WEIGHT * k, NOISE_WEIGHT * (1 - k)
+        k = np.atleast_1d(np.asarray(k, dtype=np.float64))
+        ax, bx = (NOISE_WEIGHT * k)[:, None], (NOISE_WEIGHT * (1 - k))[:, None]
         cc = np.clip(c, 0.0, 1.0)
         # E[(X - c)^+] = k * (1 - I_c(a+1, b)) - c * (1 - I_c(a, b)); for c < 0 it is k - c
-        excess = k * (1.0 - special.betainc(ax + 1, bx, cc)) - cc * (1.0 - special.betainc(ax, bx, cc))
-        excess = np.where(c < 0.0, k - c, excess)
-    return float(min(max(mean - float(np.sum(wy * excess)), 0.0), 1.0))
+        excess = k[:, None] * (1.0 - special.betainc(ax + 1, bx, cc)) - cc * (1.0 - special.betainc(ax, bx, cc))
+        excess = np.where(c < 0.0, k[:, None] - c, excess)
+        mean = k + 1.01 * bb
+    return np.clip(mean - np.sum(wy * excess, axis=1), 0.0, 1.0)
 
 
-def outcome_cdf(m: Matchup, side, pit, tier, slot, pitch_count=0, use_noise=None):
-    """Cumulative P over [K, BB, 1B, 2B, 3B, HR] (OUT is the remainder) for one PA context —
-    the marginal law of core/pa_simulator.py:91-143 + core/bip_resolution.py + fatigue_modeling.py."""
+def outcome_cdf_batch(m: Matchup, side, pit, tier, slot, pitch_count, use_noise=None):
+    """Rows of cumulative P over [K, BB, 1B, 2B, 3B, HR] (OUT is the remainder) for arrays of PA
+    contexts — the marginal law of core/pa_simulator.py:91-143 + core/bip_resolution.py +
+    core/fatigue_modeling.py.  Returns float64 [N, 6]."""
     use_noise = m.use_noise if use_noise is None else use_noise
-    pen = TTO_PENALTY[tier]
-    fl = max(0, (pitch_count - FATIGUE_START) / 25)
+    side, pit, tier, slot = (np.asarray(x, dtype=np.int64) for x in (side, pit, tier, slot))
+    pc = np.asarray(pitch_count, dtype=np.float64)
+    pen = np.asarray(TTO_PENALTY)[tier]
+    fl = np.maximum(0.0, (pc - FATIGUE_START) / 25)
     ak = m.pit_k[side, pit] * (1 - pen) * (1.0 - 0.02 * fl)
     ab = m.pit_bb[side, pit] * (1 + pen) * (1.0 + 0.03 * fl)
     k = (m.bat_k[side, slot] + ak) / 2 * m.k_mod
     bb = (m.bat_bb[side, slot] + ab) / 2 * m.bb_mod
-    pk, pkbb = _p_k_or_bb(k, bb, use_noise)
+    pk, pkbb = _p_k_or_bb_batch(k, bb, use_noise)
     contact = 1.0 - pkbb
     cdf_bip, cdf_hit, cdf_fb = contact_cdfs()
     w_bip = np.diff(np.concatenate([[0.0], cdf_bip]))
     h = np.diff(np.concatenate([[0.0], cdf_hit]))
     f = np.diff(np.concatenate([[0.0], cdf_fb]))
-    hr = min(max(float(m.pit_hr[side, pit]), 0.0), 1.0)
-    ph = float(np.dot(w_bip, m.hit_prob[side, pit, slot]))
+    hr = np.clip(m.pit_hr[side, pit], 0.0, 1.0)
+    ph = m.hit_prob[side, pit, slot] @ w_bip
     s1 = (1 - hr) * (ph * h[0] + (1 - ph) * INFIELD_FALLBACK * f[0])
     s2 = (1 - hr) * (ph * h[1] + (1 - ph) * INFIELD_FALLBACK * f[1])
     s3 = (1 - hr) * ph * h[2]
-    c = [pk, pkbb]
-    for share in (s1, s2, s3, hr):
-        c.append(c[-1] + contact * share)
-    return np.minimum(np.maximum.accumulate(np.asarray(c)), 1.0)
+    c = np.stack([pk, pkbb, pkbb + contact * s1, pkbb + contact * (s1 + s2), pkbb + contact * (s1 + s2 + s3),
+                  pkbb + contact * (s1 + s2 + s3 + hr)], axis=1)
+    return np.minimum(np.maximum.accumulate(c, axis=1), 1.0)
+
+
+def outcome_cdf(m: Matchup, side, pit, tier, slot, pitch_count=0, use_noise=None):
+    return outcome_cdf_batch(m, [side], [pit], [tier], [slot], [pitch_count], use_noise)[0]
 
 
 def outcome_probabilities(m: Matchup, side, pit, tier, slot, pitch_count=0, use_noise=None):
@@ -321,20 +343,23 @@ def build_table(m, use_noise=None) -> np.ndarray:
     fthr = np.zeros(_abi.TABLE_DTYPE["fthr"].shape, dtype=np.uint32)
     fthr[...] = 2147483648
     fslope = np.zeros(_abi.TABLE_DTYPE["fslope"].shape, dtype=np.int32)
-    for s in range(2):
-        for p in range(m.bullpen_len[s] + 1):
-            for tier in range(_abi.N_TIERS):
-                for b in range(m.lineup_len[s]):
-                    c0 = outcome_cdf(m, s, p, tier, b, 0, use_noise)
-                    alias[s, p, tier, b] = alias_row(np.diff(np.concatenate([[0.0], c0, [1.0]])))
-                    if p == 0 and m.bullpen_len[s] == 0:
-                        # a starter without a bullpen is never replaced: pitch_count passes 75
-                        q0 = _quantise(c0)
-                        q1 = _quantise(outcome_cdf(m, s, p, tier, b, FATIGUE_START + SLOPE_SPAN, use_noise))
-                        fthr[s, tier, b, :6] = q0
-                        fslope[s, tier, b, :6] = np.round((q1.astype(np.int64) - q0.astype(np.int64)) / SLOPE_SPAN)
-        if m.bullpen_len[s] == 0:
-            flags |= _abi.FLAG_FATIGUE
+    idx = [(s, p, tier, b) for s in range(2) for p in range(m.bullpen_len[s] + 1)
+           for tier in range(_abi.N_TIERS) for b in range(m.lineup_len[s])]
+    S, P, T, B = (np.array(x) for x in zip(*idx))
+    c0 = outcome_cdf_batch(m, S, P, T, B, np.zeros(len(idx)), use_noise)
+    probs = np.diff(np.concatenate([np.zeros((len(idx), 1)), c0, np.ones((len(idx), 1))], axis=1), axis=1)
+    for i, (s, p, tier, b) in enumerate(idx):
+        alias[s, p, tier, b] = alias_row(probs[i])
+    # a starter without a bullpen is never replaced: pitch_count passes 75 (fatigue_modeling.py:38)
+    fat = np.array([i for i, (s, p, tier, b) in enumerate(idx) if p == 0 and m.bullpen_len[s] == 0], dtype=np.int64)
+    if len(fat):
+        flags |= _abi.FLAG_FATIGUE
+        c1 = outcome_cdf_batch(m, S[fat], P[fat], T[fat], B[fat], np.full(len(fat), FATIGUE_START + SLOPE_SPAN), use_noise)
+        q0, q1 = _quantise(c0[fat]), _quantise(c1)
+        for j, i in enumerate(fat):
+            s, p, tier, b = idx[i]
+            fthr[s, tier, b, :6] = q0[j]
+            fslope[s, tier, b, :6] = np.round((q1[j].astype(np.int64) - q0[j].astype(np.int64)) / SLOPE_SPAN)
     t["flags"] = flags
     t["alias"] = alias
     t["fthr"] = fthr
