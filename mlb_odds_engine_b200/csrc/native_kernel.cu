@@ -19,6 +19,7 @@
 //     are flushed to the uint64 device totals once per (block, matchup);
 //   * no tensor cores: there is no dense contraction in this path.
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 
 #include "../../include/mlbsim.h"
@@ -43,7 +44,7 @@ constexpr int FATIGUE_START = 75;            // fatigue_modeling.py:38
 constexpr int SB = 32;                                    // smem joint-histogram bins per team
 constexpr int ALIAS_WORDS = 2 * MLBSIM_MAX_PITCHERS * MLBSIM_N_TIERS * MLBSIM_MAX_LINEUP * MLBSIM_ROW_WORDS;  // 4032
 constexpr int FAT_WORDS = 2 * MLBSIM_N_TIERS * MLBSIM_MAX_LINEUP * MLBSIM_ROW_WORDS;                          // 576
-constexpr int LUT_WORDS = 7 * 4 * 24;                                                                         // 672
+constexpr int LUT_WORDS = 24 * 8 * 4;   // [outs*8+bases][outcome (8 slots)][dA][dB]                           // 768
 constexpr int JOINT_WORDS = MLBSIM_N_CAPS * SB * SB;                                                          // 5120
 
 struct __align__(16) Smem {
@@ -51,7 +52,7 @@ struct __align__(16) Smem {
   uint32_t fthr[FAT_WORDS];
   int32_t fslope[FAT_WORDS];
   uint32_t lut[LUT_WORDS];
-  uint32_t tA[16];  // sub-draw A threshold by outcome*2 + (outs == 2)
+  uint32_t tA[16];  // sub-draw A threshold by (outs == 2)*8 + outcome
   uint32_t joint[JOINT_WORDS];
   uint32_t innings[MLBSIM_INN_BINS];
   uint32_t rel_games[16];
@@ -59,10 +60,43 @@ struct __align__(16) Smem {
   uint32_t n_games;
   uint32_t hdr_flags, L0, L1, nb0, nb1;
   uint32_t go;  // block-uniform "this matchup still has work"
-  // followed in dynamic shared memory by pa[14][blockDim.x]: per-thread PA outcome counters
-  // (column = thread: bank = lane, so the read-modify-write below is conflict-free)
 };
 constexpr int PA_FIELDS = 14;  // [side][outcome]
+
+}  // namespace
+
+// Statically allocated (44 KB) at global scope so that its PTX symbol keeps this plain name: the
+// hot loop takes `mov.u32 r, mlbsim_S` (a link-time constant in the .shared space) as its base and
+// every access becomes LDS [Rindex + imm] with no generic->shared conversion in the loop.
+// Dynamic shared memory holds pa[14][blockDim.x], the per-thread PA outcome counters (column =
+// thread: bank = lane, so their read-modify-write is conflict-free).
+__shared__ Smem mlbsim_S;
+extern __shared__ __align__(16) uint32_t mlbsim_S_pa[];
+
+namespace {
+#define S mlbsim_S
+#define S_pa mlbsim_S_pa
+
+__device__ __forceinline__ uint32_t smem_static_base() {
+  uint32_t a;
+  asm("mov.u32 %0, mlbsim_S;" : "=r"(a));
+  return a;
+}
+__device__ __forceinline__ uint32_t smem_dynamic_base() {
+  uint32_t a;
+  asm("mov.u32 %0, mlbsim_S_pa;" : "=r"(a));
+  return a;
+}
+
+// All hot shared-memory traffic uses 32-bit shared-window addresses (ld/st/red.shared), so the
+// loop carries one base register instead of 64-bit generic pointers.
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v)); }
+__device__ __forceinline__ void red_inc_shared(uint32_t addr) { asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr)); }
 
 // ---- per-side context word (one per batting side; `cur` = side at bat, `oth` = the other) -------
 // slot[3:0] | tier[5:4] | pit[8:6] | pitch_count[31:9]      pitch_count is the top field, so
@@ -77,12 +111,17 @@ constexpr int CX_PC_SHIFT = 9;
 constexpr uint32_t CX_NEXT_PA = (1u << CX_PC_SHIFT) + 1u;  // one more pitch, next batter
 
 // ---- half-inning state word -------------------------------------------------------------------
-// ob[4:0] = outs*8 + bases | n_pa[13:8] | runs[21:16] | reached_count[29:24]
+// ob[4:0] = outs*8 + bases | n_pa + 34 [14:8] (bit 14 = the 30-PA cap) | runs[21:16] |
+// reached_count[29:24] | three outs [30] (set by the LUT entry) | no PA yet in this half [31]
 constexpr uint32_t HS_OB = 31u;
-constexpr uint32_t HS_NPA_ONE = 1u << 8;
-constexpr uint32_t HS_NPA_MASK = 0x3Fu << 8;
+constexpr uint32_t HS_FRESH = 1u << 31;
+constexpr uint32_t HS_NEW_HALF = HS_FRESH | ((64u - MAX_PA_PER_HALF) << 8);
+constexpr uint32_t HS_KEEP = ~(HS_OB | HS_FRESH);        // hs' = (hs & HS_KEEP) + HS_PA_ONE + entry
+constexpr uint32_t HS_PA_ONE = 1u << 8;
+constexpr uint32_t HS_OVER = (1u << 30) | (1u << 14);   // three outs, or 30 PAs
+constexpr uint32_t HS_REACHED = 0x3Fu << 24;
 
-// LUT entry: new_ob | runs << 16 | reached << 24, so that  hs' = (hs & ~31) + 256 + entry.
+// LUT entry: new_ob | runs << 16 | reached << 24 | three_outs << 30
 __device__ uint32_t transition_entry(int o, int dA, int dB, int outs, int bases) {
   int nb = bases, r = 0, oa = 0;
   const int on1 = bases & 1, on2 = (bases >> 1) & 1, on3 = (bases >> 2) & 1;
@@ -105,7 +144,7 @@ __device__ uint32_t transition_entry(int o, int dA, int dB, int outs, int bases)
   int no = outs + oa;
   if (no > 3) no = 3;
   const int reached = (r > 0) || (nb != 0);
-  return (uint32_t)(no * 8 + nb) | ((uint32_t)r << 16) | ((uint32_t)reached << 24);
+  return (uint32_t)(no * 8 + nb) | ((uint32_t)r << 16) | ((uint32_t)reached << 24) | ((uint32_t)(no == 3) << 30);
 }
 
 // threshold of sub-draw A: double play (K/OUT), runner on 2B scores on a single (0.46 with two
@@ -124,9 +163,9 @@ __device__ __forceinline__ uint32_t lanemask_lt() {
 
 // joint-histogram commit: shared u32 bin when both scores fit the 32x32 window, else the global
 // u64 bin directly (a team scoring >= 32 runs: ~never, but exact)
-__device__ __forceinline__ void commit_joint(uint32_t* sj, unsigned long long* H, uint32_t c, uint32_t a, uint32_t h) {
+__device__ __forceinline__ void commit_joint(uint32_t joint_addr, unsigned long long* H, uint32_t c, uint32_t a, uint32_t h) {
   if ((a | h) < (uint32_t)SB) {
-    atomicAdd(&sj[c * (SB * SB) + a * SB + h], 1u);
+    red_inc_shared(joint_addr + ((c * (SB * SB) + a * SB + h) << 2));
   } else {
     const uint32_t ac = a < MLBSIM_HIST_BINS - 1 ? a : MLBSIM_HIST_BINS - 1;
     const uint32_t hc = h < MLBSIM_HIST_BINS - 1 ? h : MLBSIM_HIST_BINS - 1;
@@ -134,24 +173,198 @@ __device__ __forceinline__ void commit_joint(uint32_t* sj, unsigned long long* H
   }
 }
 
+// word offsets inside mlbsim_hist
+constexpr size_t H_INN = (size_t)MLBSIM_N_CAPS * MLBSIM_HIST_BINS * MLBSIM_HIST_BINS;
+constexpr size_t H_PA = H_INN + MLBSIM_INN_BINS;
+constexpr size_t H_RELG = H_PA + 16;
+constexpr size_t H_RELP = H_RELG + 16;
+constexpr size_t H_N = H_RELP + 16;
+
+// One matchup, all the sims this warp can grab.  FATIGUE: some staff has no bullpen (pitch counts
+// pass 75); COUNT_PA: keep the PA_RECAP_LOG outcome counters.
+template <bool FATIGUE, bool COUNT_PA>
+__device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned long long* const H,
+                                             unsigned long long* const counter, const uint32_t rng_matchup, const uint32_t L0,
+                                             const uint32_t L1, const uint32_t nb0, const uint32_t nb1) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t n_sims = args.n_sims;
+  const uint32_t sb = smem_static_base();
+  const uint32_t A_ALIAS = sb + (uint32_t)offsetof(Smem, alias);
+  const uint32_t A_FTHR = sb + (uint32_t)offsetof(Smem, fthr);
+  const uint32_t A_FSLOPE = sb + (uint32_t)offsetof(Smem, fslope);
+  const uint32_t A_LUT = sb + (uint32_t)offsetof(Smem, lut);
+  const uint32_t A_TA = sb + (uint32_t)offsetof(Smem, tA);
+  const uint32_t A_JOINT = sb + (uint32_t)offsetof(Smem, joint);
+  const uint32_t A_INN = sb + (uint32_t)offsetof(Smem, innings);
+  const uint32_t A_RELG = sb + (uint32_t)offsetof(Smem, rel_games);
+  const uint32_t A_RELP = sb + (uint32_t)offsetof(Smem, rel_picks);
+  const uint32_t A_NG = sb + (uint32_t)offsetof(Smem, n_games);
+  // per-thread PA counters: pa[f][tid], f = side*7 + outcome
+  const uint32_t pa_stride = blockDim.x * 4u;  // bytes between outcomes
+  const uint32_t pa_side = 7u * pa_stride;     // bytes between sides
+  const uint32_t pa_mine = smem_dynamic_base() + threadIdx.x * 4u;
+
+  // ---- warp-uniform work state ----
+  uint32_t chunk_next = 0, chunk_end = 0;
+  bool exhausted = false;
+
+  // ---- lane state ----
+  bool alive = false;
+  uint32_t c0 = 0, c1 = 0;   // Philox counter: c0 = sim_lo, c1 = PA number | matchup | sim_hi
+  uint32_t cur = 0, oth = 0; // side contexts: cur = side at bat
+  uint32_t sc = 0;           // away | home << 16
+  uint32_t hidx = 0;         // half-inning index: side = hidx & 1, inning = (hidx >> 1) + 1
+  uint32_t hs = HS_NEW_HALF; // half-inning state
+  uint32_t used = 0;         // reliever bitmasks: home staff bits 0-7, away staff 8-15
+  uint32_t w1_first = 0;     // w1 of the current half's first PA (end-of-half draw)
+  uint32_t pa_addr = pa_mine;  // counters of the side at bat
+
+  for (;;) {
+    // ---------------- refill / termination (warp-synchronous) ----------------
+    const uint32_t need = __ballot_sync(0xffffffffu, !alive);
+    if (need) {
+      if (chunk_next >= chunk_end && !exhausted) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(counter, (unsigned long long)args.chunk);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= (unsigned long long)n_sims) {
+          exhausted = true;
+        } else {
+          chunk_next = (uint32_t)base;
+          const unsigned long long e = base + args.chunk;
+          chunk_end = e < (unsigned long long)n_sims ? (uint32_t)e : n_sims;
+        }
+      }
+      const uint32_t avail = chunk_end - chunk_next;
+      const uint32_t rank = __popc(need & lanemask_lt());
+      if (!alive && rank < avail) {
+        const unsigned long long sim = (unsigned long long)args.sim_lo + (chunk_next + rank);
+        c0 = (uint32_t)sim;
+        c1 = ((uint32_t)(sim >> 32) << RNG_SIMHI_SHIFT) | rng_matchup;
+        cur = 0; oth = 0; sc = 0; hidx = 0; hs = HS_NEW_HALF; used = 0; pa_addr = pa_mine;
+        alive = true;
+      }
+      const uint32_t want = __popc(need);
+      chunk_next += want < avail ? want : avail;
+      if (exhausted && __ballot_sync(0xffffffffu, alive) == 0) break;
+    }
+
+    if (alive) {
+      // ---------------- one plate appearance ----------------
+      uint32_t w0, w1;
+      philox2x32_10(c0, c1, args.keys, w0, w1);
+      ++c1;
+
+      // The first PA of a half has empty bases, so its w1 never reaches the transition: keep it
+      // as this half's end-of-inning (misc / ghost run) draw.
+      if ((int)hs < 0) w1_first = w1;
+
+      const uint32_t side = hidx & 1u;
+      const uint32_t slot = cur & CX_SLOT;
+      const uint32_t T = (cur >> CX_T_SHIFT) & 31u;  // pit*4 + tier
+      const uint32_t row = (side * (MLBSIM_MAX_PITCHERS * MLBSIM_N_TIERS) + T) * MLBSIM_MAX_LINEUP + slot;
+      // Walker alias draw: one shared-memory word per PA
+      const uint32_t col = w0 >> 29;
+      const uint32_t e = lds32(A_ALIAS + ((row * MLBSIM_ROW_WORDS + col) << 2));
+      uint32_t o = ((w0 & 0x1FFFFFFFu) < (e >> 3)) ? col : (e & 7u);
+      if (FATIGUE) {
+        if (T < 4u && cur >= ((uint32_t)(FATIGUE_START + 1) << CX_PC_SHIFT)) {  // starter past 75 pitches
+          const uint32_t ex = (cur >> CX_PC_SHIFT) - FATIGUE_START;
+          const uint32_t srow = (((side * MLBSIM_N_TIERS + T) * MLBSIM_MAX_LINEUP + slot) * MLBSIM_ROW_WORDS) << 2;
+          const uint32_t u = w0 >> 1;
+          o = 0;
+#pragma unroll
+          for (int j = 0; j < 6; ++j) o += (u >= lds32(A_FTHR + srow + 4 * j) + ex * lds32(A_FSLOPE + srow + 4 * j)) ? 1u : 0u;
+        }
+      }
+
+      // base-running sub-draws from w1: A = full 32-bit compare, B = its low 16 bits
+      const uint32_t o4 = o << 2;
+      const uint32_t tA = lds32(A_TA + ((hs & 16u) << 1) + o4);  // [(outs == 2)][outcome]
+      const uint32_t idx = ((hs & HS_OB) << 7) + (o4 << 2) + (w1 < tA ? 8u : 0u) + ((w1 & 0xFFFFu) < T_080_16 ? 4u : 0u);
+      const uint32_t ent = lds32(A_LUT + idx);
+      hs = (hs & HS_KEEP) + HS_PA_ONE + ent;
+
+      if (COUNT_PA) {
+        const uint32_t pa = pa_addr + o * pa_stride;
+        sts32(pa, lds32(pa) + 1u);
+      }
+
+      // next batter, one more pitch (pitch_count counts PAs: half_inning_simulator.py:218-220)
+      cur += CX_NEXT_PA;
+      const uint32_t L = side ? L1 : L0;
+      const bool wrapped = (cur & CX_SLOT) == L;
+      if (wrapped) cur -= L;
+
+      if ((hs & HS_OVER) == 0u) {
+        // TTO (half_inning_simulator.py:177-178): the next PA of this half starts a new pass
+        // through the lineup.  A wrap that coincides with the end of the half does not count:
+        // the next half then starts at index 0, where the reference's `batter_idx > 0` is false.
+        if (wrapped && (cur & CX_TIER_MASK) != CX_TIER_MASK) cur += CX_TIER_ONE;
+      } else {
+        // ---------------- end of half inning ----------------
+        uint32_t runs = (hs >> 16) & 63u;
+        const uint32_t x2 = (uint32_t)(w1_first < T_END_BOTH) + (uint32_t)(w1_first < T_END_ANY);
+        const uint32_t x1 = (uint32_t)(w1_first < T_END_GHOST);
+        const uint32_t extra = (runs == 0u) ? x2 : x1;
+        runs += (hs & HS_REACHED) ? extra : 0u;  // only if a runner reached
+        sc += runs << (side * 16u);
+        const uint32_t a = sc & 0xFFFFu, h = sc >> 16;
+        // first 1/3/5/7 innings: committed when the bottom half of that inning ends (hidx = 1, 5, 9, 13)
+        if ((hidx & 3u) == 1u && hidx < 16u) commit_joint(A_JOINT, H, hidx >> 2, a, h);
+        // game_simulator.py:72 (bottom of the 9th skipped when the home team leads) and :110-111
+        const bool over = ((side != 0u) & (hidx >= 17u) & (a != h)) | ((hidx == 16u) & (h > a));
+        hs = HS_NEW_HALF;
+        if (!over) {
+          ++hidx;
+          const uint32_t t = cur; cur = oth; oth = t;
+          if (COUNT_PA) pa_addr = side ? pa_mine : pa_mine + pa_side;  // `side` is the half that just ended
+          // should_replace_pitcher (game_simulator.py:8-12) for the staff that now takes the mound
+          const uint32_t nb = side ? nb0 : nb1;
+          if (nb != 0u && ((cur & CX_TIER_GE2) != 0u || cur >= ((uint32_t)(PITCH_LIMIT + 1) << CX_PC_SHIFT))) {
+            // stationary law of simulate_reliever_chain: uniform, with replacement.  The half ended on
+            // an out, whose transition ignores the low half of w1 (only singles read it).
+            const uint32_t idx = ((w1 & 0xFFFFu) * nb) >> 16;
+            cur = (cur & CX_SLOT) | ((idx + 1u) << CX_PIT_SHIFT);
+            const uint32_t bit = idx + (side ? 0u : 8u);
+            used |= 1u << bit;
+            red_inc_shared(A_RELP + (bit << 2));
+          }
+        } else {
+          // ---------------- game over: commit ----------------
+          commit_joint(A_JOINT, H, 4u, a, h);
+          const uint32_t inn = (hidx >> 1) + 1u;
+          red_inc_shared(A_INN + ((inn < MLBSIM_INN_BINS - 1 ? inn : MLBSIM_INN_BINS - 1) << 2));
+          uint32_t um = used;
+          while (um) {
+            const int b = __ffs(um) - 1;
+            um &= um - 1;
+            red_inc_shared(A_RELG + (b << 2));
+          }
+          red_inc_shared(A_NG);
+          alive = false;
+        }
+      }
+    }
+    __syncwarp();  // reconverge before the next iteration's ballot: one loop trip = one PA for all lanes
+  }
+}
+
 }  // namespace
 
 extern "C" __global__ void __launch_bounds__(MLBSIM_NATIVE_MAX_THREADS, 1)
 mlbsim_native_kernel(const NativeArgs args) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  Smem& S = *reinterpret_cast<Smem*>(smem_raw);
-  uint32_t* const S_pa = reinterpret_cast<uint32_t*>(smem_raw + sizeof(Smem));
-
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const uint32_t n_sims = args.n_sims;
+  const bool count_pa = (args.flags & 1u) == 0;
 
   // transition LUT + sub-draw thresholds: derived once per block from the branchy semantics above
   for (int i = tid; i < LUT_WORDS; i += blockDim.x) {
-    const int ob = i % 24, sel = i / 24;
-    S.lut[i] = transition_entry(sel >> 2, (sel >> 1) & 1, sel & 1, ob >> 3, ob & 7);
+    const int ob = i >> 5, o = (i >> 2) & 7, dA = (i >> 1) & 1, dB = i & 1;
+    S.lut[i] = transition_entry(o < 7 ? o : MLBSIM_OUT, dA, dB, ob >> 3, ob & 7);
   }
-  if (tid < 16) S.tA[tid] = subdraw_a_threshold(tid >> 1, tid & 1);
+  if (tid < 16) S.tA[tid] = subdraw_a_threshold(tid & 7, tid >> 3);
 
   for (uint32_t step = 0; step < args.n_matchups; ++step) {
     const uint32_t m = (blockIdx.x + step) % args.n_matchups;
@@ -174,6 +387,9 @@ mlbsim_native_kernel(const NativeArgs args) {
       for (int i = tid; i < JOINT_WORDS; i += blockDim.x) S.joint[i] = 0;
       if (tid < MLBSIM_INN_BINS) S.innings[tid] = 0;
       if (tid < 16) { S.rel_games[tid] = 0; S.rel_picks[tid] = 0; }
+      if (count_pa) {
+        for (int f = 0; f < PA_FIELDS; ++f) S_pa[f * blockDim.x + tid] = 0u;
+      }
       if (tid == 0) {
         S.n_games = 0;
         S.hdr_flags = T->flags; S.L0 = T->lineup_len[0]; S.L1 = T->lineup_len[1];
@@ -183,175 +399,23 @@ mlbsim_native_kernel(const NativeArgs args) {
     __syncthreads();
 
     const bool fatigue = (S.hdr_flags & MLBSIM_FLAG_FATIGUE) != 0;
-    const bool count_pa = (args.flags & 1u) == 0;
     const uint32_t L0 = S.L0, L1 = S.L1, nb0 = S.nb0, nb1 = S.nb1;
     const uint32_t rng_matchup = (args.matchup_base + m) << RNG_MATCHUP_SHIFT;
     unsigned long long* const H = args.hist + (size_t)m * MLBSIM_HIST_WORDS;
     unsigned long long* const counter = args.counters + m;
-    // word offsets inside mlbsim_hist
-    constexpr size_t H_INN = (size_t)MLBSIM_N_CAPS * MLBSIM_HIST_BINS * MLBSIM_HIST_BINS;
-    constexpr size_t H_PA = H_INN + MLBSIM_INN_BINS;
-    constexpr size_t H_RELG = H_PA + 16;
-    constexpr size_t H_RELP = H_RELG + 16;
-    constexpr size_t H_N = H_RELP + 16;
 
-    // per-thread PA counters: pa[f][tid], f = side*7 + outcome
-    const uint32_t pa_stride = blockDim.x * 4u;               // bytes between fields
-    const uint32_t pa_side = 7u * pa_stride;                   // bytes between sides
-    unsigned char* const pa_mine = reinterpret_cast<unsigned char*>(S_pa) + tid * 4u;
-    if (count_pa) {
-#pragma unroll
-      for (int f = 0; f < PA_FIELDS; ++f) *reinterpret_cast<uint32_t*>(pa_mine + f * pa_stride) = 0u;
-    }
-
-    // ---- warp-uniform work state ----
-    uint32_t chunk_next = 0, chunk_end = 0;
-    bool exhausted = false;
-
-    // ---- lane state ----
-    bool alive = false;
-    uint32_t c0 = 0, c1 = 0;           // Philox counter: c0 = sim_lo, c1 = draw number | matchup | sim_hi
-    uint32_t cur = 0, oth = 0;         // side contexts: cur = side at bat
-    uint32_t sc = 0;                   // away | home << 16
-    uint32_t hidx = 0;                 // half-inning index: side = hidx & 1, inning = (hidx >> 1) + 1
-    uint32_t hs = 0;                   // half-inning state
-    uint32_t used = 0;                 // reliever bitmasks: home staff bits 0-7, away staff 8-15
-    uint32_t w1_first = 0;             // w1 of the current half's first PA (end-of-half draw)
-
-    for (;;) {
-      // ---------------- refill / termination (warp-synchronous) ----------------
-      const uint32_t need = __ballot_sync(0xffffffffu, !alive);
-      if (need) {
-        if (chunk_next >= chunk_end && !exhausted) {
-          unsigned long long base = 0;
-          if (lane == 0) base = atomicAdd(counter, (unsigned long long)args.chunk);
-          base = __shfl_sync(0xffffffffu, base, 0);
-          if (base >= (unsigned long long)n_sims) {
-            exhausted = true;
-          } else {
-            chunk_next = (uint32_t)base;
-            const unsigned long long e = base + args.chunk;
-            chunk_end = e < (unsigned long long)n_sims ? (uint32_t)e : n_sims;
-          }
-        }
-        const uint32_t avail = chunk_end - chunk_next;
-        const uint32_t rank = __popc(need & lanemask_lt());
-        if (!alive && rank < avail) {
-          const unsigned long long sim = (unsigned long long)args.sim_lo + (chunk_next + rank);
-          c0 = (uint32_t)sim;
-          c1 = ((uint32_t)(sim >> 32) << RNG_SIMHI_SHIFT) | rng_matchup;
-          cur = 0; oth = 0; sc = 0; hidx = 0; hs = 0; used = 0;
-          alive = true;
-        }
-        const uint32_t want = __popc(need);
-        chunk_next += want < avail ? want : avail;
-        if (exhausted && __ballot_sync(0xffffffffu, alive) == 0) break;
-      }
-
-      if (alive) {
-        // ---------------- one plate appearance ----------------
-        uint32_t w0, w1;
-        philox2x32_10(c0, c1, args.keys, w0, w1);
-
-        const uint32_t side = hidx & 1u;
-        const uint32_t slot = cur & CX_SLOT;
-        const bool first_pa = (hs & HS_NPA_MASK) == 0;
-        // The first PA of a half has empty bases, so its w1 never reaches the transition: keep it
-        // as this half's end-of-inning (misc / ghost run) draw.
-        if (first_pa) w1_first = w1;
-        // TTO: half_inning_simulator.py:177-178 — bump when the lineup wraps, except at the very
-        // first PA of a half that starts at slot 0
-        if (slot == 0 && !first_pa && (cur & CX_TIER_MASK) != CX_TIER_MASK) cur += CX_TIER_ONE;
-        const uint32_t T = (cur >> CX_T_SHIFT) & 31u;  // pit*4 + tier
-        const uint32_t row = (side * (MLBSIM_MAX_PITCHERS * MLBSIM_N_TIERS) + T) * MLBSIM_MAX_LINEUP + slot;
-        // Walker alias draw: one shared-memory word per PA
-        const uint32_t col = w0 >> 29;
-        const uint32_t e = S.alias[row * MLBSIM_ROW_WORDS + col];
-        uint32_t o = ((w0 & 0x1FFFFFFFu) < (e >> 3)) ? col : (e & 7u);
-        if (fatigue) {
-          if (T < 4u && cur >= ((uint32_t)(FATIGUE_START + 1) << CX_PC_SHIFT)) {  // starter past 75 pitches
-            const uint32_t ex = (cur >> CX_PC_SHIFT) - FATIGUE_START;
-            const uint32_t srow = ((side * MLBSIM_N_TIERS + T) * MLBSIM_MAX_LINEUP + slot) * MLBSIM_ROW_WORDS;
-            const uint4 ta = *reinterpret_cast<const uint4*>(&S.fthr[srow]);
-            const uint2 tb = *reinterpret_cast<const uint2*>(&S.fthr[srow + 4]);
-            const int4 sa = *reinterpret_cast<const int4*>(&S.fslope[srow]);
-            const int2 sb = *reinterpret_cast<const int2*>(&S.fslope[srow + 4]);
-            const uint32_t u = w0 >> 1;
-            o = (u >= ta.x + ex * (uint32_t)sa.x) + (u >= ta.y + ex * (uint32_t)sa.y) + (u >= ta.z + ex * (uint32_t)sa.z) +
-                (u >= ta.w + ex * (uint32_t)sa.w) + (u >= tb.x + ex * (uint32_t)sb.x) + (u >= tb.y + ex * (uint32_t)sb.y);
-          }
-        }
-
-        // base-running sub-draws from w1: A = full 32-bit compare, B = its low 16 bits
-        const uint32_t ob = hs & HS_OB;
-        const uint32_t tA = S.tA[o * 2u + (ob >> 4)];
-        const uint32_t sel = o * 4u + (w1 < tA ? 2u : 0u) + ((w1 & 0xFFFFu) < T_080_16 ? 1u : 0u);
-        const uint32_t ent = S.lut[sel * 24u + ob];
-        hs = (hs & ~HS_OB) + HS_NPA_ONE + ent;
-
-        if (count_pa) {
-          uint32_t* p = reinterpret_cast<uint32_t*>(pa_mine + (side ? pa_side : 0u) + o * pa_stride);
-          *p += 1u;
-        }
-
-        // next batter, one more pitch (pitch_count counts PAs: half_inning_simulator.py:218-220)
-        cur += CX_NEXT_PA;
-        const uint32_t L = side ? L1 : L0;
-        if ((cur & CX_SLOT) == L) cur -= L;
-
-        // ---------------- end of half inning ----------------
-        if ((hs & HS_OB) >= 24u || (hs & HS_NPA_MASK) >= ((uint32_t)MAX_PA_PER_HALF << 8)) {
-          uint32_t runs = (hs >> 16) & 63u;
-          const uint32_t x2 = (uint32_t)(w1_first < T_END_BOTH) + (uint32_t)(w1_first < T_END_ANY);
-          const uint32_t x1 = (uint32_t)(w1_first < T_END_GHOST);
-          const uint32_t extra = (runs == 0u) ? x2 : x1;
-          runs += (hs >= (1u << 24)) ? extra : 0u;  // only if a runner reached
-          sc += runs << (side * 16u);
-          const uint32_t a = sc & 0xFFFFu, h = sc >> 16;
-          // first 1/3/5/7 innings: committed when the bottom half of that inning ends (hidx = 1, 5, 9, 13)
-          if ((hidx & 3u) == 1u && hidx < 16u) commit_joint(S.joint, H, hidx >> 2, a, h);
-          // game_simulator.py:72 (bottom of the 9th skipped when the home team leads) and :110-111
-          const bool over = ((side != 0u) & (hidx >= 17u) & (a != h)) | ((hidx == 16u) & (h > a));
-          hs = 0;
-          if (!over) {
-            ++hidx;
-            const uint32_t t = cur; cur = oth; oth = t;
-            // should_replace_pitcher (game_simulator.py:8-12) for the staff that now takes the mound
-            const uint32_t nb = side ? nb0 : nb1;  // `side` is the half that just ended
-            if (nb != 0u && ((cur & CX_TIER_GE2) != 0u || cur >= ((uint32_t)(PITCH_LIMIT + 1) << CX_PC_SHIFT))) {
-              // stationary law of simulate_reliever_chain: uniform, with replacement.  The half ended on
-              // an out, whose transition ignores the low half of w1 (only singles read it).
-              const uint32_t idx = ((w1 & 0xFFFFu) * nb) >> 16;
-              cur = (cur & CX_SLOT) | ((idx + 1u) << CX_PIT_SHIFT);
-              const uint32_t bit = idx + (side ? 0u : 8u);
-              used |= 1u << bit;
-              atomicAdd(&S.rel_picks[bit], 1u);
-            }
-          } else {
-            // ---------------- game over: commit ----------------
-            commit_joint(S.joint, H, 4u, a, h);
-            const uint32_t inn = (hidx >> 1) + 1u;
-            atomicAdd(&S.innings[inn < MLBSIM_INN_BINS - 1 ? inn : MLBSIM_INN_BINS - 1], 1u);
-            uint32_t um = used;
-            while (um) {
-              const int b = __ffs(um) - 1;
-              um &= um - 1;
-              atomicAdd(&S.rel_games[b], 1u);
-            }
-            atomicAdd(&S.n_games, 1u);
-            hidx = 0;
-            alive = false;
-          }
-        }
-        ++c1;  // next draw number
-      }
+    if (fatigue) {
+      if (count_pa) play_matchup<true, true>(args, H, counter, rng_matchup, L0, L1, nb0, nb1);
+      else play_matchup<true, false>(args, H, counter, rng_matchup, L0, L1, nb0, nb1);
+    } else {
+      if (count_pa) play_matchup<false, true>(args, H, counter, rng_matchup, L0, L1, nb0, nb1);
+      else play_matchup<false, false>(args, H, counter, rng_matchup, L0, L1, nb0, nb1);
     }
 
     // ---- block flush: shared u32 bins / per-thread counters -> device u64 totals ----
     if (count_pa) {
-#pragma unroll
       for (int f = 0; f < PA_FIELDS; ++f) {
-        const uint32_t v = __reduce_add_sync(0xffffffffu, *reinterpret_cast<uint32_t*>(pa_mine + f * pa_stride));
+        const uint32_t v = __reduce_add_sync(0xffffffffu, S_pa[f * blockDim.x + tid]);
         if (lane == 0 && v) atomicAdd(&H[H_PA + (f / 7) * 8 + (f % 7)], (unsigned long long)v);
       }
     }
@@ -464,4 +528,4 @@ mlbsim_persim_kernel(const PersimArgs args) {
   }
 }
 
-size_t mlbsim_native_smem_bytes(int threads_per_block) { return sizeof(Smem) + (size_t)PA_FIELDS * 4u * (size_t)threads_per_block; }
+size_t mlbsim_native_smem_bytes(int threads_per_block) { return (size_t)PA_FIELDS * 4u * (size_t)threads_per_block; }  // dynamic part only
