@@ -133,5 +133,85 @@ def main():
             make_stats(name, m, noise, args.stats_games, seed=77 + i)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--distribution" not in sys.argv:
     main()
+
+
+# ---------------------------------------------------------------------------------------------
+# N1 fixture: the reference's own reduction / pricing chain on a fixed set of per-sim results
+# ---------------------------------------------------------------------------------------------
+def make_distribution_fixture(n_sims=10000, seed=20250404, game_id="2025-04-04-TEX@HOU"):
+    """Runs the UNMODIFIED `simulate_distribution` (cli/run_distribution_simulator.py:195) with its
+    module-global `simulate_game` replaced by an iterator over per-sim results produced by the
+    oracle's native twin (deterministic: the test regenerates them), and stores what it priced."""
+    import importlib.machinery
+    import shutil
+    import types
+
+    import oracle as orc
+    from mlb_odds_engine_b200 import tables
+
+    rh.load_reference()
+
+    def stub(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        m.__spec__ = importlib.machinery.ModuleSpec(name, None)
+        sys.modules[name] = m
+        return m
+
+    mp = stub("matplotlib"); mp.pyplot = stub("matplotlib.pyplot"); stub("bs4", BeautifulSoup=object)
+    sel = stub("selenium"); sel.webdriver = stub("selenium.webdriver"); stub("selenium.webdriver.chrome")
+    stub("selenium.webdriver.chrome.options", Options=object); stub("selenium.webdriver.chrome.service", Service=object)
+    for extra in ("selenium.webdriver.common", "selenium.webdriver.common.by", "selenium.webdriver.support",
+                  "selenium.webdriver.support.ui", "selenium.webdriver.support.expected_conditions", "dotenv"):
+        if extra not in sys.modules:
+            stub(extra, By=object, WebDriverWait=object, load_dotenv=lambda *a, **k: None)
+    import cli.run_distribution_simulator as rds
+
+    matchup = synth.make_matchup(game_id)
+    table = tables.build_table(matchup)
+    games = orc.native_persim(table, 0, 0, n_sims, seed)
+    names = [[p["name"] for p in matchup["home_bullpen"]], [p["name"] for p in matchup["away_bullpen"]]]
+
+    def results():
+        for g in games:
+            k = int(g["n_innings"])
+            yield {
+                "home_score": int(g["home_score"]), "away_score": int(g["away_score"]),
+                "innings": [{"inning": i + 1, "away_runs": int(g["away_runs"][i]), "home_runs": int(g["home_runs"][i])} for i in range(k)],
+                "used_home_relievers": [names[0][int(x)] for x in g["used_home"][: int(g["n_used"][0])]],
+                "used_away_relievers": [names[1][int(x)] for x in g["used_away"][: int(g["n_used"][1])]],
+            }
+
+    it = results()
+    rds.simulate_game = lambda **kw: next(it)
+    rds.load_all_stats = lambda: ({}, {})
+    starters = {}
+    for side in ("home", "away"):
+        p = dict(matchup[f"{side}_pitcher"])
+        starters[side] = p
+    rds.build_game_assets = lambda gid, bs, ps: {
+        "lineups": {"home": matchup["home_lineup"], "away": matchup["away_lineup"]},
+        "pitchers": starters,
+        "bullpens": {"home": matchup["home_bullpen"], "away": matchup["away_bullpen"]},
+    }
+    os.makedirs("logs", exist_ok=True)
+    shutil.copy(os.path.join(rh.REFERENCE_ROOT, "logs", "calibration_offset.json"), "logs/calibration_offset.json")
+    rds.simulate_distribution(game_id, 9.5, no_weather=True, export_json="./dist_out.json", n_simulations=n_sims)
+    doc = json.load(open("./dist_out.json"))
+    for block in ("raw_distributions", "scaled_distributions"):
+        for v in doc[block].values():
+            v.pop("values", None)
+    fixture = {
+        "game_id": game_id, "n_sims": n_sims, "seed": seed,
+        "calibration": json.load(open("logs/calibration_offset.json")),
+        "doc": doc,
+    }
+    with open(os.path.join(GOLDEN, "distribution_TEXHOU.json"), "w") as f:
+        json.dump(fixture, f, indent=1, sort_keys=True)
+    print(f"distribution fixture: {len(doc['markets'])} market entries, home {doc['home_score']:.3f} away {doc['away_score']:.3f}")
+
+
+if __name__ == "__main__" and "--distribution" in sys.argv:
+    make_distribution_fixture()

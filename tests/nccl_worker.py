@@ -1,0 +1,42 @@
+"""Worker of tests/test_gpu_multi.py: one process per GPU (torchrun), NCCL all-reduce of histograms."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+
+def main():
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import oracle as orc
+    from mlb_odds_engine_b200 import synth
+    from mlb_odds_engine_b200.dist import ShardedSimulator
+
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    S = ShardedSimulator(local)
+    slate = synth.make_slate(n_games=3)
+    slate[1]["home_bullpen"] = None
+    S.load_matchups(slate)
+    n, seed = 300_001, 5
+    tot = S.simulate(n, seed, sim_lo=77)
+    ok = True
+    if dist.get_rank() == 0:
+        for m in range(3):
+            want = orc.native(S.sim._tables[m], m, 77, 77 + n, seed)
+            if tot[m].tobytes() != want.tobytes():
+                ok = False
+                print(f"matchup {m}: all-reduced histogram differs from the oracle", flush=True)
+        print("nccl worker:", "OK" if ok else "MISMATCH", "world", dist.get_world_size(), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
