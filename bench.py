@@ -196,6 +196,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("MLBSIM_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
 
     from mlb_odds_engine_b200 import _abi, tables
@@ -325,7 +326,7 @@ def main():
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32", "data": "synthetic",
         "config": {"workload": wname, "matchups": n_m, "sims_per_matchup_per_gpu_per_step": sims_per_gpu,
-                   "rng": "Philox2x32-10: one block per plate appearance + one per half-inning boundary, counter=(sim, draw, kind, matchup), key=f(seed)",
+                   "rng": "Philox2x32-10, one block per plate appearance, counter=(sim index, PA number, matchup), key=f(seed)",
                    "parallelism": f"sim-index shards x{world}, uint64 histogram all-reduce" if world > 1 else "1 GPU",
                    "l2": "256 MB device buffer rewritten between timed iterations (L2 flush); every step simulates a fresh sim-index range",
                    "threads_per_block": args.threads_per_block or 512, "table_build_ms_once": 1e3 * t_build},
