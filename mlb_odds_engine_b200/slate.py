@@ -1,0 +1,67 @@
+"""Slate runner on the GPU path: replaces the serial per-game loop of `cli/full_slate_runner.py:135-162`
+(one `simulate_distribution` per game id, 10 000 sims each) by ONE multi-matchup launch followed by
+per-game histogram-fed pricing and the same per-game JSON files (`backtest/sims/<date>/<game_id>.json`,
+`cli/run_distribution_simulator.py:797-850`).
+
+Asset building (lineup scraping, probable pitchers, park/weather) stays with the reference's
+network-bound builders (out of scope): callers pass the dicts those
+builders produce (`core/game_asset_builder.py:263-267` + the env dict of
+`cli/run_distribution_simulator.py:335-341`).
+"""
+from __future__ import annotations
+
+import os
+
+from . import distribution, tables
+from .simulator import GpuSimulator
+
+
+def matchup_from_assets(game_id: str, assets: dict, env: dict | None = None, use_noise: bool = True) -> dict:
+    """{"lineups","pitchers","bullpens"} (build_game_assets) -> simulate_game keyword dict."""
+    return {
+        "game_id": game_id,
+        "home_lineup": assets["lineups"]["home"], "away_lineup": assets["lineups"]["away"],
+        "home_pitcher": assets["pitchers"]["home"], "away_pitcher": assets["pitchers"]["away"],
+        "env": env or {},
+        "home_bullpen": assets.get("bullpens", {}).get("home", []),
+        "away_bullpen": assets.get("bullpens", {}).get("away", []),
+        "use_noise": use_noise,
+    }
+
+
+def run_slate(matchups: list[dict], n_sims: int = 10_000, seed: int = 0, calibration: dict | None = None,
+              out_dir: str | None = None, safe: bool = False, sim: GpuSimulator | None = None,
+              start_times: dict | None = None) -> dict:
+    """Simulate every game of the slate in one launch and price it.  `matchups`: simulate_game keyword
+    dicts carrying `game_id`.  Returns {game_id: document}; with `out_dir` also writes
+    `<out_dir>/<date>/<game_id>.json`.  Per-game failures (malformed assets) raise, or with
+    `safe=True` are reported under "failed" and skipped — the semantics of `--safe`
+    (cli/full_slate_runner.py:157-162)."""
+    own = sim is None
+    sim = sim or GpuSimulator(0)
+    built, failed = [], {}
+    for m in matchups:
+        gid = m.get("game_id", f"game{len(built)}")
+        try:
+            built.append((gid, tables.as_matchup(m)))
+        except Exception as e:  # what simulate_game would raise on the first PA
+            if not safe:
+                raise
+            failed[gid] = f"{type(e).__name__}: {e}"
+    docs = {}
+    if built:
+        sim.load_matchups([m for _, m in built])
+        hists = sim.simulate(n_sims, seed=seed)
+        for (gid, _), h in zip(built, hists):
+            doc = distribution.price_from_histogram(h, gid, calibration, (start_times or {}).get(gid))
+            doc["reliever_usage"] = h.reliever_usage()
+            doc["pa_recap"] = h.pa_recap()
+            docs[gid] = doc
+            if out_dir:
+                date_tag = "-".join(gid.split("-")[:3])
+                distribution.write_sim_json(doc, os.path.join(out_dir, date_tag, f"{gid}.json"))
+    if own:
+        sim.close()
+    if failed:
+        docs["failed"] = failed
+    return docs
