@@ -329,7 +329,7 @@ def main():
                    "rng": "Philox2x32-10, one block per plate appearance, counter=(sim index, PA number, matchup), key=f(seed)",
                    "parallelism": f"sim-index shards x{world}, uint64 histogram all-reduce" if world > 1 else "1 GPU",
                    "l2": "256 MB device buffer rewritten between timed iterations (L2 flush); every step simulates a fresh sim-index range",
-                   "threads_per_block": args.threads_per_block or 512, "table_build_ms_once": 1e3 * t_build},
+                   "threads_per_block": args.threads_per_block or 768, "table_build_ms_once": 1e3 * t_build},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(tbl.nbytes),
                 "d2h_bytes_per_step": int(n_m * _abi.HIST_DTYPE.itemsize)},
         "gpu_launches": int(launches),

@@ -20,6 +20,7 @@ OBJ_DIR = os.path.join(PKG, "build")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", INCLUDE] + ARCH
+COMMON += os.environ.get("MLBSIM_NVCC_DEFS", "").split()   # e.g. "-DOPT_ANYSYNC=1" (tuning sweeps)
 UNITS = {
     "native_kernel.cu": [],
     "replay_kernel.cu": ["-fmad=false"],

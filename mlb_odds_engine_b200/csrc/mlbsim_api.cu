@@ -142,7 +142,7 @@ int mlbsim_synchronize(mlbsim_ctx* ctx) {
 int mlbsim_set_launch_config(mlbsim_ctx* ctx, int threads_per_block, int blocks_per_sm) {
   if (!ctx) return MLBSIM_ERR_ARG;
   if (threads_per_block < 0 || threads_per_block > MLBSIM_NATIVE_MAX_THREADS || (threads_per_block % 32) != 0)
-    return fail(ctx, MLBSIM_ERR_ARG, "threads_per_block must be a multiple of 32 in [0, 1024]");
+    return fail(ctx, MLBSIM_ERR_ARG, "threads_per_block must be a multiple of 32 in [0, 768]");
   if (blocks_per_sm < 0 || blocks_per_sm > 32) return fail(ctx, MLBSIM_ERR_ARG, "blocks_per_sm out of range");
   ctx->threads_per_block = threads_per_block;
   ctx->blocks_per_sm = blocks_per_sm;
@@ -191,7 +191,7 @@ static int launch_native(mlbsim_ctx* ctx, int matchup_lo, int matchup_hi, uint64
   if ((unsigned)matchup_hi > RNG_MAX_MATCHUPS) return fail(ctx, MLBSIM_ERR_ARG, "more than 4096 matchups (Philox counter field)");
   if (!hist_dev) return fail(ctx, MLBSIM_ERR_ARG, "hist pointer is NULL");
   const int n_m = matchup_hi - matchup_lo;
-  const int threads = ctx->threads_per_block ? ctx->threads_per_block : 512;
+  const int threads = ctx->threads_per_block ? ctx->threads_per_block : MLBSIM_NATIVE_MAX_THREADS;
   const size_t smem = mlbsim_native_smem_bytes(threads);
   int occ = 0;
   CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mlbsim_native_kernel, threads, smem));

@@ -26,6 +26,29 @@
 #include "native_kernel.h"
 #include "philox.cuh"
 
+// tuning switches (scripts/variant_sweep.sh measures them on the GPU box)
+#ifndef OPT_ANYSYNC
+#define OPT_ANYSYNC 1
+#endif
+#ifndef OPT_RARE_EXTRAS
+#define OPT_RARE_EXTRAS 1
+#endif
+#ifndef OPT_UNROLL
+#define OPT_UNROLL 3   /* plate appearances per refill check (measured: 1 -> 3 = +6 %) */
+#endif
+#ifndef NATIVE_LB_THREADS
+#define NATIVE_LB_THREADS MLBSIM_NATIVE_MAX_THREADS
+#endif
+#ifndef NATIVE_LB_BLOCKS
+#define NATIVE_LB_BLOCKS 2   /* 2 x 768 threads = 48 warps per SM at <= 40 registers (measured best, profiles/r01_variants.txt) */
+#endif
+#ifndef OPT_LAZY_OVER
+#define OPT_LAZY_OVER 0
+#endif
+#ifndef OPT_PASUM
+#define OPT_PASUM 0
+#endif
+
 namespace {
 
 // ---- model constants (reference file:line) ----------------------------------------------------
@@ -120,6 +143,7 @@ constexpr uint32_t HS_KEEP = ~(HS_OB | HS_FRESH);        // hs' = (hs & HS_KEEP)
 constexpr uint32_t HS_PA_ONE = 1u << 8;
 constexpr uint32_t HS_OVER = (1u << 30) | (1u << 14);   // three outs, or 30 PAs
 constexpr uint32_t HS_REACHED = 0x3Fu << 24;
+constexpr uint32_t HS_DEAD = 0xFFFFFFFFu;                // lane has no game (never a live value: ob <= 23)
 
 // LUT entry: new_ob | runs << 16 | reached << 24 | three_outs << 30
 __device__ uint32_t transition_entry(int o, int dA, int dB, int outs, int bases) {
@@ -209,20 +233,25 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
   bool exhausted = false;
 
   // ---- lane state ----
-  bool alive = false;
   uint32_t c0 = 0, c1 = 0;   // Philox counter: c0 = sim_lo, c1 = PA number | matchup | sim_hi
   uint32_t cur = 0, oth = 0; // side contexts: cur = side at bat
   uint32_t sc = 0;           // away | home << 16
   uint32_t hidx = 0;         // half-inning index: side = hidx & 1, inning = (hidx >> 1) + 1
-  uint32_t hs = HS_NEW_HALF; // half-inning state
+  uint32_t hs = HS_DEAD;     // half-inning state; HS_DEAD = this lane has no game
   uint32_t used = 0;         // reliever bitmasks: home staff bits 0-7, away staff 8-15
   uint32_t w1_first = 0;     // w1 of the current half's first PA (end-of-half draw)
   uint32_t pa_addr = pa_mine;  // counters of the side at bat
+  const uint32_t pa_sum = 2u * pa_mine + pa_side;  // pa_addr toggles between pa_mine and pa_mine + pa_side
 
   for (;;) {
     // ---------------- refill / termination (warp-synchronous) ----------------
-    const uint32_t need = __ballot_sync(0xffffffffu, !alive);
+#if OPT_ANYSYNC
+    if (__any_sync(0xffffffffu, hs == HS_DEAD)) {
+      const uint32_t need = __ballot_sync(0xffffffffu, hs == HS_DEAD);
+#else
+    const uint32_t need = __ballot_sync(0xffffffffu, hs == HS_DEAD);
     if (need) {
+#endif
       if (chunk_next >= chunk_end && !exhausted) {
         unsigned long long base = 0;
         if (lane == 0) base = atomicAdd(counter, (unsigned long long)args.chunk);
@@ -237,19 +266,20 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
       }
       const uint32_t avail = chunk_end - chunk_next;
       const uint32_t rank = __popc(need & lanemask_lt());
-      if (!alive && rank < avail) {
+      if (hs == HS_DEAD && rank < avail) {
         const unsigned long long sim = (unsigned long long)args.sim_lo + (chunk_next + rank);
         c0 = (uint32_t)sim;
         c1 = ((uint32_t)(sim >> 32) << RNG_SIMHI_SHIFT) | rng_matchup;
         cur = 0; oth = 0; sc = 0; hidx = 0; hs = HS_NEW_HALF; used = 0; pa_addr = pa_mine;
-        alive = true;
       }
       const uint32_t want = __popc(need);
       chunk_next += want < avail ? want : avail;
-      if (exhausted && __ballot_sync(0xffffffffu, alive) == 0) break;
+      if (exhausted && !__any_sync(0xffffffffu, hs != HS_DEAD)) break;
     }
 
-    if (alive) {
+#pragma unroll
+    for (int rep = 0; rep < OPT_UNROLL; ++rep)
+    if (hs != HS_DEAD) {
       // ---------------- one plate appearance ----------------
       uint32_t w0, w1;
       philox2x32_10(c0, c1, args.keys, w0, w1);
@@ -304,23 +334,45 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
       } else {
         // ---------------- end of half inning ----------------
         uint32_t runs = (hs >> 16) & 63u;
-        const uint32_t x2 = (uint32_t)(w1_first < T_END_BOTH) + (uint32_t)(w1_first < T_END_ANY);
-        const uint32_t x1 = (uint32_t)(w1_first < T_END_GHOST);
-        const uint32_t extra = (runs == 0u) ? x2 : x1;
-        runs += (hs & HS_REACHED) ? extra : 0u;  // only if a runner reached
+        // misc / ghost run (half_inning_simulator.py:12-25): rare (2 %), only if a runner reached.
+        // T_END_BOTH < T_END_GHOST < T_END_ANY, so one compare screens all three.
+#if OPT_RARE_EXTRAS
+        if (w1_first < T_END_ANY && (hs & HS_REACHED) != 0u) {
+          runs += (runs == 0u) ? 1u + (uint32_t)(w1_first < T_END_BOTH) : (uint32_t)(w1_first < T_END_GHOST);
+        }
+#else
+        {
+          const uint32_t x2 = (uint32_t)(w1_first < T_END_BOTH) + (uint32_t)(w1_first < T_END_ANY);
+          const uint32_t x1 = (uint32_t)(w1_first < T_END_GHOST);
+          const uint32_t extra = (runs == 0u) ? x2 : x1;
+          runs += (hs & HS_REACHED) ? extra : 0u;
+        }
+#endif
         sc += runs << (side * 16u);
-        const uint32_t a = sc & 0xFFFFu, h = sc >> 16;
         // first 1/3/5/7 innings: committed when the bottom half of that inning ends (hidx = 1, 5, 9, 13)
-        if ((hidx & 3u) == 1u && hidx < 16u) commit_joint(A_JOINT, H, hidx >> 2, a, h);
+        if ((hidx & 3u) == 1u && hidx < 16u) commit_joint(A_JOINT, H, hidx >> 2, sc & 0xFFFFu, sc >> 16);
         // game_simulator.py:72 (bottom of the 9th skipped when the home team leads) and :110-111
-        const bool over = ((side != 0u) & (hidx >= 17u) & (a != h)) | ((hidx == 16u) & (h > a));
-        hs = HS_NEW_HALF;
+#if OPT_LAZY_OVER
+        bool over = false;
+        if (hidx >= 16u) {
+          const uint32_t a = sc & 0xFFFFu, h = sc >> 16;
+          over = side ? (a != h) : (hidx == 16u && h > a);   // side == 1 here means hidx >= 17
+        }
+#else
+        const uint32_t a_ = sc & 0xFFFFu, h_ = sc >> 16;
+        const bool over = ((side != 0u) & (hidx >= 17u) & (a_ != h_)) | ((hidx == 16u) & (h_ > a_));
+#endif
         if (!over) {
+          hs = HS_NEW_HALF;
           ++hidx;
           const uint32_t t = cur; cur = oth; oth = t;
-          if (COUNT_PA) pa_addr = side ? pa_mine : pa_mine + pa_side;  // `side` is the half that just ended
+#if OPT_PASUM
+          if (COUNT_PA) pa_addr = pa_sum - pa_addr;
+#else
+          if (COUNT_PA) pa_addr = side ? pa_mine : pa_mine + pa_side;
+#endif
           // should_replace_pitcher (game_simulator.py:8-12) for the staff that now takes the mound
-          const uint32_t nb = side ? nb0 : nb1;
+          const uint32_t nb = side ? nb0 : nb1;  // `side` is the half that just ended
           if (nb != 0u && ((cur & CX_TIER_GE2) != 0u || cur >= ((uint32_t)(PITCH_LIMIT + 1) << CX_PC_SHIFT))) {
             // stationary law of simulate_reliever_chain: uniform, with replacement.  The half ended on
             // an out, whose transition ignores the low half of w1 (only singles read it).
@@ -332,7 +384,7 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
           }
         } else {
           // ---------------- game over: commit ----------------
-          commit_joint(A_JOINT, H, 4u, a, h);
+          commit_joint(A_JOINT, H, 4u, sc & 0xFFFFu, sc >> 16);
           const uint32_t inn = (hidx >> 1) + 1u;
           red_inc_shared(A_INN + ((inn < MLBSIM_INN_BINS - 1 ? inn : MLBSIM_INN_BINS - 1) << 2));
           uint32_t um = used;
@@ -342,7 +394,7 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
             red_inc_shared(A_RELG + (b << 2));
           }
           red_inc_shared(A_NG);
-          alive = false;
+          hs = HS_DEAD;
         }
       }
     }
@@ -352,7 +404,7 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
 
 }  // namespace
 
-extern "C" __global__ void __launch_bounds__(MLBSIM_NATIVE_MAX_THREADS, 1)
+extern "C" __global__ void __launch_bounds__(NATIVE_LB_THREADS, NATIVE_LB_BLOCKS)
 mlbsim_native_kernel(const NativeArgs args) {
   const int tid = threadIdx.x;
   const int lane = tid & 31;
