@@ -294,6 +294,7 @@ int mlbsim_run_replay_dev(mlbsim_ctx* ctx, const mlbsim_params* params_host, con
   const long long cap = (long long)ctx->prop.multiProcessorCount * 16;
   if (blocks > cap) blocks = cap;
   CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  CK(ctx, cudaMemsetAsync(out_dev, 0, sizeof(mlbsim_replay_game) * (size_t)n_games, ctx->stream));  // kernel writes non-zero fields only
   mlbsim_replay_kernel<<<(int)blocks, threads, 0, ctx->stream>>>(a);
   CK(ctx, cudaGetLastError());
   CK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));

@@ -241,7 +241,9 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
   uint32_t used = 0;         // reliever bitmasks: home staff bits 0-7, away staff 8-15
   uint32_t w1_first = 0;     // w1 of the current half's first PA (end-of-half draw)
   uint32_t pa_addr = pa_mine;  // counters of the side at bat
+#if OPT_PASUM
   const uint32_t pa_sum = 2u * pa_mine + pa_side;  // pa_addr toggles between pa_mine and pa_mine + pa_side
+#endif
 
   for (;;) {
     // ---------------- refill / termination (warp-synchronous) ----------------

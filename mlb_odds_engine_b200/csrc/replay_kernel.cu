@@ -13,15 +13,37 @@
 #include "../../include/mlbsim.h"
 #include "native_kernel.h"
 
+#ifndef REPLAY_L2_PREFETCH
+#define REPLAY_L2_PREFETCH 256 /* L2 prefetch-size hint of the tape loads: 0 (none), 128 or 256 bytes; 256 = +5 % measured */
+#endif
+
 namespace {
 
+// Sequential reader of one game's float64 tape: one 8-byte read-only load per draw.  Consecutive
+// draws of a lane fall in the same 32-byte sector / 128-byte line, which L1 keeps between them as
+// long as the per-thread footprint stays small — hence no per-thread record in local memory
+// (results go straight to global memory) and a modest number of resident threads per SM.
+// (Measured on B200, 400 k games: an explicit 4-double register buffer with prefetch was 4.5x
+// slower than this — 86 registers and a divergent refill at every call site.)
 struct Tape {
   const double* p;
   uint32_t len;
   uint32_t pos;
+  __device__ __forceinline__ void init(const double* tape, uint64_t, uint64_t lo, uint64_t hi) {
+    p = tape + lo; len = (uint32_t)(hi - lo); pos = 0;
+  }
   __device__ __forceinline__ double next() {
     // past-the-end reads return 0.5 and are flagged by the caller through pos > len
-    const double v = pos < len ? __ldg(p + pos) : 0.5;
+    double v = 0.5;
+    if (pos < len) {
+#if REPLAY_L2_PREFETCH == 256
+      asm volatile("ld.global.nc.L2::256B.f64 %0, [%1];" : "=d"(v) : "l"(p + pos));
+#elif REPLAY_L2_PREFETCH == 128
+      asm volatile("ld.global.nc.L2::128B.f64 %0, [%1];" : "=d"(v) : "l"(p + pos));
+#else
+      v = __ldg(p + pos);
+#endif
+    }
     ++pos;
     return v;
   }
@@ -81,7 +103,8 @@ __device__ int replay_pa(const mlbsim_params& P, Tape& tp, int side, int slot, c
 }
 
 // core/half_inning_simulator.py:138-258
-__device__ int replay_half(const mlbsim_params& P, Tape& tp, int side, int& slot_io, Staff& st, uint16_t* pa_counts) {
+__device__ __forceinline__ int replay_half(const mlbsim_params& P, Tape& tp, int side, int& slot_io, Staff& st,
+                                            unsigned long long& pa_counts) {
   const int L = P.lineup_len[side];
   int outs = 0, runs = 0, n = 0, bases = 0;
   bool reached = false;
@@ -89,7 +112,7 @@ __device__ int replay_half(const mlbsim_params& P, Tape& tp, int side, int& slot
   while (outs < 3 && n < 30) {
     if (bi > 0 && bi % L == 0) st.tto += 1;
     const int o = replay_pa(P, tp, side, bi % L, st);
-    pa_counts[o] += 1;
+    pa_counts += 1ull << (9 * o);   // 9-bit fields: up to 511 of one outcome per side per game
     int r = 0;
     if (o == MLBSIM_K || o == MLBSIM_OUT) {
       if ((bases & 1) && outs < 2 && tp.next() < 0.14) { bases &= ~1; outs += 2; }
@@ -127,7 +150,10 @@ __device__ int replay_half(const mlbsim_params& P, Tape& tp, int side, int& slot
 
 }  // namespace
 
-extern "C" __global__ void __launch_bounds__(128)
+#ifndef REPLAY_MIN_BLOCKS
+#define REPLAY_MIN_BLOCKS 8
+#endif
+extern "C" __global__ void __launch_bounds__(128, REPLAY_MIN_BLOCKS)
 mlbsim_replay_kernel(const ReplayArgs args) {
   __shared__ mlbsim_params P;
   {
@@ -136,59 +162,67 @@ mlbsim_replay_kernel(const ReplayArgs args) {
     for (int i = threadIdx.x; i < (int)(sizeof(mlbsim_params) / 4); i += blockDim.x) dst[i] = src[i];
   }
   __syncthreads();
+  const uint64_t total = args.offsets[args.n_games];
 
+  // `out` was zeroed by the launcher: only non-zero fields are written, straight to global memory
+  // (no per-thread record in local memory).
   for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < args.n_games;
        g += (long long)gridDim.x * blockDim.x) {
-    const uint64_t lo = args.offsets[g], hi = args.offsets[g + 1];
-    Tape tp{args.tape + lo, (uint32_t)(hi - lo), 0u};
-    __align__(16) mlbsim_replay_game R;
-    {
-      uint32_t* z = reinterpret_cast<uint32_t*>(&R);
-#pragma unroll 1
-      for (int i = 0; i < (int)(sizeof(R) / 4); ++i) z[i] = 0;
-    }
-    int score[2] = {0, 0}, slot[2] = {0, 0}, n_used[2] = {0, 0};
-    Staff st[2] = {{0, 1, 0}, {0, 1, 0}};
+    Tape tp;
+    tp.init(args.tape, total, args.offsets[g], args.offsets[g + 1]);
+    mlbsim_replay_game* const R = args.out + g;
+    int status = 0;
+    int score0 = 0, score1 = 0, slot0 = 0, slot1 = 0, used0 = 0, used1 = 0;
+    Staff st0 = {0, 1, 0}, st1 = {0, 1, 0};
+    unsigned long long pa0 = 0, pa1 = 0;
     int inning = 1;
     for (;;) {
-      int r[2] = {0, 0};
-      for (int side = 0; side < 2; ++side) {
-        if (side == 1 && inning == 9 && score[1] > score[0]) break;
-        if ((st[side].pc > 90 || st[side].tto >= 3) && P.bullpen_len[side] > 0) {
+      int r0 = 0, r1 = 0;
+      // ---- top: away bats (side 0) against the home staff ----
+      if ((st0.pc > 90 || st0.tto >= 3) && P.bullpen_len[0] > 0) {
+        int idx = (int)tp.next();
+        const int nb = P.bullpen_len[0];
+        idx = idx < 0 ? 0 : (idx >= nb ? nb - 1 : idx);
+        st0.pit = 1 + idx; st0.pc = 0; st0.tto = 1;
+        if (used0 < MLBSIM_REPLAY_MAX_USED) R->used_home[used0] = (uint8_t)idx; else status |= MLBSIM_ST_USED_OVERFLOW;
+        used0++;
+      }
+      r0 = replay_half(P, tp, 0, slot0, st0, pa0);
+      score0 += r0;
+      // ---- bottom: home bats (side 1) unless it leads after the top of the 9th ----
+      if (!(inning == 9 && score1 > score0)) {
+        if ((st1.pc > 90 || st1.tto >= 3) && P.bullpen_len[1] > 0) {
           int idx = (int)tp.next();
-          const int nb = P.bullpen_len[side];
+          const int nb = P.bullpen_len[1];
           idx = idx < 0 ? 0 : (idx >= nb ? nb - 1 : idx);
-          st[side].pit = 1 + idx; st[side].pc = 0; st[side].tto = 1;
-          uint8_t* used = side == 0 ? R.used_home : R.used_away;
-          if (n_used[side] < MLBSIM_REPLAY_MAX_USED) used[n_used[side]] = (uint8_t)idx;
-          else R.status |= MLBSIM_ST_USED_OVERFLOW;
-          n_used[side]++;
+          st1.pit = 1 + idx; st1.pc = 0; st1.tto = 1;
+          if (used1 < MLBSIM_REPLAY_MAX_USED) R->used_away[used1] = (uint8_t)idx; else status |= MLBSIM_ST_USED_OVERFLOW;
+          used1++;
         }
-        r[side] = replay_half(P, tp, side, slot[side], st[side], R.pa[side]);
-        score[side] += r[side];
+        r1 = replay_half(P, tp, 1, slot1, st1, pa1);
+        score1 += r1;
       }
       if (inning <= MLBSIM_REPLAY_MAX_INNINGS) {
-        R.away_runs[inning - 1] = (uint8_t)(r[0] > 255 ? 255 : r[0]);
-        R.home_runs[inning - 1] = (uint8_t)(r[1] > 255 ? 255 : r[1]);
+        if (r0) R->away_runs[inning - 1] = (uint8_t)(r0 > 255 ? 255 : r0);
+        if (r1) R->home_runs[inning - 1] = (uint8_t)(r1 > 255 ? 255 : r1);
       } else {
-        R.status |= MLBSIM_ST_INNINGS_OVERFLOW;
+        status |= MLBSIM_ST_INNINGS_OVERFLOW;
       }
-      if (inning >= 9 && score[0] != score[1]) break;
+      if (inning >= 9 && score0 != score1) break;
       // a tape that ran dry cannot end the game by itself (0.5 draws): stop after a bound
       if (tp.pos > tp.len && inning >= 200) break;
       inning += 1;
     }
-    R.home_score = score[1];
-    R.away_score = score[0];
-    R.n_innings = inning;
-    R.tape_used = (int32_t)tp.pos;
-    R.n_used[0] = n_used[0];
-    R.n_used[1] = n_used[1];
-    if (tp.pos > tp.len) R.status |= MLBSIM_ST_TAPE_UNDERRUN;
-    // 176-byte records: write as 16-byte vectors (struct is 4-byte aligned fields, 16-byte multiple)
-    const uint4* s4 = reinterpret_cast<const uint4*>(&R);
-    uint4* d4 = reinterpret_cast<uint4*>(args.out + g);
+    if (tp.pos > tp.len) status |= MLBSIM_ST_TAPE_UNDERRUN;
+    int4 head0 = make_int4(score1, score0, inning, (int)tp.pos);
+    int4 head1 = make_int4(used0, used1, status, 0);
+    reinterpret_cast<int4*>(R)[0] = head0;
+    reinterpret_cast<int4*>(R)[1] = head1;
 #pragma unroll
-    for (int i = 0; i < (int)(sizeof(R) / 16); ++i) d4[i] = s4[i];
+    for (int o = 0; o < MLBSIM_N_OUTCOMES; ++o) {
+      const uint16_t c0 = (uint16_t)((pa0 >> (9 * o)) & 511ull), c1 = (uint16_t)((pa1 >> (9 * o)) & 511ull);
+      if (c0) R->pa[0][o] = c0;
+      if (c1) R->pa[1][o] = c1;
+    }
   }
 }
