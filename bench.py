@@ -36,7 +36,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="single", choices=["single", "slate"])
+    ap.add_argument("--workload", default="single", choices=["single", "slate", "sweep"])
     ap.add_argument("--sims", type=int, default=None, help="sims per matchup per GPU per step")
     ap.add_argument("--seed", type=int, default=20250404)
     ap.add_argument("--threads-per-block", type=int, default=0)
@@ -53,10 +53,19 @@ def workload(args):
         ms = [synth.make_matchup("2025-04-04-TEX@HOU")]
         sims = args.sims or 10_000_000
         name = "single game 2025-04-04-TEX@HOU x 10M sims per GPU per step (BASELINE configs[1])"
-    else:
+    elif args.workload == "slate":
         ms = synth.make_slate("2025-04-04", 15)
         sims = args.sims or 1_000_000
         name = "15-game slate x 1M sims per game per GPU per step (BASELINE configs[2])"
+    else:
+        import numpy as np
+        from mlb_odds_engine_b200 import sweep
+
+        base = synth.make_matchup("2025-04-04-TEX@HOU", bullpens=False)   # the tools/ scripts simulate without bullpens
+        ms, _ = sweep.grid_matchups(base, "home", k_rate=np.linspace(0.14, 0.34, 16), bb_rate=np.linspace(0.04, 0.12, 8),
+                                    hr_pa_projected=np.linspace(0.015, 0.06, 8))
+        sims = args.sims or 100_000
+        name = "sensitivity sweep: 1024 grid points (k_rate x bb_rate x hr_pa) x 100k sims per GPU per step (BASELINE configs[4])"
     return ms, sims, name
 
 
@@ -329,7 +338,7 @@ def main():
                    "rng": "Philox2x32-10, one block per plate appearance, counter=(sim index, PA number, matchup), key=f(seed)",
                    "parallelism": f"sim-index shards x{world}, uint64 histogram all-reduce" if world > 1 else "1 GPU",
                    "l2": "256 MB device buffer rewritten between timed iterations (L2 flush); every step simulates a fresh sim-index range",
-                   "threads_per_block": args.threads_per_block or 768, "table_build_ms_once": 1e3 * t_build},
+                   "threads_per_block": args.threads_per_block or 640, "table_build_ms_once": 1e3 * t_build},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(tbl.nbytes),
                 "d2h_bytes_per_step": int(n_m * _abi.HIST_DTYPE.itemsize)},
         "gpu_launches": int(launches),

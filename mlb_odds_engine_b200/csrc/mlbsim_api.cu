@@ -142,7 +142,7 @@ int mlbsim_synchronize(mlbsim_ctx* ctx) {
 int mlbsim_set_launch_config(mlbsim_ctx* ctx, int threads_per_block, int blocks_per_sm) {
   if (!ctx) return MLBSIM_ERR_ARG;
   if (threads_per_block < 0 || threads_per_block > MLBSIM_NATIVE_MAX_THREADS || (threads_per_block % 32) != 0)
-    return fail(ctx, MLBSIM_ERR_ARG, "threads_per_block must be a multiple of 32 in [0, 768]");
+    return fail(ctx, MLBSIM_ERR_ARG, "threads_per_block must be a multiple of 32 in [0, 640]");
   if (blocks_per_sm < 0 || blocks_per_sm > 32) return fail(ctx, MLBSIM_ERR_ARG, "blocks_per_sm out of range");
   ctx->threads_per_block = threads_per_block;
   ctx->blocks_per_sm = blocks_per_sm;

@@ -5,10 +5,13 @@
 // (+ bip_resolution, fatigue_modeling, bullpen_utils.simulate_reliever_chain).
 //
 // Execution model
-//   * one thread = one game at a time, a register-resident state machine; one loop iteration =
-//     one plate appearance for every live lane of the warp (flat loop: half-inning, inning and
-//     game boundaries are predicated blocks inside the iteration, so lanes never wait for each
-//     other at those boundaries);
+//   * one thread = one game at a time, a register-resident state machine.  The warp runs in
+//     ROUNDS: OPT_UNROLL plate-appearance steps (every live lane whose half inning is still
+//     running plays one PA per step: straight-line code, ~31 of 32 lanes active), then ONE
+//     boundary pass for all lanes whose half ended during the round (misc/ghost run, score,
+//     first-1/3/5/7 commits, game-over test, side swap, pitcher hook).  Batching the boundaries
+//     costs a lane at most OPT_UNROLL-1 idle steps per half inning but runs the boundary code
+//     once per round with ~4x more active lanes (measured +11 % over per-PA boundaries);
 //   * a lane that finishes a game immediately starts the next unassigned sim of its warp's
 //     chunk (warp-ballot prefix, no atomics); warps pull chunks of the matchup's sim range
 //     from a global counter.  Sim i draws Philox2x32-10 blocks with counter (i, draw number,
@@ -26,27 +29,16 @@
 #include "native_kernel.h"
 #include "philox.cuh"
 
-// tuning switches (scripts/variant_sweep.sh measures them on the GPU box)
-#ifndef OPT_ANYSYNC
-#define OPT_ANYSYNC 1
-#endif
-#ifndef OPT_RARE_EXTRAS
-#define OPT_RARE_EXTRAS 1
-#endif
+// tuning switches (scripts/variant_sweep.sh rebuilds with -D... and measures on the GPU box;
+// results in profiles/r01_variants.txt)
 #ifndef OPT_UNROLL
-#define OPT_UNROLL 3   /* plate appearances per refill check (measured: 1 -> 3 = +6 %) */
+#define OPT_UNROLL 4   /* plate appearances per round: one refill check and one boundary pass per round */
 #endif
 #ifndef NATIVE_LB_THREADS
 #define NATIVE_LB_THREADS MLBSIM_NATIVE_MAX_THREADS
 #endif
 #ifndef NATIVE_LB_BLOCKS
-#define NATIVE_LB_BLOCKS 2   /* 2 x 768 threads = 48 warps per SM at <= 40 registers (measured best, profiles/r01_variants.txt) */
-#endif
-#ifndef OPT_LAZY_OVER
-#define OPT_LAZY_OVER 0
-#endif
-#ifndef OPT_PASUM
-#define OPT_PASUM 0
+#define NATIVE_LB_BLOCKS 2   /* 2 x 640 threads = 40 warps per SM at <= 48 registers, no spills */
 #endif
 
 namespace {
@@ -143,7 +135,7 @@ constexpr uint32_t HS_KEEP = ~(HS_OB | HS_FRESH);        // hs' = (hs & HS_KEEP)
 constexpr uint32_t HS_PA_ONE = 1u << 8;
 constexpr uint32_t HS_OVER = (1u << 30) | (1u << 14);   // three outs, or 30 PAs
 constexpr uint32_t HS_REACHED = 0x3Fu << 24;
-constexpr uint32_t HS_DEAD = 0xFFFFFFFFu;                // lane has no game (never a live value: ob <= 23)
+constexpr uint32_t HS_DEAD = 1u << 15;                   // lane has no game (bit 15 is outside every live field)
 
 // LUT entry: new_ob | runs << 16 | reached << 24 | three_outs << 30
 __device__ uint32_t transition_entry(int o, int dA, int dB, int outs, int bases) {
@@ -241,19 +233,11 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
   uint32_t used = 0;         // reliever bitmasks: home staff bits 0-7, away staff 8-15
   uint32_t w1_first = 0;     // w1 of the current half's first PA (end-of-half draw)
   uint32_t pa_addr = pa_mine;  // counters of the side at bat
-#if OPT_PASUM
-  const uint32_t pa_sum = 2u * pa_mine + pa_side;  // pa_addr toggles between pa_mine and pa_mine + pa_side
-#endif
 
   for (;;) {
     // ---------------- refill / termination (warp-synchronous) ----------------
-#if OPT_ANYSYNC
     if (__any_sync(0xffffffffu, hs == HS_DEAD)) {
       const uint32_t need = __ballot_sync(0xffffffffu, hs == HS_DEAD);
-#else
-    const uint32_t need = __ballot_sync(0xffffffffu, hs == HS_DEAD);
-    if (need) {
-#endif
       if (chunk_next >= chunk_end && !exhausted) {
         unsigned long long base = 0;
         if (lane == 0) base = atomicAdd(counter, (unsigned long long)args.chunk);
@@ -279,11 +263,12 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
       if (exhausted && !__any_sync(0xffffffffu, hs != HS_DEAD)) break;
     }
 
+    uint32_t w1 = 0, side = 0;
 #pragma unroll
     for (int rep = 0; rep < OPT_UNROLL; ++rep)
-    if (hs != HS_DEAD) {
+    if ((hs & (HS_OVER | HS_DEAD)) == 0u) {   // live lane whose half inning is still running
       // ---------------- one plate appearance ----------------
-      uint32_t w0, w1;
+      uint32_t w0;
       philox2x32_10(c0, c1, args.keys, w0, w1);
       ++c1;
 
@@ -291,7 +276,7 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
       // as this half's end-of-inning (misc / ghost run) draw.
       if ((int)hs < 0) w1_first = w1;
 
-      const uint32_t side = hidx & 1u;
+      side = hidx & 1u;
       const uint32_t slot = cur & CX_SLOT;
       const uint32_t T = (cur >> CX_T_SHIFT) & 31u;  // pit*4 + tier
       const uint32_t row = (side * (MLBSIM_MAX_PITCHERS * MLBSIM_N_TIERS) + T) * MLBSIM_MAX_LINEUP + slot;
@@ -333,46 +318,29 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
         // through the lineup.  A wrap that coincides with the end of the half does not count:
         // the next half then starts at index 0, where the reference's `batter_idx > 0` is false.
         if (wrapped && (cur & CX_TIER_MASK) != CX_TIER_MASK) cur += CX_TIER_ONE;
-      } else {
+      }
+    }
+    if ((hs & HS_OVER) != 0u) {   // (a dead lane has only HS_DEAD set)
+      {
         // ---------------- end of half inning ----------------
+        side = hidx & 1u;
         uint32_t runs = (hs >> 16) & 63u;
         // misc / ghost run (half_inning_simulator.py:12-25): rare (2 %), only if a runner reached.
         // T_END_BOTH < T_END_GHOST < T_END_ANY, so one compare screens all three.
-#if OPT_RARE_EXTRAS
         if (w1_first < T_END_ANY && (hs & HS_REACHED) != 0u) {
           runs += (runs == 0u) ? 1u + (uint32_t)(w1_first < T_END_BOTH) : (uint32_t)(w1_first < T_END_GHOST);
         }
-#else
-        {
-          const uint32_t x2 = (uint32_t)(w1_first < T_END_BOTH) + (uint32_t)(w1_first < T_END_ANY);
-          const uint32_t x1 = (uint32_t)(w1_first < T_END_GHOST);
-          const uint32_t extra = (runs == 0u) ? x2 : x1;
-          runs += (hs & HS_REACHED) ? extra : 0u;
-        }
-#endif
         sc += runs << (side * 16u);
         // first 1/3/5/7 innings: committed when the bottom half of that inning ends (hidx = 1, 5, 9, 13)
         if ((hidx & 3u) == 1u && hidx < 16u) commit_joint(A_JOINT, H, hidx >> 2, sc & 0xFFFFu, sc >> 16);
         // game_simulator.py:72 (bottom of the 9th skipped when the home team leads) and :110-111
-#if OPT_LAZY_OVER
-        bool over = false;
-        if (hidx >= 16u) {
-          const uint32_t a = sc & 0xFFFFu, h = sc >> 16;
-          over = side ? (a != h) : (hidx == 16u && h > a);   // side == 1 here means hidx >= 17
-        }
-#else
         const uint32_t a_ = sc & 0xFFFFu, h_ = sc >> 16;
         const bool over = ((side != 0u) & (hidx >= 17u) & (a_ != h_)) | ((hidx == 16u) & (h_ > a_));
-#endif
         if (!over) {
           hs = HS_NEW_HALF;
           ++hidx;
           const uint32_t t = cur; cur = oth; oth = t;
-#if OPT_PASUM
-          if (COUNT_PA) pa_addr = pa_sum - pa_addr;
-#else
           if (COUNT_PA) pa_addr = side ? pa_mine : pa_mine + pa_side;
-#endif
           // should_replace_pitcher (game_simulator.py:8-12) for the staff that now takes the mound
           const uint32_t nb = side ? nb0 : nb1;  // `side` is the half that just ended
           if (nb != 0u && ((cur & CX_TIER_GE2) != 0u || cur >= ((uint32_t)(PITCH_LIMIT + 1) << CX_PC_SHIFT))) {

@@ -6,7 +6,7 @@
 #include "../../include/mlbsim.h"
 #include "philox.cuh"
 
-#define MLBSIM_NATIVE_MAX_THREADS 768
+#define MLBSIM_NATIVE_MAX_THREADS 640
 
 struct NativeArgs {
   const mlbsim_table* tables;    // device, n_matchups entries (already offset to matchup_lo)

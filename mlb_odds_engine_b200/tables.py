@@ -197,8 +197,33 @@ def _p_k_or_bb_batch(k, bb, use_noise):
     if no_k.any():
         pkbb[no_k] = _expect_clip(None, bb[no_k])
     if both.any():
-        pkbb[both] = _expect_clip(k[both], bb[both])
+        pkbb[both] = _expect_clip_cached(k[both], bb[both])
     return pk, pkbb
+
+
+_CLIP_CACHE: dict = {}
+
+
+def _expect_clip_cached(k, bb):
+    """`_expect_clip` with a (k, bb) -> value memo: slates and sweeps repeat most (batter, pitcher, tier)
+    combinations (a sweep over one pitcher leaves the other 13 pitchers' rows untouched)."""
+    out = np.empty(len(k))
+    miss = []
+    for i, key in enumerate(zip(k.tolist(), bb.tolist())):
+        v = _CLIP_CACHE.get(key)
+        if v is None:
+            miss.append(i)
+        else:
+            out[i] = v
+    if miss:
+        mi = np.array(miss)
+        vals = _expect_clip(k[mi], bb[mi])
+        out[mi] = vals
+        if len(_CLIP_CACHE) > 2_000_000:
+            _CLIP_CACHE.clear()
+        for i, v in zip(miss, vals.tolist()):
+            _CLIP_CACHE[(float(k[i]), float(bb[i]))] = v
+    return out
 
 
 _GL = None

@@ -10,7 +10,7 @@ if [ $TESTS == 1 ]; then
   timeout 1500 python -m pytest tests -m gpu -x -q > $OUT/${TAG}_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -4 $OUT/${TAG}_pytest_gpu.log
 fi
 python bench.py --steps 20 --warmup 3 > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; echo "bench rc=$?"; tail -c 1500 $OUT/${TAG}_bench.json
-for cfg in "256 0" "384 0" "512 0" "768 0" "768 1" "256 3"; do
+for cfg in "256 0" "384 0" "512 0" "640 0" "640 1" "320 4"; do
   set -- $cfg
   python bench.py --steps 5 --warmup 3 --no-cpu-baseline --threads-per-block $1 --blocks-per-sm $2 2>/dev/null | tail -1 > $OUT/_sweep.json
   python - "$1" "$2" <<'PY' >> $OUT/${TAG}_sweep.log
