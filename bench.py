@@ -36,7 +36,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="single", choices=["single", "slate", "sweep"])
+    ap.add_argument("--workload", default="single", choices=["single", "slate", "sweep", "fatigue"])
     ap.add_argument("--sims", type=int, default=None, help="sims per matchup per GPU per step")
     ap.add_argument("--seed", type=int, default=20250404)
     ap.add_argument("--threads-per-block", type=int, default=0)
@@ -53,6 +53,10 @@ def workload(args):
         ms = [synth.make_matchup("2025-04-04-TEX@HOU")]
         sims = args.sims or 10_000_000
         name = "single game 2025-04-04-TEX@HOU x 10M sims per GPU per step (BASELINE configs[1])"
+    elif args.workload == "fatigue":
+        ms = [synth.make_matchup("2025-04-04-TEX@HOU", bullpens=False)]   # starters go the distance: TTO 4+, pitch-count ramp
+        sims = args.sims or 10_000_000
+        name = "fatigue-heavy: single game without bullpens x 10M sims per GPU per step (BASELINE configs[3] shape)"
     elif args.workload == "slate":
         ms = synth.make_slate("2025-04-04", 15)
         sims = args.sims or 1_000_000
@@ -70,57 +74,98 @@ def workload(args):
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock, power and throttle reasons sampled DURING the timed region (B200_PROFILING.md): an
+    in-process NVML thread at 5 ms (nvidia_ml_py), falling back to `nvidia-smi -lms`."""
+    REASONS = (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20))
 
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
-        self.proc = None
-        self.lines = []
+        self.samples = []       # (sm_mhz, power_w, reasons_mask)
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thread = None
+        self._mode = None
+        self._proc = None
+
+    def _nvml_loop(self, h, nv):
+        while not self._stop.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.samples.append((float(sm), float(pw), int(rs)))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
+            import pynvml as nv
+
+            nv.nvmlInit()
+            # torch's device index follows CUDA_VISIBLE_DEVICES; NVML wants the physical device
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = self.gpu
+            if vis:
+                ids = [x for x in vis.split(",") if x.strip() != ""]
+                if self.gpu < len(ids) and ids[self.gpu].strip().isdigit():
+                    phys = int(ids[self.gpu])
+            h = nv.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self._mode = "nvml"
+            self._thread = threading.Thread(target=self._nvml_loop, args=(h, nv), daemon=True)
+            self._thread.start()
+            return
         except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
+            pass
         try:
-            self.proc.wait(timeout=2)
+            q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.sw_power_cap,"
+                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown")
+            self._proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20",
+                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self._mode = "smi"
+            self._thread = threading.Thread(target=self._smi_loop, daemon=True)
+            self._thread.start()
         except Exception:
-            self.proc.kill()
-        sm, mx, power, reasons = [], [], [], set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
+            self._mode = None
+
+    def _smi_loop(self):
+        for line in self._proc.stdout:
+            f = [x.strip() for x in line.split(",")]
             try:
-                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
-            except ValueError:
+                mask = 0
+                for (name, bit), val in zip(self.REASONS, f[3:7]):
+                    if val.lower().startswith("active"):
+                        mask |= bit
+                self.samples.append((float(f[0]), float(f[2]), mask))
+                self.max_mhz = float(f[1])
+            except Exception:
                 continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        # "under load" = samples in the upper half of the observed power range
-        thr = (max(power) + min(power)) / 2 if len(power) > 1 else 0
-        load = [s for s, p in zip(sm, power) if p >= thr] or sm
-        return {"sm_mhz": statistics.median(load), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                "power_w_max": max(power), "samples": len(sm)}
+
+    def mark(self):
+        """Index of the next sample: bracket the timed region with two marks."""
+        return len(self.samples)
+
+    def stop(self, lo=0, hi=None):
+        self._stop.set()
+        if self._proc:
+            self._proc.terminate()
+        if self._thread:
+            self._thread.join(timeout=1.0)
+        if self._mode is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"]}
+        window = self.samples[lo:hi] or self.samples[max(0, lo - 1):]   # a region shorter than one period: nearest sample
+        if not window:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["no samples"]}
+        mask = 0
+        for _, _, r in window:
+            mask |= r
+        return {"sm_mhz": statistics.median(s for s, _, _ in window), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(name for name, bit in self.REASONS if mask & bit),
+                "power_w_max": max(p for _, p, _ in window), "samples": len(window), "source": self._mode}
 
 
 def cpu_port_throughput(matchups, seconds, use_noise=True):
@@ -245,12 +290,13 @@ def main():
             ev[1].record()
 
     # ---------------- device-resident timing ----------------
+    sampler = ClockSampler(local)
+    sampler.start()          # already running through the warm-up, so the timed region is covered from its first ms
     for _ in range(args.warmup):
         device_step()
         flush.fill_(1)
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
+    mark_lo = sampler.mark()
     launches0 = S.ctx.launch_count()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     kev = []
@@ -261,7 +307,7 @@ def main():
     barrier()
     t_wall = time.perf_counter() - t_wall
     launches = S.ctx.launch_count() - launches0
-    clocks = sampler.stop()
+    clocks = sampler.stop(mark_lo, sampler.mark())
     step_ms = [a.elapsed_time(b) for a, b in evs]
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=f"cuda:{local}")
     if world > 1:
