@@ -64,6 +64,22 @@ def scenarios():
     short["away_lineup"][1]["bb_rate"] = 1.9
     short["away_pitcher"]["bb_rate"] = 0.15        # bb >= 1 for one slot -> no draw, walk unless K
     out["short_degenerate"] = (short, True, 60)
+    # the 30-PA cap (half_inning_simulator.py:160,174): the home lineup never makes an out (HR every PA),
+    # so every bottom half ends on the cap; the away side plays normally
+    cap = copy.deepcopy(synth.make_matchup("2025-04-08-ATL@PHI", n_relievers=(2, 3)))
+    for b in cap["home_lineup"]:
+        b["k_rate"] = 0.0
+        b["bb_rate"] = 0.0
+    for p in [cap["away_pitcher"]] + cap["away_bullpen"]:
+        p["k_rate"] = 0.0
+        p["bb_rate"] = 0.0
+        p["hr_pa"] = {"hr_pa_projected": 1.0}
+    out["pa_cap"] = (cap, True, 20)
+    # no noise and no bullpens together (fatigue ramp with deterministic K/BB probabilities)
+    nn = copy.deepcopy(synth.make_matchup("2025-04-09-MIN@DET"))
+    nn["home_bullpen"] = None
+    nn["away_bullpen"] = None
+    out["nonoise_nobullpen"] = (nn, False, 60)
     return out
 
 

@@ -8,7 +8,7 @@ from mlb_odds_engine_b200 import tables
 
 
 def test_golden_fixtures_present():
-    assert len(REPLAY_SCENARIOS) >= 6
+    assert len(REPLAY_SCENARIOS) >= 8
 
 
 @pytest.mark.parametrize("name", REPLAY_SCENARIOS)
