@@ -24,9 +24,10 @@ COMMON += os.environ.get("MLBSIM_NVCC_DEFS", "").split()   # e.g. "-DOPT_ANYSYNC
 UNITS = {
     "native_kernel.cu": [],
     "replay_kernel.cu": ["-fmad=false"],
+    "replay_flat_kernel.cu": ["-fmad=false"],
     "mlbsim_api.cu": [],
 }
-DEPS = ["native_kernel.h", "philox.cuh", os.path.join(INCLUDE, "mlbsim.h")]
+DEPS = ["native_kernel.h", "philox.cuh", "game_rules.cuh", os.path.join(INCLUDE, "mlbsim.h")]
 
 
 def _nvcc() -> str:

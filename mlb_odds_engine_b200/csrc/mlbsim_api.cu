@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -28,6 +29,7 @@ struct mlbsim_ctx {
   uint64_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
+  bool replay_simple = false;  // MLBSIM_REPLAY_KERNEL=simple selects the nested-loop replay kernel
   std::string err;
 };
 
@@ -91,6 +93,10 @@ int mlbsim_init(int device, mlbsim_ctx** out) {
   }
   if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
   ctx->stream = ctx->own_stream;
+  {
+    const char* rk = std::getenv("MLBSIM_REPLAY_KERNEL");
+    ctx->replay_simple = rk && std::strcmp(rk, "simple") == 0;
+  }
   if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return bail("cudaEventCreate", e);
   if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail("cudaEventCreate", e);
   if ((e = cudaMalloc(&ctx->params_dev, sizeof(mlbsim_params))) != cudaSuccess) return bail("cudaMalloc", e);
@@ -289,13 +295,31 @@ int mlbsim_run_replay_dev(mlbsim_ctx* ctx, const mlbsim_params* params_host, con
   CK(ctx, cudaSetDevice(ctx->device));
   CK(ctx, cudaMemcpyAsync(ctx->params_dev, params_host, sizeof(mlbsim_params), cudaMemcpyHostToDevice, ctx->stream));
   ReplayArgs a{ctx->params_dev, tape_dev, tape_offsets_dev, out_dev, (long long)n_games};
-  const int threads = 128;
-  long long blocks = (n_games + threads - 1) / threads;
-  const long long cap = (long long)ctx->prop.multiProcessorCount * 16;
-  if (blocks > cap) blocks = cap;
+  if (n_games >= (1ll << 32)) return fail(ctx, MLBSIM_ERR_ARG, "more than 2^32 - 1 games per replay call");
+  if (ctx->counters_cap < 1) {
+    CK(ctx, cudaMalloc(&ctx->counters_dev, sizeof(unsigned long long)));
+    ctx->counters_cap = 1;
+  }
   CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-  CK(ctx, cudaMemsetAsync(out_dev, 0, sizeof(mlbsim_replay_game) * (size_t)n_games, ctx->stream));  // kernel writes non-zero fields only
-  mlbsim_replay_kernel<<<(int)blocks, threads, 0, ctx->stream>>>(a);
+  CK(ctx, cudaMemsetAsync(out_dev, 0, sizeof(mlbsim_replay_game) * (size_t)n_games, ctx->stream));  // kernels write non-zero fields only
+  if (ctx->replay_simple) {
+    // nested-loop version (one thread walks one game start to finish); kept for A/B measurements
+    const int threads = 128;
+    long long blocks = (n_games + threads - 1) / threads;
+    const long long cap = (long long)ctx->prop.multiProcessorCount * 16;
+    if (blocks > cap) blocks = cap;
+    mlbsim_replay_kernel<<<(int)blocks, threads, 0, ctx->stream>>>(a);
+  } else {
+    const int threads = MLBSIM_REPLAY_FLAT_THREADS;
+    const int grid = ctx->prop.multiProcessorCount * MLBSIM_REPLAY_FLAT_BLOCKS;
+    const long long warps = (long long)grid * (threads / 32);
+    long long chunk = n_games / (warps * 4 + 1);
+    chunk = (chunk / 32) * 32;
+    if (chunk < 32) chunk = 32;
+    if (chunk > 256) chunk = 256;
+    CK(ctx, cudaMemsetAsync(ctx->counters_dev, 0, sizeof(unsigned long long), ctx->stream));
+    mlbsim_replay_flat_kernel<<<grid, threads, 0, ctx->stream>>>(a, ctx->counters_dev, (uint32_t)chunk);
+  }
   CK(ctx, cudaGetLastError());
   CK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
   ctx->timed = true;

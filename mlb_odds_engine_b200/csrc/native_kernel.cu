@@ -26,6 +26,7 @@
 #include <stdint.h>
 
 #include "../../include/mlbsim.h"
+#include "game_rules.cuh"
 #include "native_kernel.h"
 #include "philox.cuh"
 
@@ -33,6 +34,9 @@
 // results in profiles/r01_variants.txt)
 #ifndef OPT_UNROLL
 #define OPT_UNROLL 4   /* plate appearances per round: one refill check and one boundary pass per round */
+#endif
+#ifndef OPT_KEYS_LOCAL
+#define OPT_KEYS_LOCAL 0
 #endif
 #ifndef NATIVE_LB_THREADS
 #define NATIVE_LB_THREADS MLBSIM_NATIVE_MAX_THREADS
@@ -137,32 +141,6 @@ constexpr uint32_t HS_OVER = (1u << 30) | (1u << 14);   // three outs, or 30 PAs
 constexpr uint32_t HS_REACHED = 0x3Fu << 24;
 constexpr uint32_t HS_DEAD = 1u << 15;                   // lane has no game (bit 15 is outside every live field)
 
-// LUT entry: new_ob | runs << 16 | reached << 24 | three_outs << 30
-__device__ uint32_t transition_entry(int o, int dA, int dB, int outs, int bases) {
-  int nb = bases, r = 0, oa = 0;
-  const int on1 = bases & 1, on2 = (bases >> 1) & 1, on3 = (bases >> 2) & 1;
-  if (o == MLBSIM_K || o == MLBSIM_OUT) {  // half_inning_simulator.py:73-82
-    if (on1 && outs < 2 && dA) { nb = bases & 6; oa = 2; } else { oa = 1; }
-  } else if (o == MLBSIM_BB) {             // :84-94
-    r = (bases == 7);
-    nb = 1 | (on1 << 1) | ((on2 | on3) << 2);  // runner on 2B always goes to 3B; 3B holds unless forced
-  } else if (o == MLBSIM_1B) {             // :97-109 (+ :28-39 folded into dA at two outs)
-    r = on3 + (on2 & dA);
-    nb = 1 | ((on1 & dB) << 1) | ((on2 & (dA ^ 1)) << 2);
-  } else if (o == MLBSIM_2B) {             // :112-123
-    r = on3 + on2 + (on1 & dA);
-    nb = 2 | ((on1 & (dA ^ 1)) << 2);
-  } else if (o == MLBSIM_3B) {             // :126-129
-    r = on1 + on2 + on3; nb = 4;
-  } else {                                 // HR :132-136
-    r = on1 + on2 + on3 + 1; nb = 0;
-  }
-  int no = outs + oa;
-  if (no > 3) no = 3;
-  const int reached = (r > 0) || (nb != 0);
-  return (uint32_t)(no * 8 + nb) | ((uint32_t)r << 16) | ((uint32_t)reached << 24) | ((uint32_t)(no == 3) << 30);
-}
-
 // threshold of sub-draw A: double play (K/OUT), runner on 2B scores on a single (0.46 with two
 // outs: 0.4 + 0.6*0.1), runner on 1B scores on a double
 __device__ uint32_t subdraw_a_threshold(int o, int two_outs) {
@@ -220,6 +198,9 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
   const uint32_t pa_side = 7u * pa_stride;     // bytes between sides
   const uint32_t pa_mine = smem_dynamic_base() + threadIdx.x * 4u;
 
+#if OPT_KEYS_LOCAL
+  const Philox2Keys keys = args.keys;
+#endif
   // ---- warp-uniform work state ----
   uint32_t chunk_next = 0, chunk_end = 0;
   bool exhausted = false;
@@ -269,7 +250,11 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
     if ((hs & (HS_OVER | HS_DEAD)) == 0u) {   // live lane whose half inning is still running
       // ---------------- one plate appearance ----------------
       uint32_t w0;
+#if OPT_KEYS_LOCAL
+      philox2x32_10(c0, c1, keys, w0, w1);
+#else
       philox2x32_10(c0, c1, args.keys, w0, w1);
+#endif
       ++c1;
 
       // The first PA of a half has empty bases, so its w1 never reaches the transition: keep it

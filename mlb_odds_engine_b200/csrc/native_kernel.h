@@ -42,5 +42,12 @@ struct PersimArgs {
 extern "C" __global__ void mlbsim_persim_kernel(const PersimArgs args);
 extern "C" __global__ void mlbsim_native_kernel(const NativeArgs args);
 extern "C" __global__ void mlbsim_replay_kernel(const ReplayArgs args);
+extern "C" __global__ void mlbsim_replay_flat_kernel(const ReplayArgs args, unsigned long long* counter, uint32_t chunk);
 #endif
 size_t mlbsim_native_smem_bytes(int threads_per_block);
+#ifndef MLBSIM_REPLAY_FLAT_THREADS
+#define MLBSIM_REPLAY_FLAT_THREADS 256
+#endif
+#ifndef MLBSIM_REPLAY_FLAT_BLOCKS
+#define MLBSIM_REPLAY_FLAT_BLOCKS 6   /* 1536 threads per SM at 40 registers: measured best (profiles/r01_replay_variants.log) */
+#endif

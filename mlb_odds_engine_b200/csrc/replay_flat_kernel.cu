@@ -1,0 +1,265 @@
+// replay_flat_kernel.cu — tape-replay mode, flat-loop version (the default replay kernel).
+//
+// Same contract as replay_kernel.cu (bit-exact integers on the reference's recorded draws,
+// float64 compares, no FMA contraction) but organised like the native kernel: the warp runs in
+// rounds of REPLAY_UNROLL plate-appearance steps followed by one boundary pass, lanes refill by
+// ballot prefix, and inside a PA step every tape read is a PREDICATED load at the lane's own
+// position (`if the reference would draw here: v = tape[pos++]`) instead of a branch — the
+// draw grammar of SURVEY.md §8(c) becomes straight-line code:
+//     [beta_k] [beta_bb] u u_hr [u_bip u_hit (u_hit3 | u_fb [u_fb2])] [h1] [h2] [h3]
+// so lanes that take different paths through core/pa_simulator.py:91-143 and the handlers of
+// core/half_inning_simulator.py:73-136 still execute together.
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/mlbsim.h"
+#include "game_rules.cuh"
+#include "native_kernel.h"
+
+#ifndef REPLAY_UNROLL
+#define REPLAY_UNROLL 4
+#endif
+#define REPLAY_FLAT_THREADS MLBSIM_REPLAY_FLAT_THREADS
+#define REPLAY_FLAT_BLOCKS MLBSIM_REPLAY_FLAT_BLOCKS
+
+namespace {
+
+constexpr int LUT_WORDS = 24 * 8 * 4;  // [outs*8+bases][outcome][dA][dB], same layout as the native kernel
+
+// context word: slot[3:0] | tier[5:4] (min(tto,4)-1) | pit[8:6] | pitch_count[31:9]
+constexpr uint32_t CX_SLOT = 0xFu;
+constexpr uint32_t CX_TIER_ONE = 1u << 4;
+constexpr uint32_t CX_TIER_MASK = 3u << 4;
+constexpr uint32_t CX_TIER_GE2 = 2u << 4;
+constexpr int CX_PIT_SHIFT = 6;
+constexpr int CX_PC_SHIFT = 9;
+constexpr uint32_t CX_NEXT_PA = (1u << CX_PC_SHIFT) + 1u;
+// half state: ob[4:0] | n_pa + 34 [14:8] | runs[21:16] | reached[29:24] | three outs [30]
+constexpr uint32_t HS_OB = 31u;
+constexpr uint32_t HS_NEW_HALF = (64u - 30u) << 8;
+constexpr uint32_t HS_PA_ONE = 1u << 8;
+constexpr uint32_t HS_OVER = (1u << 30) | (1u << 14);
+constexpr uint32_t HS_REACHED = 0x3Fu << 24;
+constexpr uint32_t HS_DEAD = 1u << 15;
+
+struct FlatSmem {
+  mlbsim_params P;
+  uint32_t lut[LUT_WORDS];
+};
+
+__device__ __forceinline__ uint32_t lanemask_lt() {
+  uint32_t m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+
+// predicated tape read: past-the-end reads yield 0.5 (flagged later through pos > len)
+__device__ __forceinline__ double take(const double* p, uint32_t& pos, uint32_t len, bool want) {
+  double v = 0.5;
+  if (want) {
+    if (pos < len) asm volatile("ld.global.nc.L2::256B.f64 %0, [%1];" : "=d"(v) : "l"(p + pos));
+    ++pos;
+  }
+  return v;
+}
+
+}  // namespace
+
+extern "C" __global__ void __launch_bounds__(REPLAY_FLAT_THREADS, REPLAY_FLAT_BLOCKS)
+mlbsim_replay_flat_kernel(const ReplayArgs args, unsigned long long* counter, uint32_t chunk) {
+  __shared__ FlatSmem S;
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(args.params);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&S.P);
+    for (int i = threadIdx.x; i < (int)(sizeof(mlbsim_params) / 4); i += blockDim.x) dst[i] = src[i];
+    for (int i = threadIdx.x; i < LUT_WORDS; i += blockDim.x) {
+      const int ob = i >> 5, o = (i >> 2) & 7, dA = (i >> 1) & 1, dB = i & 1;
+      S.lut[i] = transition_entry(o < 7 ? o : MLBSIM_OUT, dA, dB, ob >> 3, ob & 7);
+    }
+  }
+  __syncthreads();
+  const mlbsim_params& P = S.P;
+  const int lane = threadIdx.x & 31;
+  const uint32_t n_games = (uint32_t)args.n_games;
+  const bool noise = P.use_noise != 0;
+  const uint32_t L0 = (uint32_t)P.lineup_len[0], L1 = (uint32_t)P.lineup_len[1];
+  const uint32_t nb0 = (uint32_t)P.bullpen_len[0], nb1 = (uint32_t)P.bullpen_len[1];
+
+  uint32_t chunk_next = 0, chunk_end = 0;
+  bool exhausted = false;
+
+  // lane state
+  const double* tp = nullptr;
+  uint32_t pos = 0, len = 0, game = 0;
+  uint32_t cur = 0, oth = 0, sc = 0, hidx = 0, hs = HS_DEAD;
+  uint32_t nused = 0;                          // picks so far: home staff [7:0], away staff [15:8]
+  uint32_t status = 0;
+  unsigned long long pa_cur = 0, pa_oth = 0;   // 9-bit outcome counters of the side at bat / the other side
+
+  for (;;) {
+    // ---------------- refill / termination ----------------
+    if (__any_sync(0xffffffffu, hs == HS_DEAD)) {
+      const uint32_t need = __ballot_sync(0xffffffffu, hs == HS_DEAD);
+      if (chunk_next >= chunk_end && !exhausted) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(counter, (unsigned long long)chunk);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= (unsigned long long)n_games) {
+          exhausted = true;
+        } else {
+          chunk_next = (uint32_t)base;
+          const unsigned long long e = base + chunk;
+          chunk_end = e < (unsigned long long)n_games ? (uint32_t)e : n_games;
+        }
+      }
+      const uint32_t avail = chunk_end - chunk_next;
+      const uint32_t rank = __popc(need & lanemask_lt());
+      if (hs == HS_DEAD && rank < avail) {
+        game = chunk_next + rank;
+        const uint64_t lo = args.offsets[game], hi = args.offsets[game + 1];
+        tp = args.tape + lo; len = (uint32_t)(hi - lo); pos = 0;
+        cur = 0; oth = 0; sc = 0; hidx = 0; hs = HS_NEW_HALF; nused = 0; status = 0; pa_cur = 0; pa_oth = 0;
+      }
+      const uint32_t want = __popc(need);
+      chunk_next += want < avail ? want : avail;
+      if (exhausted && !__any_sync(0xffffffffu, hs != HS_DEAD)) break;
+    }
+
+#pragma unroll
+    for (int rep = 0; rep < REPLAY_UNROLL; ++rep)
+    if ((hs & (HS_OVER | HS_DEAD)) == 0u) {
+      // ---------------- one plate appearance (core/pa_simulator.py:91-143) ----------------
+      const uint32_t side = hidx & 1u;
+      const uint32_t slot = cur & CX_SLOT;
+      const uint32_t tier = (cur >> 4) & 3u;
+      const uint32_t pit = (cur >> CX_PIT_SHIFT) & 7u;
+      const int pc = (int)(cur >> CX_PC_SHIFT);
+      // core/fatigue_modeling.py:25-43 — two separate multiplies per rate, in this order
+      const double pen = tier == 0 ? 0.0 : tier == 1 ? 0.015 : tier == 2 ? 0.035 : 0.060;
+      double ak = __dmul_rn(P.pit_k[side][pit], __dsub_rn(1.0, pen));
+      double ab = __dmul_rn(P.pit_bb[side][pit], __dadd_rn(1.0, pen));
+      double fl = __ddiv_rn((double)(pc - 75), 25.0);
+      if (!(fl > 0.0)) fl = 0.0;
+      ak = __dmul_rn(ak, __dsub_rn(1.0, __dmul_rn(0.02, fl)));
+      ab = __dmul_rn(ab, __dadd_rn(1.0, __dmul_rn(0.03, fl)));
+      double k = __dmul_rn(__ddiv_rn(__dadd_rn(P.bat_k[side][slot], ak), 2.0), P.k_mod);
+      double bb = __dmul_rn(__ddiv_rn(__dadd_rn(P.bat_bb[side][slot], ab), 2.0), P.bb_mod);
+      // beta_noise (:23-32): a draw only when 0 < p < 1
+      const double vk = take(tp, pos, len, noise && k > 0.0 && k < 1.0);
+      const double vb = take(tp, pos, len, noise && bb > 0.0 && bb < 1.0);
+      const double kp = noise ? (k <= 0.0 ? 0.0 : k >= 1.0 ? 1.0 : vk) : k;
+      double bp = noise ? (bb <= 0.0 ? 0.0 : bb >= 1.0 ? 1.0 : vb) : bb;
+      bp = __dmul_rn(bp, 1.01);
+      const double u = take(tp, pos, len, true);
+      const double uhr = take(tp, pos, len, true);                     // always consumed (:126)
+      const bool is_k = u < kp;
+      const bool is_bb = !is_k && (u < __dadd_rn(kp, bp));
+      const bool contact = !is_k && !is_bb;
+      const bool is_hr = contact && (uhr < P.pit_hr[side][pit]);
+      const bool bip = contact && !is_hr;
+      // resolve_contact (:51-88)
+      const double ubip = take(tp, pos, len, bip);
+      uint32_t type = (uint32_t)(P.cdf_bip[0] <= ubip) + (uint32_t)(P.cdf_bip[1] <= ubip) + (uint32_t)(P.cdf_bip[2] <= ubip) +
+                      (uint32_t)(P.cdf_bip[3] <= ubip);
+      if (type > 3u) type = 3u;
+      const double uhit = take(tp, pos, len, bip);                     // stdlib stream (core/bip_resolution.py:62)
+      const bool hit = bip && (uhit < P.hit_prob[side][pit][slot][type]);
+      const double u7 = take(tp, pos, len, bip);                       // hit: 1B/2B/3B split; else the 10 % fallback draw
+      const bool fb = bip && !hit && (u7 < 0.10);
+      const double u8 = take(tp, pos, len, fb);
+      uint32_t o = MLBSIM_OUT;
+      if (hit) o = MLBSIM_1B + (uint32_t)(P.cdf_hit[0] <= u7) + (uint32_t)(P.cdf_hit[1] <= u7) + (uint32_t)(P.cdf_hit[2] <= u7);
+      if (fb) o = MLBSIM_1B + (uint32_t)(P.cdf_fb[0] <= u8) + (uint32_t)(P.cdf_fb[1] <= u8);
+      if (is_hr) o = MLBSIM_HR;
+      if (is_bb) o = MLBSIM_BB;
+      if (is_k) o = MLBSIM_K;
+
+      // ---------------- handler draws (core/half_inning_simulator.py:73-136, :28-39) ----------------
+      const uint32_t ob = hs & HS_OB;
+      const uint32_t outs = ob >> 3;
+      const bool on1 = (ob & 1u) != 0, on2 = (ob & 2u) != 0;
+      const bool is_out = (o == MLBSIM_K) || (o == MLBSIM_OUT);
+      const bool is_1b = o == MLBSIM_1B, is_2b = o == MLBSIM_2B;
+      // h1: double-play draw | runner on 2B on a single | runner on 1B on a double
+      const double h1 = take(tp, pos, len, (is_out && on1 && outs < 2u) || (is_1b && on2) || (is_2b && on1));
+      // h2: runner on 1B on a single
+      const double h2 = take(tp, pos, len, is_1b && on1);
+      // h3: two outs, runner from 2B held at 3B on a single
+      const bool held = is_1b && on2 && !(h1 < 0.4);
+      const double h3 = take(tp, pos, len, held && outs == 2u);
+      bool dA;
+      if (is_out) dA = h1 < 0.14;
+      else if (is_1b) dA = (h1 < 0.4) || (held && outs == 2u && h3 < 0.10);
+      else dA = h1 < 0.4;
+      const bool dB = h2 < 0.8;
+      const uint32_t ent = S.lut[(ob << 5) + (o << 2) + (dA ? 2u : 0u) + (dB ? 1u : 0u)];
+      hs = (hs & ~HS_OB) + HS_PA_ONE + ent;
+      pa_cur += 1ull << (9u * o);
+
+      cur += CX_NEXT_PA;
+      const uint32_t L = side ? L1 : L0;
+      const bool wrapped = (cur & CX_SLOT) == L;
+      if (wrapped) cur -= L;
+      if ((hs & HS_OVER) == 0u) {
+        if (wrapped && (cur & CX_TIER_MASK) != CX_TIER_MASK) cur += CX_TIER_ONE;   // :177-178
+      }
+    }
+
+    if ((hs & HS_OVER) != 0u) {
+      // ---------------- end of half inning (:242-250) ----------------
+      const uint32_t side = hidx & 1u;
+      uint32_t runs = (hs >> 16) & 63u;
+      const bool reached = (hs & HS_REACHED) != 0u;
+      const double um = take(tp, pos, len, reached && runs == 0u);
+      if (reached && runs == 0u && um < 0.011) runs += 1u;
+      const double ug = take(tp, pos, len, reached);
+      if (reached && ug < 0.01) runs += 1u;
+      sc += runs << (side * 16u);
+      const uint32_t inning = (hidx >> 1) + 1u;
+      mlbsim_replay_game* const R = args.out + game;
+      if (runs) {
+        if (inning <= MLBSIM_REPLAY_MAX_INNINGS) {
+          uint8_t* dst = side ? R->home_runs : R->away_runs;
+          dst[inning - 1] = (uint8_t)(runs > 255u ? 255u : runs);
+        }
+      }
+      if (inning > MLBSIM_REPLAY_MAX_INNINGS) status |= MLBSIM_ST_INNINGS_OVERFLOW;
+      const uint32_t a = sc & 0xFFFFu, h = sc >> 16;
+      bool over = (side != 0u && hidx >= 17u && a != h) || (hidx == 16u && h > a);
+      // a tape that ran dry cannot end the game by itself (0.5 draws): stop after a bound (as the oracle does)
+      if (side != 0u && pos > len && inning >= 200u) over = true;
+      if (!over) {
+        hs = HS_NEW_HALF;
+        ++hidx;
+        { const uint32_t t = cur; cur = oth; oth = t; }
+        { const unsigned long long t = pa_cur; pa_cur = pa_oth; pa_oth = t; }
+        const uint32_t nb = side ? nb0 : nb1;     // staff that now takes the mound
+        if (nb != 0u && ((cur & CX_TIER_GE2) != 0u || cur >= ((uint32_t)91 << CX_PC_SHIFT))) {   // game_simulator.py:8-12
+          int idx = (int)take(tp, pos, len, true);
+          idx = idx < 0 ? 0 : (idx >= (int)nb ? (int)nb - 1 : idx);
+          cur = (cur & CX_SLOT) | ((uint32_t)(idx + 1) << CX_PIT_SHIFT);
+          const uint32_t sh = side ? 0u : 8u;     // new side 0 -> home staff
+          const uint32_t cnt = (nused >> sh) & 255u;
+          if (cnt < MLBSIM_REPLAY_MAX_USED) (side ? R->used_home : R->used_away)[cnt] = (uint8_t)idx;
+          else status |= MLBSIM_ST_USED_OVERFLOW;
+          nused += 1u << sh;
+        }
+      } else {
+        if (pos > len) status |= MLBSIM_ST_TAPE_UNDERRUN;
+        // side at bat when the game ended: pa_cur belongs to it
+        const unsigned long long pa0 = side ? pa_oth : pa_cur, pa1 = side ? pa_cur : pa_oth;
+        reinterpret_cast<int4*>(R)[0] = make_int4((int)h, (int)a, (int)inning, (int)pos);
+        reinterpret_cast<int4*>(R)[1] = make_int4((int)(nused & 255u), (int)((nused >> 8) & 255u), (int)status, 0);
+#pragma unroll
+        for (int o = 0; o < MLBSIM_N_OUTCOMES; ++o) {
+          const uint16_t c0 = (uint16_t)((pa0 >> (9 * o)) & 511ull), c1 = (uint16_t)((pa1 >> (9 * o)) & 511ull);
+          if (c0) R->pa[0][o] = c0;
+          if (c1) R->pa[1][o] = c1;
+        }
+        hs = HS_DEAD;
+      }
+    }
+    __syncwarp();
+  }
+}
