@@ -357,9 +357,15 @@ def main():
     peak_tinst = info["sm_count"] * 4 * 32 * sm_max_mhz * 1e6 / 1e12   # thread-instr/s, all 4 schedulers issuing every cycle
     achieved_tinst = per_gpu_rate_kernel * I_ALG / 1e12
     hbm_bytes_per_launch = n_m * (_abi.TABLE_DTYPE.itemsize + _abi.HIST_DTYPE.itemsize)
+    traffic = None
+    try:   # DRAM bytes of one launch from the committed ncu --set full capture (independent of the sim count: tables + flush)
+        with open(os.path.join(ROOT, "profiles", "native_ncu_traffic.json")) as f:
+            traffic = json.load(f)["dram_bytes_per_launch"]
+    except Exception:
+        pass
     roofline = {
         "bound": "issue", "achieved": achieved_tinst, "peak": peak_tinst, "unit": "Tinst/s (thread instructions)",
-        "frac": achieved_tinst / peak_tinst, "traffic": None,
+        "frac": achieved_tinst / peak_tinst, "traffic": traffic,
         "kernel": "mlbsim_native_kernel", "kernel_ms": kern_ms, "games_per_launch": n_m * sims_per_gpu,
         "i_alg_thread_instr_per_game": I_ALG,
         "peak_source": f"{info['sm_count']} SMs x 4 schedulers x 32 lanes x {sm_max_mhz:.0f} MHz (MEASURED_PEAKS.json sm_max_mhz)",

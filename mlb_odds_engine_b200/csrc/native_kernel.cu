@@ -35,9 +35,6 @@
 #ifndef OPT_UNROLL
 #define OPT_UNROLL 4   /* plate appearances per round: one refill check and one boundary pass per round */
 #endif
-#ifndef OPT_KEYS_LOCAL
-#define OPT_KEYS_LOCAL 0
-#endif
 #ifndef NATIVE_LB_THREADS
 #define NATIVE_LB_THREADS MLBSIM_NATIVE_MAX_THREADS
 #endif
@@ -198,9 +195,6 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
   const uint32_t pa_side = 7u * pa_stride;     // bytes between sides
   const uint32_t pa_mine = smem_dynamic_base() + threadIdx.x * 4u;
 
-#if OPT_KEYS_LOCAL
-  const Philox2Keys keys = args.keys;
-#endif
   // ---- warp-uniform work state ----
   uint32_t chunk_next = 0, chunk_end = 0;
   bool exhausted = false;
@@ -250,11 +244,7 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
     if ((hs & (HS_OVER | HS_DEAD)) == 0u) {   // live lane whose half inning is still running
       // ---------------- one plate appearance ----------------
       uint32_t w0;
-#if OPT_KEYS_LOCAL
-      philox2x32_10(c0, c1, keys, w0, w1);
-#else
       philox2x32_10(c0, c1, args.keys, w0, w1);
-#endif
       ++c1;
 
       // The first PA of a half has empty bases, so its w1 never reaches the transition: keep it
