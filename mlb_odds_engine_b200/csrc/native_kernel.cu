@@ -189,7 +189,6 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
   const uint32_t A_INN = sb + (uint32_t)offsetof(Smem, innings);
   const uint32_t A_RELG = sb + (uint32_t)offsetof(Smem, rel_games);
   const uint32_t A_RELP = sb + (uint32_t)offsetof(Smem, rel_picks);
-  const uint32_t A_NG = sb + (uint32_t)offsetof(Smem, n_games);
   // per-thread PA counters: pa[f][tid], f = side*7 + outcome
   const uint32_t pa_stride = blockDim.x * 4u;  // bytes between outcomes
   const uint32_t pa_side = 7u * pa_stride;     // bytes between sides
@@ -324,6 +323,9 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
             const uint32_t idx = ((w1 & 0xFFFFu) * nb) >> 16;
             cur = (cur & CX_SLOT) | ((idx + 1u) << CX_PIT_SHIFT);
             const uint32_t bit = idx + (side ? 0u : 8u);
+            // "sims in which reliever i appeared" (run_distribution_simulator.py:391-397): count his first
+            // appearance in this game here rather than walking the mask when the game ends
+            if (((used >> bit) & 1u) == 0u) red_inc_shared(A_RELG + (bit << 2));
             used |= 1u << bit;
             red_inc_shared(A_RELP + (bit << 2));
           }
@@ -332,13 +334,6 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
           commit_joint(A_JOINT, H, 4u, sc & 0xFFFFu, sc >> 16);
           const uint32_t inn = (hidx >> 1) + 1u;
           red_inc_shared(A_INN + ((inn < MLBSIM_INN_BINS - 1 ? inn : MLBSIM_INN_BINS - 1) << 2));
-          uint32_t um = used;
-          while (um) {
-            const int b = __ffs(um) - 1;
-            um &= um - 1;
-            red_inc_shared(A_RELG + (b << 2));
-          }
-          red_inc_shared(A_NG);
           hs = HS_DEAD;
         }
       }
@@ -424,12 +419,16 @@ mlbsim_native_kernel(const NativeArgs args) {
         atomicAdd(&H[((size_t)c * MLBSIM_HIST_BINS + a) * MLBSIM_HIST_BINS + h], (unsigned long long)v);
       }
     }
-    if (tid < MLBSIM_INN_BINS && S.innings[tid]) atomicAdd(&H[H_INN + tid], (unsigned long long)S.innings[tid]);
+    if (tid < MLBSIM_INN_BINS) {
+      const uint32_t v = S.innings[tid];
+      if (v) atomicAdd(&H[H_INN + tid], (unsigned long long)v);
+      const uint32_t games = __reduce_add_sync(0xffffffffu, v);   // every finished game sits in exactly one innings bin
+      if (tid == 0 && games) atomicAdd(&H[H_N], (unsigned long long)games);
+    }
     if (tid < 16) {
       if (S.rel_games[tid]) atomicAdd(&H[H_RELG + tid], (unsigned long long)S.rel_games[tid]);
       if (S.rel_picks[tid]) atomicAdd(&H[H_RELP + tid], (unsigned long long)S.rel_picks[tid]);
     }
-    if (tid == 0 && S.n_games) atomicAdd(&H[H_N], (unsigned long long)S.n_games);
   }
 }
 
