@@ -202,10 +202,12 @@ def run_reference(args):
     ms, sims, name = workload(args)
     cores = orc.get_threads()
     params = [tables.build_params(m) for m in ms]
-    # each step = a bounded sample of the workload: ~2 s of CPU work
+    # each step = a bounded sample of the workload: ~2 s of CPU work, less when K is large so that the
+    # whole run (warm-up + K steps) stays around two minutes
     probe_n = 20_000
     t = time.perf_counter(); orc.grammar(params[0], 1, 0, probe_n); rate = probe_n / (time.perf_counter() - t)
-    per_step = max(10_000, int(rate * 2.0 / len(params)))
+    step_seconds = min(2.0, 120.0 / max(1, args.steps + args.warmup))
+    per_step = max(2_000, int(rate * step_seconds / len(params)))
     lo = 0
     for _ in range(args.warmup):
         for p in params:
