@@ -15,14 +15,24 @@ import itertools
 
 import numpy as np
 
-from . import _abi
+from . import _abi, assets
 from .simulator import GpuSimulator
 
+# pitcher fields that reach the simulation only through `project_hr_pa` (core/project_hr_pa.py:57-89)
+UPSTREAM_FIELDS = frozenset({"stuff_plus", "location_plus", "barrel_batted_rate", "xSLG", "xwOBAcon", "sweet_spot_pct",
+                             "xSLG_diff", "wOBAdiff", "K_pct", "BB_pct", "FIP", "TBF", "league_avg_hr_pa"})
 
-def grid_matchups(base: dict, side: str = "home", **axes) -> tuple[list[dict], list[dict]]:
+
+def grid_matchups(base: dict, side: str = "home", project: bool = False, **axes) -> tuple[list[dict], list[dict]]:
     """Cartesian grid over pitcher fields of `base[f"{side}_pitcher"]`; `hr_pa_projected` addresses the
-    nested `hr_pa` dict.  Returns (matchups, points)."""
+    nested `hr_pa` dict.  With `project=True` every grid point's `hr_pa` is recomputed with
+    `assets.project_hr_pa` after the fields are set — what `build_game_assets` does for a real pitcher
+    (core/game_asset_builder.py:214) — so upstream knobs (Stuff+, Location+, barrel rate, ...) move the
+    tables; EV / LA then act twice, through the projection and through BIP resolution, as in the reference.
+    Returns (matchups, points)."""
     names = list(axes)
+    if project and "hr_pa_projected" in names:
+        raise ValueError("hr_pa_projected cannot be a grid axis when project=True (it is recomputed)")
     out, points = [], []
     for combo in itertools.product(*(axes[n] for n in names)):
         m = copy.deepcopy(base)
@@ -32,9 +42,41 @@ def grid_matchups(base: dict, side: str = "home", **axes) -> tuple[list[dict], l
                 p.setdefault("hr_pa", {})["hr_pa_projected"] = float(v)
             else:
                 p[n] = float(v)
+        if project:
+            p["hr_pa"] = assets.project_hr_pa(p, mutate=False)
         out.append(m)
         points.append(dict(zip(names, (float(v) for v in combo))))
     return out, points
+
+
+def sensitivity_matchups(field: str, values, project: bool = False) -> list[dict]:
+    """The matchups of `tools/test_<field>_sensitivity.py:10-66`: nine copies of the league-average batter on
+    both sides, the same template pitcher (K 22.5 %, BB 8.2 %, no `hr_pa` ⇒ the 0.046 default, no EV / LA) on both
+    mounds with `field` set to each value, neutral env, no bullpens.  In the reference these sweeps are flat for
+    stuff_plus / command_plus / location_plus / hr_fb_rate / iso_allowed because nothing on the hot path reads
+    them; `project=True` routes them through the HR/PA projection instead."""
+    batter = {"name": "avg_batter", "handedness": "R", "k_rate": 0.225, "bb_rate": 0.082, "iso": 0.145,
+              "avg": 0.245, "woba": 0.320}
+    env = {"park_hr_mult": 1.0, "single_mult": 1.0, "weather_hr_mult": 1.0, "adi_mult": 1.0,
+           "umpire": {"K": 1.0, "BB": 1.0}}
+    out = []
+    for v in values:
+        pit = {"name": f"{field}_{v}", "throws": "R", "stuff_plus": 100, "command_plus": 100, "location_plus": 100,
+               "k_rate": 0.225, "bb_rate": 0.082, "hr_fb_rate": 0.115, "iso_allowed": 0.140}
+        pit[field] = v
+        if project:
+            pit["hr_pa"] = assets.project_hr_pa(pit, mutate=False)
+        out.append({"game_id": f"{field}={v}", "home_lineup": [dict(batter) for _ in range(9)],
+                    "away_lineup": [dict(batter) for _ in range(9)], "home_pitcher": dict(pit),
+                    "away_pitcher": dict(pit), "env": env, "home_bullpen": None, "away_bullpen": None})
+    return out
+
+
+def pooled_rates(row: dict) -> dict:
+    """HOME + AWAY outcome percentages as the tools print them (tools/test_stuff_plus_sensitivity.py:71-85)."""
+    n = {o: row["counts"]["HOME"][o] + row["counts"]["AWAY"][o] for o in _abi.OUTCOMES}
+    total = sum(n.values())
+    return {o: (100.0 * c / total if total else 0.0) for o, c in n.items()}
 
 
 def run_sweep(matchups: list[dict], n_sims: int = 100_000, seed: int = 0, sim: GpuSimulator | None = None,
@@ -50,6 +92,8 @@ def run_sweep(matchups: list[dict], n_sims: int = 100_000, seed: int = 0, sim: G
         pa = h.rec["pa"][:, :7].astype(np.float64)
         home_mean, away_mean = h.mean_scores()
         rows.append({
+            "counts": {team: {o: int(pa[s, i]) for i, o in enumerate(_abi.OUTCOMES)}
+                       for s, team in ((0, "AWAY"), (1, "HOME"))},
             "rates": {team: {o: float(pa[s, i] / max(pa[s].sum(), 1.0)) for i, o in enumerate(_abi.OUTCOMES)}
                       for s, team in ((0, "AWAY"), (1, "HOME"))},
             "pa_per_game": float(pa.sum() / h.n_games),

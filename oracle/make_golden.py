@@ -149,7 +149,7 @@ def main():
             make_stats(name, m, noise, args.stats_games, seed=77 + i)
 
 
-if __name__ == "__main__" and "--distribution" not in sys.argv:
+if __name__ == "__main__" and "--distribution" not in sys.argv and "--assets" not in sys.argv:
     main()
 
 
@@ -231,3 +231,85 @@ def make_distribution_fixture(n_sims=10000, seed=20250404, game_id="2025-04-04-T
 
 if __name__ == "__main__" and "--distribution" in sys.argv:
     make_distribution_fixture()
+
+
+# ---------------------------------------------------------------------------------------------
+# N3 fixture: the reference's HR/PA projection and bullpen builder on seeded stats rows
+# ---------------------------------------------------------------------------------------------
+def make_assets_fixture(n_pitchers=300, seed=20250405):
+    """Calls the UNMODIFIED `project_hr_pa` (core/project_hr_pa.py:46) and `build_bullpen_for_team`
+    (assets/bullpen_utils.py:19; its network lookup of today's starters replaced by an empty dict) on
+    seeded synthetic stats rows and stores inputs + outputs as JSON (floats round-trip exactly)."""
+    import copy, contextlib, io, json, math
+    mods = rh.load_reference()
+    rng = np.random.default_rng(seed)
+    opt = {"xSLG": (0.3, 0.5), "xwOBAcon": (0.3, 0.45), "sweet_spot_pct": (0.25, 0.4), "xSLG_diff": (-0.05, 0.05),
+           "wOBAdiff": (-0.04, 0.04), "K_pct": (0.12, 0.36), "BB_pct": (0.03, 0.14), "FIP": (2.5, 5.5),
+           "location_plus": (80.0, 120.0)}
+    rows = []
+    for i in range(n_pitchers):
+        tbf = float(rng.choice([0, 1, 37, 180, 499, 500, 650, 699, 700, 899, 900, 1100]))
+        p = {"name": f"Pitcher {i}", "role": "RP" if rng.random() < 0.5 else "SP",
+             "stuff_plus": float(rng.choice([70, 90, 90.5, 95, 95.5, 100, 104.2, 110, 115, 120, 131.7])),
+             "HR": float(rng.integers(0, 40)), "TBF": tbf, "IP": float(rng.choice([0, 1, 55.3, 180.1])),
+             "barrel_batted_rate": float(rng.uniform(0.02, 0.12)), "exit_velocity_avg": float(rng.normal(88.5, 2)),
+             "launch_angle_avg": float(rng.normal(13, 4))}
+        for k, (lo, hi) in opt.items():
+            if rng.random() < 0.5:
+                p[k] = float(rng.uniform(lo, hi))
+        quirk = rng.integers(0, 12)
+        if quirk == 0:
+            p["exit_velocity_avg"] = "N/A"
+        elif quirk == 1:
+            p["launch_angle_avg"] = None
+        elif quirk == 2:
+            p["barrel_batted_rate"] = float("nan")
+        elif quirk == 3:
+            del p["role"], p["stuff_plus"]
+        elif quirk == 4:
+            p["league_avg_hr_pa"] = 0.0275
+        elif quirk == 5:
+            del p["TBF"], p["IP"], p["HR"]
+        rows.append(p)
+    proj = []
+    with contextlib.redirect_stdout(io.StringIO()):
+        for p in rows:
+            proj.append(mods.php.project_hr_pa(copy.deepcopy(p)))
+
+    # bullpen builder: 3 teams x 10 candidate rows, some unusable
+    bu = mods.bu
+    bu.fetch_probable_pitchers = lambda: {"g": {"home": {"name": "AAA Arm 0"}, "away": {"name": "Nobody"}}}
+    stats = {}
+    for team in ("AAA", "BBB", "CCC"):
+        for j in range(10):
+            r = {"name": f"{team} Arm {j}", "team_abbr": team, "throws": "L" if j % 3 == 0 else "R",
+                 "k_rate": float(rng.uniform(0.15, 0.35)), "bb_rate": float(rng.uniform(0.04, 0.14)),
+                 "hr_fb_rate": float(rng.choice([0.09, 11.5, 14.0, 0.13])), "stuff_plus": float(rng.normal(100, 12)),
+                 "command_plus": float(rng.normal(100, 8)), "location_plus": float(rng.normal(100, 8)),
+                 "barrel_batted_rate": float(rng.uniform(0.03, 0.1)), "exit_velocity_avg": float(rng.normal(88, 2)),
+                 "launch_angle_avg": float(rng.normal(13, 3)), "HR": float(rng.integers(0, 12)),
+                 "TBF": float(rng.integers(0, 320))}
+            if j == 4:
+                r["stuff_plus"] = None
+            if j == 5:
+                r["hr_fb_rate"] = float("nan")
+            if j == 6:
+                del r["k_rate"], r["exit_velocity_avg"], r["TBF"]
+            if j == 7:
+                r["bb_rate"] = "bad"
+            stats[bu.normalize_name(r["name"])] = r
+    pens = {}
+    with contextlib.redirect_stdout(io.StringIO()):
+        for team in ("AAA", "BBB", "CCC"):
+            pens[team] = bu.build_bullpen_for_team(team, copy.deepcopy(stats), None)
+        pens["AAA_top3"] = bu.build_bullpen_for_team("AAA", copy.deepcopy(stats), None, max_relievers=3)
+    out = {"generator": "oracle/make_golden.py --assets", "seed": seed, "pitchers": rows, "projections": proj,
+           "pitcher_stats": stats, "excluded_starters": [bu.normalize_name("AAA Arm 0")], "bullpens": pens}
+    path = os.path.join(GOLDEN, "assets_hr_pa_bullpen.json")
+    with open(path, "w") as f:
+        json.dump(out, f, indent=0)
+    print(f"wrote {path}: {len(rows)} projections, {sum(len(v) for v in pens.values())} bullpen entries")
+
+
+if __name__ == "__main__" and "--assets" in sys.argv:
+    make_assets_fixture()
