@@ -20,6 +20,9 @@ from __future__ import annotations
 
 import math
 
+import copy
+import os
+
 import numpy as np
 
 from . import _abi
@@ -227,17 +230,35 @@ def _expect_clip_cached(k, bb):
 
 
 _GL = None
+_CLIP_THREADS = max(1, min(16, (os.cpu_count() or 1)))
 
 
 def _gauss_legendre_01():
     global _GL
     if _GL is None:
-        nodes, weights = np.polynomial.legendre.leggauss(96)   # 64 nodes already agree with 400 to 4e-15
+        nodes, weights = np.polynomial.legendre.leggauss(48)   # agrees with 400 nodes to 7e-15 (32: 2e-12)
         _GL = (0.5 * (nodes + 1.0), 0.5 * weights)
     return _GL
 
 
 def _expect_clip(k, bb):
+    """`_expect_clip_rows` over the host's cores for large batches (the special-function loops release the GIL)."""
+    n = len(np.atleast_1d(bb))
+    workers = min(_CLIP_THREADS, n // 128)
+    if workers < 2:
+        return _expect_clip_rows(k, bb)
+    from concurrent.futures import ThreadPoolExecutor
+
+    bb = np.atleast_1d(np.asarray(bb, dtype=np.float64))
+    k = None if k is None else np.atleast_1d(np.asarray(k, dtype=np.float64))
+    cuts = np.linspace(0, n, workers + 1).astype(int)
+    with ThreadPoolExecutor(workers) as pool:
+        parts = pool.map(lambda i: _expect_clip_rows(None if k is None else k[cuts[i]:cuts[i + 1]],
+                                                     bb[cuts[i]:cuts[i + 1]]), range(workers))
+        return np.concatenate(list(parts))
+
+
+def _expect_clip_rows(k, bb):
     """E[min(1, X + 1.01*Y)] for arrays k, bb: X ~ Beta(30k, 30(1-k)) (X = 0 if k is None),
     Y ~ Beta(30bb, 30(1-bb)).  For realistic rates the clip term is ~1e-11 and the result equals
     k + 1.01*bb to ten digits; for extreme grid points (k = 0.5, bb = 0.3: 0.4 %) it matters
@@ -263,19 +284,24 @@ def _expect_clip(k, bb):
     return np.clip(mean - np.sum(wy * excess, axis=1), 0.0, 1.0)
 
 
+def _effective_rates(m: Matchup, side, pit, tier, slot, pitch_count):
+    """Per-PA K and BB rates before noise: fatigue-adjusted pitcher rate averaged with the batter's, times the
+    umpire modifiers (core/fatigue_modeling.py:23-43 then core/pa_simulator.py:108-114)."""
+    pc = np.asarray(pitch_count, dtype=np.float64)
+    pen = np.asarray(TTO_PENALTY)[tier]
+    fl = np.maximum(0.0, (pc - FATIGUE_START) / 25)
+    ak = m.pit_k[side, pit] * (1 - pen) * (1.0 - 0.02 * fl)
+    ab = m.pit_bb[side, pit] * (1 + pen) * (1.0 + 0.03 * fl)
+    return (m.bat_k[side, slot] + ak) / 2 * m.k_mod, (m.bat_bb[side, slot] + ab) / 2 * m.bb_mod
+
+
 def outcome_cdf_batch(m: Matchup, side, pit, tier, slot, pitch_count, use_noise=None):
     """Rows of cumulative P over [K, BB, 1B, 2B, 3B, HR] (OUT is the remainder) for arrays of PA
     contexts — the marginal law of core/pa_simulator.py:91-143 + core/bip_resolution.py +
     core/fatigue_modeling.py.  Returns float64 [N, 6]."""
     use_noise = m.use_noise if use_noise is None else use_noise
     side, pit, tier, slot = (np.asarray(x, dtype=np.int64) for x in (side, pit, tier, slot))
-    pc = np.asarray(pitch_count, dtype=np.float64)
-    pen = np.asarray(TTO_PENALTY)[tier]
-    fl = np.maximum(0.0, (pc - FATIGUE_START) / 25)
-    ak = m.pit_k[side, pit] * (1 - pen) * (1.0 - 0.02 * fl)
-    ab = m.pit_bb[side, pit] * (1 + pen) * (1.0 + 0.03 * fl)
-    k = (m.bat_k[side, slot] + ak) / 2 * m.k_mod
-    bb = (m.bat_bb[side, slot] + ab) / 2 * m.bb_mod
+    k, bb = _effective_rates(m, side, pit, tier, slot, pitch_count)
     pk, pkbb = _p_k_or_bb_batch(k, bb, use_noise)
     contact = 1.0 - pkbb
     cdf_bip, cdf_hit, cdf_fb = contact_cdfs()
@@ -345,6 +371,59 @@ def alias_row(p) -> np.ndarray:
     return out
 
 
+def alias_rows(P) -> np.ndarray:
+    """`alias_row` for N rows at once ([N, 7] probabilities -> [N, 8] uint32): the same stack discipline
+    (highest column first) run in lock step over all rows, so the result is identical entry for entry."""
+    P = np.asarray(P, dtype=np.float64)
+    N = len(P)
+    q = np.zeros((N, ALIAS_COLS))
+    q[:, :7] = P * ALIAS_COLS / P.sum(axis=1)[:, None]
+    cut = np.ones((N, ALIAS_COLS))
+    alias = np.tile(np.arange(ALIAS_COLS), (N, 1))
+    small = np.zeros((N, ALIAS_COLS), dtype=np.int64)
+    large = np.zeros((N, ALIAS_COLS), dtype=np.int64)
+    ns = np.zeros(N, dtype=np.int64)
+    nl = np.zeros(N, dtype=np.int64)
+    for i in range(ALIAS_COLS):
+        lt = q[:, i] < 1.0
+        r = np.nonzero(lt)[0]
+        small[r, ns[r]] = i
+        ns[r] += 1
+        r = np.nonzero(~lt)[0]
+        large[r, nl[r]] = i
+        nl[r] += 1
+    for _ in range(ALIAS_COLS):
+        r = np.nonzero((ns > 0) & (nl > 0))[0]
+        if len(r) == 0:
+            break
+        sm, lg = small[r, ns[r] - 1], large[r, nl[r] - 1]
+        ns[r] -= 1
+        nl[r] -= 1
+        cut[r, sm] = q[r, sm]
+        alias[r, sm] = lg
+        q[r, lg] = q[r, lg] - (1.0 - q[r, sm])
+        lt = q[r, lg] < 1.0
+        rs, rl = r[lt], r[~lt]
+        small[rs, ns[rs]] = lg[lt]
+        ns[rs] += 1
+        large[rl, nl[rl]] = lg[~lt]
+        nl[rl] += 1
+    top = np.argmax(P, axis=1)
+    for stack, depth in ((small, ns), (large, nl)):      # leftovers are full columns up to rounding
+        for j in range(ALIAS_COLS):
+            r = np.nonzero(depth > j)[0]
+            col = stack[r, j]
+            cut[r, col] = 1.0
+            alias[r, col] = np.where(col < 7, col, top[r])
+    one = 1 << ALIAS_FRAC_BITS
+    c = np.floor(cut * one + 0.5).astype(np.int64)
+    cols = np.arange(ALIAS_COLS)[None, :]
+    full = c >= one
+    a = np.where(full & (cols < 7), cols, alias)
+    c = np.where(full | (cols == 7), 0, np.maximum(c, 0))
+    return ((c << 3) | a).astype(np.uint32)
+
+
 def alias_probabilities(row) -> np.ndarray:
     """Exact outcome probabilities an alias row encodes (for tests)."""
     one = float(1 << ALIAS_FRAC_BITS)
@@ -356,44 +435,81 @@ def alias_probabilities(row) -> np.ndarray:
     return p[:7]
 
 
-def build_table(m, use_noise=None) -> np.ndarray:
-    m = as_matchup(m) if use_noise is None else as_matchup(m, use_noise)
-    use_noise = m.use_noise if use_noise is None else use_noise
-    t = np.zeros((), dtype=_abi.TABLE_DTYPE)
-    t["magic"] = _abi.TABLE_MAGIC
-    t["lineup_len"] = m.lineup_len
-    t["bullpen_len"] = m.bullpen_len
-    flags = 0
-    alias = np.zeros(_abi.TABLE_DTYPE["alias"].shape, dtype=np.uint32)   # unused rows: always K (never reached)
-    fthr = np.zeros(_abi.TABLE_DTYPE["fthr"].shape, dtype=np.uint32)
-    fthr[...] = 2147483648
-    fslope = np.zeros(_abi.TABLE_DTYPE["fslope"].shape, dtype=np.int32)
+def _table_rows(m: Matchup):
+    """(side, pitcher, tier, slot) of every row the kernel can reach for this matchup."""
     idx = [(s, p, tier, b) for s in range(2) for p in range(m.bullpen_len[s] + 1)
            for tier in range(_abi.N_TIERS) for b in range(m.lineup_len[s])]
-    S, P, T, B = (np.array(x) for x in zip(*idx))
-    c0 = outcome_cdf_batch(m, S, P, T, B, np.zeros(len(idx)), use_noise)
-    probs = np.diff(np.concatenate([np.zeros((len(idx), 1)), c0, np.ones((len(idx), 1))], axis=1), axis=1)
-    for i, (s, p, tier, b) in enumerate(idx):
-        alias[s, p, tier, b] = alias_row(probs[i])
-    # a starter without a bullpen is never replaced: pitch_count passes 75 (fatigue_modeling.py:38)
-    fat = np.array([i for i, (s, p, tier, b) in enumerate(idx) if p == 0 and m.bullpen_len[s] == 0], dtype=np.int64)
-    if len(fat):
-        flags |= _abi.FLAG_FATIGUE
-        c1 = outcome_cdf_batch(m, S[fat], P[fat], T[fat], B[fat], np.full(len(fat), FATIGUE_START + SLOPE_SPAN), use_noise)
-        q0, q1 = _quantise(c0[fat]), _quantise(c1)
-        for j, i in enumerate(fat):
-            s, p, tier, b = idx[i]
-            fthr[s, tier, b, :6] = q0[j]
-            fslope[s, tier, b, :6] = np.round((q1[j].astype(np.int64) - q0[j].astype(np.int64)) / SLOPE_SPAN)
-    t["flags"] = flags
-    t["alias"] = alias
-    t["fthr"] = fthr
-    t["fslope"] = fslope
-    return t
+    return tuple(np.array(x, dtype=np.int64) for x in zip(*idx))
+
+
+def _fatigue_rows(m: Matchup, S, P):
+    """Rows that need pitch-count slopes: a starter without a bullpen is never replaced, so his pitch count passes
+    75 (core/fatigue_modeling.py:38)."""
+    return np.nonzero((P == 0) & (np.asarray(m.bullpen_len)[S] == 0))[0]
+
+
+def _warm_clip_cache(ms) -> None:
+    """One threaded pass of the noise integral over every distinct (k, bb) of a batch of matchups; the per-matchup
+    builds that follow are cache hits.  Pure optimisation: values are the ones `build_table` would compute."""
+    ks, bs = [], []
+    for m in ms:
+        if not m.use_noise:
+            continue
+        S, P, T, B = _table_rows(m)
+        k, bb = _effective_rates(m, S, P, T, B, np.zeros(len(S)))
+        ks.append(k), bs.append(bb)
+        fat = _fatigue_rows(m, S, P)
+        if len(fat):
+            k, bb = _effective_rates(m, S[fat], P[fat], T[fat], B[fat], np.full(len(fat), FATIGUE_START + SLOPE_SPAN))
+            ks.append(k), bs.append(bb)
+    if not ks:
+        return
+    kb = np.unique(np.stack([np.concatenate(ks), np.concatenate(bs)], axis=1), axis=0)
+    k, bb = kb[:, 0], kb[:, 1]
+    both = (bb > 0.0) & (bb < 1.0) & (k > 0.0) & (k < 1.0)      # the branch of _p_k_or_bb_batch that integrates
+    if both.any():
+        _expect_clip_cached(k[both], bb[both])
+
+
+def build_table(m, use_noise=None) -> np.ndarray:
+    """One `mlbsim_table` (include/mlbsim.h) from a matchup: alias rows for every reachable (side, pitcher, TTO tier,
+    lineup slot) and, for starters that are never replaced, 31-bit thresholds with pitch-count slopes."""
+    m = as_matchup(m) if use_noise is None else as_matchup(m, use_noise)
+    if use_noise is not None and bool(use_noise) != bool(m.use_noise):
+        m = copy.copy(m)
+        m.use_noise = bool(use_noise)
+    return build_tables([m])[0]
 
 
 def build_tables(matchups, use_noise=True) -> np.ndarray:
-    out = np.zeros(len(matchups), dtype=_abi.TABLE_DTYPE)
-    for i, m in enumerate(matchups):
-        out[i] = build_table(m, use_noise=None if isinstance(m, Matchup) else use_noise)
+    """Tables for a batch of matchups (dicts take `use_noise` as the default for a missing key).  The noise integral
+    and the alias construction each run once over the rows of all matchups."""
+    ms = [m if isinstance(m, Matchup) else as_matchup(m, use_noise) for m in matchups]
+    out = np.zeros(len(ms), dtype=_abi.TABLE_DTYPE)
+    if not ms:
+        return out
+    if len(ms) > 1:
+        _warm_clip_cache(ms)
+    alias = np.zeros((len(ms),) + _abi.TABLE_DTYPE["alias"].shape, dtype=np.uint32)   # unused rows: always K (never reached)
+    fthr = np.full((len(ms),) + _abi.TABLE_DTYPE["fthr"].shape, 2147483648, dtype=np.uint32)
+    fslope = np.zeros((len(ms),) + _abi.TABLE_DTYPE["fslope"].shape, dtype=np.int32)
+    where, rows = [], []
+    for i, m in enumerate(ms):
+        S, P, T, B = _table_rows(m)
+        c0 = outcome_cdf_batch(m, S, P, T, B, np.zeros(len(S)))
+        rows.append(np.diff(np.concatenate([np.zeros((len(S), 1)), c0, np.ones((len(S), 1))], axis=1), axis=1))
+        where.append((np.full(len(S), i), S, P, T, B))
+        fat = _fatigue_rows(m, S, P)
+        if len(fat):
+            out["flags"][i] |= _abi.FLAG_FATIGUE
+            c1 = outcome_cdf_batch(m, S[fat], P[fat], T[fat], B[fat], np.full(len(fat), FATIGUE_START + SLOPE_SPAN))
+            q0, q1 = _quantise(c0[fat]), _quantise(c1)
+            fthr[i, S[fat], T[fat], B[fat], :6] = q0
+            fslope[i, S[fat], T[fat], B[fat], :6] = np.round((q1.astype(np.int64) - q0.astype(np.int64)) / SLOPE_SPAN)
+        out["lineup_len"][i] = m.lineup_len
+        out["bullpen_len"][i] = m.bullpen_len
+    I, S, P, T, B = (np.concatenate(x) for x in zip(*where))
+    alias[I, S, P, T, B] = alias_rows(np.concatenate(rows))
+    out["magic"] = _abi.TABLE_MAGIC
+    out["alias"], out["fthr"], out["fslope"] = alias, fthr, fslope
     return out
