@@ -52,15 +52,15 @@ def workload(args):
     if args.workload == "single":
         ms = [synth.make_matchup("2025-04-04-TEX@HOU")]
         sims = args.sims or 10_000_000
-        name = "single game 2025-04-04-TEX@HOU x 10M sims per GPU per step (BASELINE configs[1])"
+        name = f"single game 2025-04-04-TEX@HOU x {_count(sims)} sims per GPU per step (BASELINE configs[{0 if sims <= 10_000 else 1}])"
     elif args.workload == "fatigue":
         ms = [synth.make_matchup("2025-04-04-TEX@HOU", bullpens=False)]   # starters go the distance: TTO 4+, pitch-count ramp
         sims = args.sims or 10_000_000
-        name = "fatigue-heavy: single game without bullpens x 10M sims per GPU per step (BASELINE configs[3] shape)"
+        name = f"fatigue-heavy: single game without bullpens x {_count(sims)} sims per GPU per step (BASELINE configs[3] shape)"
     elif args.workload == "slate":
         ms = synth.make_slate("2025-04-04", 15)
         sims = args.sims or 1_000_000
-        name = "15-game slate x 1M sims per game per GPU per step (BASELINE configs[2])"
+        name = f"15-game slate x {_count(sims)} sims per game per GPU per step (BASELINE configs[2])"
     else:
         import numpy as np
         from mlb_odds_engine_b200 import sweep
@@ -69,8 +69,12 @@ def workload(args):
         ms, _ = sweep.grid_matchups(base, "home", k_rate=np.linspace(0.14, 0.34, 16), bb_rate=np.linspace(0.04, 0.12, 8),
                                     hr_pa_projected=np.linspace(0.015, 0.06, 8))
         sims = args.sims or 100_000
-        name = "sensitivity sweep: 1024 grid points (k_rate x bb_rate x hr_pa) x 100k sims per GPU per step (BASELINE configs[4])"
+        name = f"sensitivity sweep: 1024 grid points (k_rate x bb_rate x hr_pa) x {_count(sims)} sims per GPU per step (BASELINE configs[4])"
     return ms, sims, name
+
+
+def _count(n: int) -> str:
+    return f"{n // 1_000_000}M" if n % 1_000_000 == 0 and n else f"{n // 1000}k" if n % 1000 == 0 and n else str(n)
 
 
 class ClockSampler:

@@ -35,6 +35,12 @@
 #ifndef OPT_UNROLL
 #define OPT_UNROLL 4   /* plate appearances per round: one refill check and one boundary pass per round */
 #endif
+#ifndef OPT_PAD16
+#define OPT_PAD16 1    /* alias rows padded to 16 lineup slots + biased slot counter: row address = ctx bits, lineup wrap = carry */
+#endif
+#ifndef OPT_PA_RED
+#define OPT_PA_RED 1   /* PA outcome counters: 1 = red.shared.add on the thread's own column (measured +2 %), 0 = ld/add/st */
+#endif
 #ifndef NATIVE_LB_THREADS
 #define NATIVE_LB_THREADS MLBSIM_NATIVE_MAX_THREADS
 #endif
@@ -60,15 +66,24 @@ constexpr int FATIGUE_START = 75;            // fatigue_modeling.py:38
 constexpr int SB = 32;                                    // smem joint-histogram bins per team
 constexpr int ALIAS_WORDS = 2 * MLBSIM_MAX_PITCHERS * MLBSIM_N_TIERS * MLBSIM_MAX_LINEUP * MLBSIM_ROW_WORDS;  // 4032
 constexpr int FAT_WORDS = 2 * MLBSIM_N_TIERS * MLBSIM_MAX_LINEUP * MLBSIM_ROW_WORDS;                          // 576
-constexpr int LUT_WORDS = 24 * 8 * 4;   // [outs*8+bases][outcome (8 slots)][dA][dB]                           // 768
+// transition LUT: one 256-byte row per (outs*8 + bases): words 0-31 = [outcome (8 slots)][dA][dB] entries,
+// words 32-39 = the sub-draw A threshold of each outcome at this number of outs, rest unused
+constexpr int LUT_ROW_WORDS = 64;
+constexpr int LUT_WORDS = 32 * LUT_ROW_WORDS;                                                                  // 2048
+constexpr uint32_t LUT_TA_BYTE = 32u * 4u;
 constexpr int JOINT_WORDS = MLBSIM_N_CAPS * SB * SB;                                                          // 5120
 
+constexpr int PAD_SLOTS = 16;
+constexpr int ALIAS_PAD_WORDS = 2 * MLBSIM_MAX_PITCHERS * MLBSIM_N_TIERS * PAD_SLOTS * MLBSIM_ROW_WORDS;          // 7168
+constexpr int ALIAS_PAD_SIDE_BYTES = ALIAS_PAD_WORDS / 2 * 4;                                                  // 14336
+
 struct __align__(16) Smem {
+#if !OPT_PAD16
   uint32_t alias[ALIAS_WORDS];
+#endif
   uint32_t fthr[FAT_WORDS];
   int32_t fslope[FAT_WORDS];
   uint32_t lut[LUT_WORDS];
-  uint32_t tA[16];  // sub-draw A threshold by (outs == 2)*8 + outcome
   uint32_t joint[JOINT_WORDS];
   uint32_t innings[MLBSIM_INN_BINS];
   uint32_t rel_games[16];
@@ -78,14 +93,21 @@ struct __align__(16) Smem {
   uint32_t go;  // block-uniform "this matchup still has work"
 };
 constexpr int PA_FIELDS = 14;  // [side][outcome]
+// Dynamic shared memory: [padded alias table (OPT_PAD16)] [pa[14][PA_STRIDE]].  The counter stride is the
+// compile-time maximum block size, not blockDim.x, so that `outcome * stride` is an immediate multiply.
+constexpr uint32_t PA_STRIDE = MLBSIM_NATIVE_MAX_THREADS;
+constexpr uint32_t DYN_ALIAS_BYTES = OPT_PAD16 ? (uint32_t)ALIAS_PAD_WORDS * 4u : 0u;
+constexpr uint32_t DYN_PA_WORD0 = DYN_ALIAS_BYTES / 4u;
 
 }  // namespace
 
 // Statically allocated (44 KB) at global scope so that its PTX symbol keeps this plain name: the
 // hot loop takes `mov.u32 r, mlbsim_S` (a link-time constant in the .shared space) as its base and
 // every access becomes LDS [Rindex + imm] with no generic->shared conversion in the loop.
-// Dynamic shared memory holds pa[14][blockDim.x], the per-thread PA outcome counters (column =
-// thread: bank = lane, so their read-modify-write is conflict-free).
+// Dynamic shared memory holds (OPT_PAD16) the alias table re-laid as [side][pitcher][tier][16 slots][8 words]: the low nine bits of a side's
+// context word ARE the row number, and rows sit at slot + 16 - L so that running off the end of the
+// lineup is a carry out of the slot field into the tier field; then pa[14][PA_STRIDE], the per-thread PA outcome
+// counters (column = thread: bank = lane, so their read-modify-write is conflict-free).
 __shared__ Smem mlbsim_S;
 extern __shared__ __align__(16) uint32_t mlbsim_S_pa[];
 
@@ -125,16 +147,27 @@ constexpr int CX_T_SHIFT = 4;  // (ctx >> 4) & 31 = pit*4 + tier
 constexpr int CX_PIT_SHIFT = 6;
 constexpr int CX_PC_SHIFT = 9;
 constexpr uint32_t CX_NEXT_PA = (1u << CX_PC_SHIFT) + 1u;  // one more pitch, next batter
+#if OPT_PAD16
+// OPT_PAD16: slot field holds slot + (16 - L) ("biased"), and bias[31:28] = 16 - L rides in the top
+// nibble (pitch_count keeps 19 bits).  ctx & CX_ROW = row number in the padded alias table.
+constexpr int CX_BIAS_SHIFT = 28;
+constexpr uint32_t CX_PC_BITS = (1u << CX_BIAS_SHIFT) - 1u;   // mask that drops the bias nibble
+constexpr uint32_t CX_ROW = 0x1FFu;
+#else
+constexpr uint32_t CX_PC_BITS = 0xFFFFFFFFu;
+#endif
 
 // ---- half-inning state word -------------------------------------------------------------------
-// ob[4:0] = outs*8 + bases | n_pa + 34 [14:8] (bit 14 = the 30-PA cap) | runs[21:16] |
-// reached_count[29:24] | three outs [30] (set by the LUT entry) | no PA yet in this half [31]
-constexpr uint32_t HS_OB = 31u;
+// n_pa + 34 [6:0] (bit 6 = the 30-PA cap) | ob[12:8] = outs*8 + bases, i.e. already the byte offset of the
+// LUT row | runs[21:16] | reached_count[29:24] | three outs [30] (set by the LUT entry) | no PA yet in this half [31]
+constexpr int HS_OB_SHIFT = 8;
+constexpr uint32_t HS_OB = 31u << HS_OB_SHIFT;
+
 constexpr uint32_t HS_FRESH = 1u << 31;
-constexpr uint32_t HS_NEW_HALF = HS_FRESH | ((64u - MAX_PA_PER_HALF) << 8);
+constexpr uint32_t HS_NEW_HALF = HS_FRESH | (64u - MAX_PA_PER_HALF);
 constexpr uint32_t HS_KEEP = ~(HS_OB | HS_FRESH);        // hs' = (hs & HS_KEEP) + HS_PA_ONE + entry
-constexpr uint32_t HS_PA_ONE = 1u << 8;
-constexpr uint32_t HS_OVER = (1u << 30) | (1u << 14);   // three outs, or 30 PAs
+constexpr uint32_t HS_PA_ONE = 1u;
+constexpr uint32_t HS_OVER = (1u << 30) | (1u << 6);    // three outs, or 30 PAs
 constexpr uint32_t HS_REACHED = 0x3Fu << 24;
 constexpr uint32_t HS_DEAD = 1u << 15;                   // lane has no game (bit 15 is outside every live field)
 
@@ -180,19 +213,25 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
   const int lane = threadIdx.x & 31;
   const uint32_t n_sims = args.n_sims;
   const uint32_t sb = smem_static_base();
+#if OPT_PAD16
+  const uint32_t A_ALIAS = smem_dynamic_base();                                  // padded table: start of dynamic smem
+  const uint32_t init0 = (16u - L0) * ((1u << CX_BIAS_SHIFT) + 1u);             // bias nibble + biased slot 0
+  const uint32_t init1 = (16u - L1) * ((1u << CX_BIAS_SHIFT) + 1u);
+  uint32_t alias_base = A_ALIAS;                                                  // rows of the side at bat
+#else
   const uint32_t A_ALIAS = sb + (uint32_t)offsetof(Smem, alias);
+#endif
   const uint32_t A_FTHR = sb + (uint32_t)offsetof(Smem, fthr);
   const uint32_t A_FSLOPE = sb + (uint32_t)offsetof(Smem, fslope);
   const uint32_t A_LUT = sb + (uint32_t)offsetof(Smem, lut);
-  const uint32_t A_TA = sb + (uint32_t)offsetof(Smem, tA);
   const uint32_t A_JOINT = sb + (uint32_t)offsetof(Smem, joint);
   const uint32_t A_INN = sb + (uint32_t)offsetof(Smem, innings);
   const uint32_t A_RELG = sb + (uint32_t)offsetof(Smem, rel_games);
   const uint32_t A_RELP = sb + (uint32_t)offsetof(Smem, rel_picks);
   // per-thread PA counters: pa[f][tid], f = side*7 + outcome
-  const uint32_t pa_stride = blockDim.x * 4u;  // bytes between outcomes
-  const uint32_t pa_side = 7u * pa_stride;     // bytes between sides
-  const uint32_t pa_mine = smem_dynamic_base() + threadIdx.x * 4u;
+  constexpr uint32_t pa_stride = PA_STRIDE * 4u;  // bytes between outcomes
+  constexpr uint32_t pa_side = 7u * pa_stride;    // bytes between sides
+  const uint32_t pa_mine = smem_dynamic_base() + DYN_ALIAS_BYTES + threadIdx.x * 4u;
 
   // ---- warp-uniform work state ----
   uint32_t chunk_next = 0, chunk_end = 0;
@@ -230,7 +269,12 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
         const unsigned long long sim = (unsigned long long)args.sim_lo + (chunk_next + rank);
         c0 = (uint32_t)sim;
         c1 = ((uint32_t)(sim >> 32) << RNG_SIMHI_SHIFT) | rng_matchup;
-        cur = 0; oth = 0; sc = 0; hidx = 0; hs = HS_NEW_HALF; used = 0; pa_addr = pa_mine;
+#if OPT_PAD16
+        cur = init0; oth = init1; alias_base = A_ALIAS;
+#else
+        cur = 0; oth = 0;
+#endif
+        sc = 0; hidx = 0; hs = HS_NEW_HALF; used = 0; pa_addr = pa_mine;
       }
       const uint32_t want = __popc(need);
       chunk_next += want < avail ? want : avail;
@@ -250,17 +294,26 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
       // as this half's end-of-inning (misc / ghost run) draw.
       if ((int)hs < 0) w1_first = w1;
 
+      // Walker alias draw: one shared-memory word per PA
+      const uint32_t col = w0 >> 29;
+#if OPT_PAD16
+      const uint32_t e = lds32(alias_base + ((cur & CX_ROW) << 5) + (col << 2));
+#else
       side = hidx & 1u;
       const uint32_t slot = cur & CX_SLOT;
       const uint32_t T = (cur >> CX_T_SHIFT) & 31u;  // pit*4 + tier
       const uint32_t row = (side * (MLBSIM_MAX_PITCHERS * MLBSIM_N_TIERS) + T) * MLBSIM_MAX_LINEUP + slot;
-      // Walker alias draw: one shared-memory word per PA
-      const uint32_t col = w0 >> 29;
       const uint32_t e = lds32(A_ALIAS + ((row * MLBSIM_ROW_WORDS + col) << 2));
+#endif
       uint32_t o = ((w0 & 0x1FFFFFFFu) < (e >> 3)) ? col : (e & 7u);
       if (FATIGUE) {
-        if (T < 4u && cur >= ((uint32_t)(FATIGUE_START + 1) << CX_PC_SHIFT)) {  // starter past 75 pitches
-          const uint32_t ex = (cur >> CX_PC_SHIFT) - FATIGUE_START;
+#if OPT_PAD16
+        side = hidx & 1u;
+        const uint32_t slot = (cur & CX_SLOT) - (cur >> CX_BIAS_SHIFT);
+        const uint32_t T = (cur >> CX_T_SHIFT) & 31u;  // pit*4 + tier
+#endif
+        if (T < 4u && (cur & CX_PC_BITS) >= ((uint32_t)(FATIGUE_START + 1) << CX_PC_SHIFT)) {  // starter past 75 pitches
+          const uint32_t ex = ((cur & CX_PC_BITS) >> CX_PC_SHIFT) - FATIGUE_START;
           const uint32_t srow = (((side * MLBSIM_N_TIERS + T) * MLBSIM_MAX_LINEUP + slot) * MLBSIM_ROW_WORDS) << 2;
           const uint32_t u = w0 >> 1;
           o = 0;
@@ -271,17 +324,35 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
 
       // base-running sub-draws from w1: A = full 32-bit compare, B = its low 16 bits
       const uint32_t o4 = o << 2;
-      const uint32_t tA = lds32(A_TA + ((hs & 16u) << 1) + o4);  // [(outs == 2)][outcome]
-      const uint32_t idx = ((hs & HS_OB) << 7) + (o4 << 2) + (w1 < tA ? 8u : 0u) + ((w1 & 0xFFFFu) < T_080_16 ? 4u : 0u);
-      const uint32_t ent = lds32(A_LUT + idx);
+      const uint32_t lut_row = A_LUT + (hs & HS_OB);
+      const uint32_t tA = lds32(lut_row + LUT_TA_BYTE + o4);
+      const uint32_t ent = lds32(lut_row + (o4 << 2) + (w1 < tA ? 8u : 0u) + ((w1 & 0xFFFFu) < T_080_16 ? 4u : 0u));
       hs = (hs & HS_KEEP) + HS_PA_ONE + ent;
 
       if (COUNT_PA) {
         const uint32_t pa = pa_addr + o * pa_stride;
+#if OPT_PA_RED
+        red_inc_shared(pa);
+#else
         sts32(pa, lds32(pa) + 1u);
+#endif
       }
 
       // next batter, one more pitch (pitch_count counts PAs: half_inning_simulator.py:218-220)
+#if OPT_PAD16
+      {
+        // The biased slot runs from 16 - L to 15, so stepping past the last batter carries into the
+        // tier field: that carry IS the TTO increment (half_inning_simulator.py:177-178: the next PA
+        // of this half starts a new pass through the lineup).  It is taken back when the tier was
+        // already 4+ (the carry ran on into the pitcher field; -0x10 borrows it back), or when the
+        // wrap coincides with the end of the half: the next half then starts at index 0, where the
+        // reference's `batter_idx > 0` is false.
+        const uint32_t t = cur + CX_NEXT_PA;
+        uint32_t fix = t >> CX_BIAS_SHIFT;   // back to the first batter
+        if ((hs & HS_OVER) != 0u || (cur & CX_TIER_MASK) == CX_TIER_MASK) fix -= CX_TIER_ONE;
+        cur = (t & CX_SLOT) == 0u ? t + fix : t;
+      }
+#else
       cur += CX_NEXT_PA;
       const uint32_t L = side ? L1 : L0;
       const bool wrapped = (cur & CX_SLOT) == L;
@@ -293,6 +364,7 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
         // the next half then starts at index 0, where the reference's `batter_idx > 0` is false.
         if (wrapped && (cur & CX_TIER_MASK) != CX_TIER_MASK) cur += CX_TIER_ONE;
       }
+#endif
     }
     if ((hs & HS_OVER) != 0u) {   // (a dead lane has only HS_DEAD set)
       {
@@ -315,13 +387,16 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
           ++hidx;
           const uint32_t t = cur; cur = oth; oth = t;
           if (COUNT_PA) pa_addr = side ? pa_mine : pa_mine + pa_side;
+#if OPT_PAD16
+          alias_base = side ? A_ALIAS : A_ALIAS + (uint32_t)ALIAS_PAD_SIDE_BYTES;
+#endif
           // should_replace_pitcher (game_simulator.py:8-12) for the staff that now takes the mound
           const uint32_t nb = side ? nb0 : nb1;  // `side` is the half that just ended
-          if (nb != 0u && ((cur & CX_TIER_GE2) != 0u || cur >= ((uint32_t)(PITCH_LIMIT + 1) << CX_PC_SHIFT))) {
+          if (nb != 0u && ((cur & CX_TIER_GE2) != 0u || (cur & CX_PC_BITS) >= ((uint32_t)(PITCH_LIMIT + 1) << CX_PC_SHIFT))) {
             // stationary law of simulate_reliever_chain: uniform, with replacement.  The half ended on
             // an out, whose transition ignores the low half of w1 (only singles read it).
             const uint32_t idx = ((w1 & 0xFFFFu) * nb) >> 16;
-            cur = (cur & CX_SLOT) | ((idx + 1u) << CX_PIT_SHIFT);
+            cur = (cur & (CX_SLOT | ~CX_PC_BITS)) | ((idx + 1u) << CX_PIT_SHIFT);
             const uint32_t bit = idx + (side ? 0u : 8u);
             // "sims in which reliever i appeared" (run_distribution_simulator.py:391-397): count his first
             // appearance in this game here rather than walking the mask when the game ends
@@ -353,10 +428,17 @@ mlbsim_native_kernel(const NativeArgs args) {
 
   // transition LUT + sub-draw thresholds: derived once per block from the branchy semantics above
   for (int i = tid; i < LUT_WORDS; i += blockDim.x) {
-    const int ob = i >> 5, o = (i >> 2) & 7, dA = (i >> 1) & 1, dB = i & 1;
-    S.lut[i] = transition_entry(o < 7 ? o : MLBSIM_OUT, dA, dB, ob >> 3, ob & 7);
+    const int ob = i / LUT_ROW_WORDS, w = i % LUT_ROW_WORDS;
+    uint32_t v = 0;
+    if (w < 32) {
+      const int o = w >> 2, dA = (w >> 1) & 1, dB = w & 1;
+      const uint32_t e = transition_entry(o < 7 ? o : MLBSIM_OUT, dA, dB, ob >> 3, ob & 7);
+      v = (e & ~31u) | ((e & 31u) << HS_OB_SHIFT);   // next outs*8 + bases goes where the state word keeps it
+    } else if (w < 40) {
+      v = subdraw_a_threshold(w - 32, (ob >> 3) == 2);
+    }
+    S.lut[i] = v;
   }
-  if (tid < 16) S.tA[tid] = subdraw_a_threshold(tid & 7, tid >> 3);
 
   for (uint32_t step = 0; step < args.n_matchups; ++step) {
     const uint32_t m = (blockIdx.x + step) % args.n_matchups;
@@ -369,8 +451,20 @@ mlbsim_native_kernel(const NativeArgs args) {
     {
       const mlbsim_table* T = args.tables + m;
       const uint4* src = reinterpret_cast<const uint4*>(T->alias);
+#if OPT_PAD16
+      // compact [side][pit][tier][9][8] -> padded [side][pit][tier][16][8], row of slot s at s + 16 - L(side)
+      uint4* dst = reinterpret_cast<uint4*>(S_pa);
+      const uint32_t bias0 = 16u - T->lineup_len[0], bias1 = 16u - T->lineup_len[1];
+      for (int i = tid; i < ALIAS_WORDS / 4; i += blockDim.x) {
+        const uint32_t r = (uint32_t)i >> 1, group = r / MLBSIM_MAX_LINEUP, slot = r - group * MLBSIM_MAX_LINEUP;
+        const uint32_t bias = group >= (uint32_t)(MLBSIM_MAX_PITCHERS * MLBSIM_N_TIERS) ? bias1 : bias0;
+        const uint32_t pslot = slot + bias;
+        if (pslot < (uint32_t)PAD_SLOTS) dst[((group * PAD_SLOTS + pslot) << 1) + (i & 1)] = __ldg(src + i);
+      }
+#else
       uint4* dst = reinterpret_cast<uint4*>(S.alias);
       for (int i = tid; i < ALIAS_WORDS / 4; i += blockDim.x) dst[i] = __ldg(src + i);
+#endif
       if (T->flags & MLBSIM_FLAG_FATIGUE) {
         const uint4* fsrc = reinterpret_cast<const uint4*>(T->fthr);
         uint4* fdst = reinterpret_cast<uint4*>(S.fthr);
@@ -380,7 +474,7 @@ mlbsim_native_kernel(const NativeArgs args) {
       if (tid < MLBSIM_INN_BINS) S.innings[tid] = 0;
       if (tid < 16) { S.rel_games[tid] = 0; S.rel_picks[tid] = 0; }
       if (count_pa) {
-        for (int f = 0; f < PA_FIELDS; ++f) S_pa[f * blockDim.x + tid] = 0u;
+        for (int f = 0; f < PA_FIELDS; ++f) S_pa[DYN_PA_WORD0 + f * PA_STRIDE + tid] = 0u;
       }
       if (tid == 0) {
         S.n_games = 0;
@@ -407,7 +501,7 @@ mlbsim_native_kernel(const NativeArgs args) {
     // ---- block flush: shared u32 bins / per-thread counters -> device u64 totals ----
     if (count_pa) {
       for (int f = 0; f < PA_FIELDS; ++f) {
-        const uint32_t v = __reduce_add_sync(0xffffffffu, S_pa[f * blockDim.x + tid]);
+        const uint32_t v = __reduce_add_sync(0xffffffffu, S_pa[DYN_PA_WORD0 + f * PA_STRIDE + tid]);
         if (lane == 0 && v) atomicAdd(&H[H_PA + (f / 7) * 8 + (f % 7)], (unsigned long long)v);
       }
     }
@@ -524,4 +618,6 @@ mlbsim_persim_kernel(const PersimArgs args) {
   }
 }
 
-size_t mlbsim_native_smem_bytes(int threads_per_block) { return (size_t)PA_FIELDS * 4u * (size_t)threads_per_block; }  // dynamic part only
+size_t mlbsim_native_smem_bytes(int /*threads_per_block*/) {   // dynamic part only; independent of the block size
+  return (size_t)DYN_ALIAS_BYTES + (size_t)PA_FIELDS * 4u * PA_STRIDE;
+}
