@@ -66,10 +66,11 @@ constexpr int FATIGUE_START = 75;            // fatigue_modeling.py:38
 constexpr int SB = 32;                                    // smem joint-histogram bins per team
 constexpr int ALIAS_WORDS = 2 * MLBSIM_MAX_PITCHERS * MLBSIM_N_TIERS * MLBSIM_MAX_LINEUP * MLBSIM_ROW_WORDS;  // 4032
 constexpr int FAT_WORDS = 2 * MLBSIM_N_TIERS * MLBSIM_MAX_LINEUP * MLBSIM_ROW_WORDS;                          // 576
-// transition LUT: one 256-byte row per (outs*8 + bases): words 0-31 = [outcome (8 slots)][dA][dB] entries,
-// words 32-39 = the sub-draw A threshold of each outcome at this number of outs, rest unused
-constexpr int LUT_ROW_WORDS = 64;
-constexpr int LUT_WORDS = 32 * LUT_ROW_WORDS;                                                                  // 2048
+// transition LUT: one row per (outs*8 + bases): words 0-31 = [outcome (8 slots)][dA][dB] entries, words 32-39 =
+// the sub-draw A threshold of each outcome at this number of outs.  41 words per row (odd): lanes in different
+// (outs, bases) states that look up the same (outcome, dA, dB) hit different banks.
+constexpr int LUT_ROW_WORDS = 41;
+constexpr int LUT_WORDS = 32 * LUT_ROW_WORDS;                                                                  // 1312
 constexpr uint32_t LUT_TA_BYTE = 32u * 4u;
 constexpr int JOINT_WORDS = MLBSIM_N_CAPS * SB * SB;                                                          // 5120
 
@@ -158,18 +159,22 @@ constexpr uint32_t CX_PC_BITS = 0xFFFFFFFFu;
 #endif
 
 // ---- half-inning state word -------------------------------------------------------------------
-// n_pa + 34 [6:0] (bit 6 = the 30-PA cap) | ob[12:8] = outs*8 + bases, i.e. already the byte offset of the
-// LUT row | runs[21:16] | reached_count[29:24] | three outs [30] (set by the LUT entry) | no PA yet in this half [31]
-constexpr int HS_OB_SHIFT = 8;
-constexpr uint32_t HS_OB = 31u << HS_OB_SHIFT;
-
-constexpr uint32_t HS_FRESH = 1u << 31;
-constexpr uint32_t HS_NEW_HALF = HS_FRESH | (64u - MAX_PA_PER_HALF);
-constexpr uint32_t HS_KEEP = ~(HS_OB | HS_FRESH);        // hs' = (hs & HS_KEEP) + HS_PA_ONE + entry
-constexpr uint32_t HS_PA_ONE = 1u;
-constexpr uint32_t HS_OVER = (1u << 30) | (1u << 6);    // three outs, or 30 PAs
-constexpr uint32_t HS_REACHED = 0x3Fu << 24;
-constexpr uint32_t HS_DEAD = 1u << 15;                   // lane has no game (bit 15 is outside every live field)
+// byte offset of the LUT row of (outs*8 + bases) [12:2] | three outs [14] | lane has no game [15] |
+// runs [20:16] | reached_count [25:21] | n_pa + 2 [31:26]: the count starts at 2, so "no PA yet in this
+// half" is `hs < 3 << 26` and the 30th PA carries into bit 31 (the 30-PA cap).  Every field but the count
+// is written by adding the LUT entry: hs' = (hs & ~HS_ROW) + HS_PA_ONE + entry.
+constexpr uint32_t HS_ROW = 0x1FFCu;
+constexpr uint32_t HS_3OUT = 1u << 14;
+constexpr uint32_t HS_DEAD = 1u << 15;                   // (a dead lane holds exactly this value)
+constexpr int HS_RUNS_SHIFT = 16;
+constexpr int HS_REACHED_SHIFT = 21;
+constexpr uint32_t HS_REACHED = 31u << HS_REACHED_SHIFT;
+constexpr int HS_PA_SHIFT = 26;
+constexpr uint32_t HS_PA_ONE = 1u << HS_PA_SHIFT;
+constexpr uint32_t HS_NEW_HALF = (32u - MAX_PA_PER_HALF) << HS_PA_SHIFT;
+constexpr uint32_t HS_FIRST_PA_BELOW = HS_NEW_HALF + HS_PA_ONE;   // hs < this  <=>  no PA played yet in this half
+constexpr uint32_t HS_OVER = (1u << 31) | HS_3OUT;      // 30 PAs, or three outs
+constexpr uint32_t HS_KEEP = ~HS_ROW;
 
 // threshold of sub-draw A: double play (K/OUT), runner on 2B scores on a single (0.46 with two
 // outs: 0.4 + 0.6*0.1), runner on 1B scores on a double
@@ -292,7 +297,7 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
 
       // The first PA of a half has empty bases, so its w1 never reaches the transition: keep it
       // as this half's end-of-inning (misc / ghost run) draw.
-      if ((int)hs < 0) w1_first = w1;
+      if (hs < HS_FIRST_PA_BELOW) w1_first = w1;
 
       // Walker alias draw: one shared-memory word per PA
       const uint32_t col = w0 >> 29;
@@ -324,7 +329,7 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
 
       // base-running sub-draws from w1: A = full 32-bit compare, B = its low 16 bits
       const uint32_t o4 = o << 2;
-      const uint32_t lut_row = A_LUT + (hs & HS_OB);
+      const uint32_t lut_row = A_LUT + (hs & HS_ROW);
       const uint32_t tA = lds32(lut_row + LUT_TA_BYTE + o4);
       const uint32_t ent = lds32(lut_row + (o4 << 2) + (w1 < tA ? 8u : 0u) + ((w1 & 0xFFFFu) < T_080_16 ? 4u : 0u));
       hs = (hs & HS_KEEP) + HS_PA_ONE + ent;
@@ -370,7 +375,7 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
       {
         // ---------------- end of half inning ----------------
         side = hidx & 1u;
-        uint32_t runs = (hs >> 16) & 63u;
+        uint32_t runs = (hs >> HS_RUNS_SHIFT) & 31u;
         // misc / ghost run (half_inning_simulator.py:12-25): rare (2 %), only if a runner reached.
         // T_END_BOTH < T_END_GHOST < T_END_ANY, so one compare screens all three.
         if (w1_first < T_END_ANY && (hs & HS_REACHED) != 0u) {
@@ -433,7 +438,9 @@ mlbsim_native_kernel(const NativeArgs args) {
     if (w < 32) {
       const int o = w >> 2, dA = (w >> 1) & 1, dB = w & 1;
       const uint32_t e = transition_entry(o < 7 ? o : MLBSIM_OUT, dA, dB, ob >> 3, ob & 7);
-      v = (e & ~31u) | ((e & 31u) << HS_OB_SHIFT);   // next outs*8 + bases goes where the state word keeps it
+      // re-pack into the state word's fields; the next (outs*8 + bases) becomes the byte offset of its row
+      v = (e & 31u) * (uint32_t)(LUT_ROW_WORDS * 4) | (((e >> 16) & 7u) << HS_RUNS_SHIFT) | (((e >> 24) & 1u) << HS_REACHED_SHIFT) |
+          (((e >> 30) & 1u) ? HS_3OUT : 0u);
     } else if (w < 40) {
       v = subdraw_a_threshold(w - 32, (ob >> 3) == 2);
     }
