@@ -332,13 +332,16 @@ def main():
     assert int(hist["n_games"].sum()) == n_m * total_per_step, "histogram does not hold every simulated game"
 
     # ---------------- end-to-end timing (host tables in, host histograms out) ----------------
+    # (the sweep's public call returns per-grid-point summaries reduced on the device; the others full histograms)
+    e2e_call = S.simulate_summary if args.workload == "sweep" else S.simulate
+    e2e_out_bytes = (_abi.SUMMARY_DTYPE if args.workload == "sweep" else _abi.HIST_DTYPE).itemsize
     for _ in range(args.warmup):
-        S.simulate(total_per_step, args.seed, sim_lo=step_no[0] * total_per_step, tables_host=tbl_host)
+        e2e_call(total_per_step, args.seed, sim_lo=step_no[0] * total_per_step, tables_host=tbl_host)
         step_no[0] += 1
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        out = S.simulate(total_per_step, args.seed, sim_lo=step_no[0] * total_per_step, tables_host=tbl_host)
+        out = e2e_call(total_per_step, args.seed, sim_lo=step_no[0] * total_per_step, tables_host=tbl_host)
         step_no[0] += 1
     barrier()
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=f"cuda:{local}")
@@ -398,7 +401,7 @@ def main():
                    "l2": "256 MB device buffer rewritten between timed iterations (L2 flush); every step simulates a fresh sim-index range",
                    "threads_per_block": args.threads_per_block or 640, "table_build_ms_once": 1e3 * t_build},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(tbl.nbytes),
-                "d2h_bytes_per_step": int(n_m * _abi.HIST_DTYPE.itemsize)},
+                "d2h_bytes_per_step": int(n_m * e2e_out_bytes)},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,

@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define MLBSIM_ABI_VERSION 2
+#define MLBSIM_ABI_VERSION 3
 
 /* ---- model dimensions ------------------------------------------------------------------- */
 #define MLBSIM_MAX_LINEUP 9   /* len(lineup); 9 in every caller (half_inning_simulator.py:175) */
@@ -115,6 +115,23 @@ typedef struct mlbsim_hist {
 
 #define MLBSIM_HIST_WORDS (sizeof(mlbsim_hist) / 8)
 
+/* ---- native mode: per-matchup scalar summary (sweeps) ---------------------------------------
+ * What tools/test_*_sensitivity.py and tools/simulate_calibration_game.py reduce N games to — outcome
+ * counts (PA_RECAP_LOG), run means / SDs, win counts — as exact integer moments of one mlbsim_hist,
+ * computed on the device so that a 1 024-point sweep returns 320 B per grid point instead of 165 KB.
+ * Runs are clamped at 63 exactly as the histogram bins are. */
+typedef struct mlbsim_summary {
+  uint64_t n_games;
+  uint64_t pa[2][8];          /* copy of mlbsim_hist.pa */
+  uint64_t sum_runs[MLBSIM_N_CAPS][2]; /* [cap 1,3,5,7,full][0 away, 1 home]: sum over sims of runs */
+  uint64_t sum_sq[2];         /* full game: sum of away^2, home^2 */
+  uint64_t sum_cross;         /* full game: sum of away*home */
+  uint64_t home_wins;         /* full game: sims with home > away */
+  uint64_t away_wins;
+  uint64_t sum_innings;       /* sum over sims of innings played (bin 31 counts as 31) */
+  uint64_t reserved[7];
+} mlbsim_summary;
+
 /* ---- error codes --------------------------------------------------------------------------- */
 #define MLBSIM_OK 0
 #define MLBSIM_ERR_CUDA 1       /* a CUDA runtime call failed; see mlbsim_last_error */
@@ -132,7 +149,7 @@ void mlbsim_destroy(mlbsim_ctx* ctx);
 const char* mlbsim_last_error(const mlbsim_ctx* ctx); /* ctx may be NULL: last init error */
 int mlbsim_abi_version(void);
 /* sizeof of the structs above as compiled into the library: 0 params, 1 table, 2 hist,
- * 3 replay_game (a binding checks its own mirrors against these at load time). */
+ * 3 replay_game, 4 summary (a binding checks its own mirrors against these at load time). */
 size_t mlbsim_struct_size(int which);
 
 /* Device facts for roofline arithmetic. */
@@ -162,6 +179,17 @@ int mlbsim_run_native(mlbsim_ctx* ctx, int matchup_lo, int matchup_hi, uint64_t 
  * histograms, run, copy to `hist_host`, synchronise. */
 int mlbsim_run_native_host(mlbsim_ctx* ctx, int matchup_lo, int matchup_hi, uint64_t sim_lo, uint64_t sim_hi,
                            uint64_t seed, mlbsim_hist* hist_host, uint32_t flags);
+
+/* Reduce `n_matchups` device histograms to summaries (device pointers; asynchronous on the context's
+ * stream).  Replaces the per-grid-point reductions of tools/test_stuff_plus_sensitivity.py:71-85 and
+ * tools/simulate_calibration_game.py:94-128. */
+int mlbsim_summarize(mlbsim_ctx* ctx, const mlbsim_hist* hist_dev, int n_matchups, mlbsim_summary* summary_dev);
+
+/* Host-buffer convenience for sweeps: zero device histograms, run, summarise on the device, copy
+ * `matchup_hi - matchup_lo` summaries to `summary_host`, synchronise.  The full histograms stay on the
+ * device (scratch) and are not copied. */
+int mlbsim_run_native_summary_host(mlbsim_ctx* ctx, int matchup_lo, int matchup_hi, uint64_t sim_lo, uint64_t sim_hi,
+                                   uint64_t seed, mlbsim_summary* summary_host, uint32_t flags);
 
 /* Per-sim variant of native mode for small N (the compatibility path under
  * cli/run_distribution_simulator.py:368-389, which reads result["home_score"], ["away_score"],

@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import numpy as np
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 MAX_LINEUP = 9
 MAX_BULLPEN = 6
@@ -100,12 +100,48 @@ HIST_DTYPE = np.dtype(
 
 HIST_WORDS = HIST_DTYPE.itemsize // 8
 
-STRUCTS = {0: PARAMS_DTYPE, 1: TABLE_DTYPE, 2: HIST_DTYPE, 3: REPLAY_GAME_DTYPE}
+SUMMARY_DTYPE = np.dtype(
+    [
+        ("n_games", "<u8"),
+        ("pa", "<u8", (2, 8)),
+        ("sum_runs", "<u8", (N_CAPS, 2)),   # [cap][0 away, 1 home]
+        ("sum_sq", "<u8", (2,)),
+        ("sum_cross", "<u8"),
+        ("home_wins", "<u8"),
+        ("away_wins", "<u8"),
+        ("sum_innings", "<u8"),
+        ("reserved", "<u8", (7,)),
+    ],
+    align=True,
+)
+
+STRUCTS = {0: PARAMS_DTYPE, 1: TABLE_DTYPE, 2: HIST_DTYPE, 3: REPLAY_GAME_DTYPE, 4: SUMMARY_DTYPE}
+
+
+def summarize_hist(rec: np.ndarray) -> np.ndarray:
+    """Host statement of `mlbsim_summarize` (csrc/summary_kernel.cu) for one HIST_DTYPE record: what the device
+    summary must equal, integer for integer.  Used by the tests and by callers that already hold a histogram."""
+    out = np.zeros((), dtype=SUMMARY_DTYPE)
+    j = rec["joint"].astype(object)
+    a = np.arange(HIST_BINS, dtype=object)[:, None]
+    h = np.arange(HIST_BINS, dtype=object)[None, :]
+    out["n_games"] = rec["n_games"]
+    out["pa"] = rec["pa"]
+    for c in range(N_CAPS):
+        out["sum_runs"][c, 0] = int((j[c] * a).sum())
+        out["sum_runs"][c, 1] = int((j[c] * h).sum())
+    full = j[N_CAPS - 1]
+    out["sum_sq"][0], out["sum_sq"][1] = int((full * a * a).sum()), int((full * h * h).sum())
+    out["sum_cross"] = int((full * a * h).sum())
+    out["home_wins"] = int(np.where(h > a, full, 0).sum())
+    out["away_wins"] = int(np.where(a > h, full, 0).sum())
+    out["sum_innings"] = int((rec["innings"].astype(object) * np.arange(INN_BINS, dtype=object)).sum())
+    return out
 
 
 def check_sizes(sizeof) -> None:
     """`sizeof(which) -> int` from the loaded library; raises on any mismatch."""
-    names = {0: "mlbsim_params", 1: "mlbsim_table", 2: "mlbsim_hist", 3: "mlbsim_replay_game"}
+    names = {0: "mlbsim_params", 1: "mlbsim_table", 2: "mlbsim_hist", 3: "mlbsim_replay_game", 4: "mlbsim_summary"}
     for which, dt in STRUCTS.items():
         got = int(sizeof(which))
         if got != dt.itemsize:

@@ -23,6 +23,8 @@ struct mlbsim_ctx {
   int counters_cap = 0;
   mlbsim_hist* hist_scratch = nullptr;  // used by *_host entry points
   int hist_scratch_cap = 0;
+  mlbsim_summary* summary_scratch = nullptr;
+  int summary_scratch_cap = 0;
   mlbsim_params* params_dev = nullptr;
   int threads_per_block = 0;
   int blocks_per_sm = 0;
@@ -59,6 +61,7 @@ size_t mlbsim_struct_size(int which) {
     case 1: return sizeof(mlbsim_table);
     case 2: return sizeof(mlbsim_hist);
     case 3: return sizeof(mlbsim_replay_game);
+    case 4: return sizeof(mlbsim_summary);
     default: return 0;
   }
 }
@@ -114,6 +117,7 @@ void mlbsim_destroy(mlbsim_ctx* ctx) {
   cudaFree(ctx->tables_dev);
   cudaFree(ctx->counters_dev);
   cudaFree(ctx->hist_scratch);
+  cudaFree(ctx->summary_scratch);
   cudaFree(ctx->params_dev);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -270,6 +274,48 @@ int mlbsim_run_native_host(mlbsim_ctx* ctx, int matchup_lo, int matchup_hi, uint
   int rc = launch_native(ctx, matchup_lo, matchup_hi, sim_lo, sim_hi, seed, ctx->hist_scratch, flags);
   if (rc != MLBSIM_OK) return rc;
   CK(ctx, cudaMemcpyAsync(hist_host, ctx->hist_scratch, sizeof(mlbsim_hist) * (size_t)n_m, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  return MLBSIM_OK;
+}
+
+int mlbsim_summarize(mlbsim_ctx* ctx, const mlbsim_hist* hist_dev, int n_matchups, mlbsim_summary* summary_dev) {
+  if (!ctx) return MLBSIM_ERR_ARG;
+  if (!hist_dev || !summary_dev || n_matchups < 0) return fail(ctx, MLBSIM_ERR_ARG, "mlbsim_summarize: bad argument");
+  if (n_matchups == 0) return MLBSIM_OK;
+  CK(ctx, cudaSetDevice(ctx->device));
+  mlbsim_summary_kernel<<<n_matchups, MLBSIM_SUMMARY_THREADS, 0, ctx->stream>>>(hist_dev, summary_dev);
+  CK(ctx, cudaGetLastError());
+  ctx->launches++;
+  return MLBSIM_OK;
+}
+
+int mlbsim_run_native_summary_host(mlbsim_ctx* ctx, int matchup_lo, int matchup_hi, uint64_t sim_lo, uint64_t sim_hi,
+                                   uint64_t seed, mlbsim_summary* summary_host, uint32_t flags) {
+  if (!ctx) return MLBSIM_ERR_ARG;
+  if (!summary_host) return fail(ctx, MLBSIM_ERR_ARG, "summary pointer is NULL");
+  CK(ctx, cudaSetDevice(ctx->device));
+  const int n_m = matchup_hi - matchup_lo;
+  if (n_m <= 0) return fail(ctx, MLBSIM_ERR_ARG, "matchup range out of bounds");
+  if (n_m > ctx->hist_scratch_cap) {
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->hist_scratch);
+    ctx->hist_scratch = nullptr;
+    CK(ctx, cudaMalloc(&ctx->hist_scratch, sizeof(mlbsim_hist) * (size_t)n_m));
+    ctx->hist_scratch_cap = n_m;
+  }
+  if (n_m > ctx->summary_scratch_cap) {
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->summary_scratch);
+    ctx->summary_scratch = nullptr;
+    CK(ctx, cudaMalloc(&ctx->summary_scratch, sizeof(mlbsim_summary) * (size_t)n_m));
+    ctx->summary_scratch_cap = n_m;
+  }
+  CK(ctx, cudaMemsetAsync(ctx->hist_scratch, 0, sizeof(mlbsim_hist) * (size_t)n_m, ctx->stream));
+  int rc = launch_native(ctx, matchup_lo, matchup_hi, sim_lo, sim_hi, seed, ctx->hist_scratch, flags);
+  if (rc != MLBSIM_OK) return rc;
+  rc = mlbsim_summarize(ctx, ctx->hist_scratch, n_m, ctx->summary_scratch);
+  if (rc != MLBSIM_OK) return rc;
+  CK(ctx, cudaMemcpyAsync(summary_host, ctx->summary_scratch, sizeof(mlbsim_summary) * (size_t)n_m, cudaMemcpyDeviceToHost, ctx->stream));
   CK(ctx, cudaStreamSynchronize(ctx->stream));
   return MLBSIM_OK;
 }

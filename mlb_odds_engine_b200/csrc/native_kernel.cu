@@ -38,9 +38,6 @@
 #ifndef OPT_PAD16
 #define OPT_PAD16 1    /* alias rows padded to 16 lineup slots + biased slot counter: row address = ctx bits, lineup wrap = carry */
 #endif
-#ifndef OPT_PA_RED
-#define OPT_PA_RED 1   /* PA outcome counters: 1 = red.shared.add on the thread's own column (measured +2 %), 0 = ld/add/st */
-#endif
 #ifndef NATIVE_LB_THREADS
 #define NATIVE_LB_THREADS MLBSIM_NATIVE_MAX_THREADS
 #endif
@@ -134,7 +131,6 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
   return v;
 }
-__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v)); }
 __device__ __forceinline__ void red_inc_shared(uint32_t addr) { asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr)); }
 
 // ---- per-side context word (one per batting side; `cur` = side at bat, `oth` = the other) -------
@@ -336,11 +332,7 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
 
       if (COUNT_PA) {
         const uint32_t pa = pa_addr + o * pa_stride;
-#if OPT_PA_RED
-        red_inc_shared(pa);
-#else
-        sts32(pa, lds32(pa) + 1u);
-#endif
+        red_inc_shared(pa);   // own column: conflict-free; measured +2 % over ld / add / st
       }
 
       // next batter, one more pitch (pitch_count counts PAs: half_inning_simulator.py:218-220)

@@ -43,8 +43,10 @@ extern "C" __global__ void mlbsim_persim_kernel(const PersimArgs args);
 extern "C" __global__ void mlbsim_native_kernel(const NativeArgs args);
 extern "C" __global__ void mlbsim_replay_kernel(const ReplayArgs args);
 extern "C" __global__ void mlbsim_replay_flat_kernel(const ReplayArgs args, unsigned long long* counter, uint32_t chunk);
+extern "C" __global__ void mlbsim_summary_kernel(const mlbsim_hist* hist, mlbsim_summary* out);
 #endif
 size_t mlbsim_native_smem_bytes(int threads_per_block);
+#define MLBSIM_SUMMARY_THREADS 256
 #ifndef MLBSIM_REPLAY_FLAT_THREADS
 #define MLBSIM_REPLAY_FLAT_THREADS 256
 #endif

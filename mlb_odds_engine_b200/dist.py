@@ -69,6 +69,9 @@ class ShardedSimulator:
             words = n_matchups * _abi.HIST_WORDS
             self.hist_dev = torch.zeros(words, dtype=torch.int64, device=f"cuda:{self.device}")
             self.hist_pinned = torch.zeros(words, dtype=torch.int64).pin_memory()
+            swords = n_matchups * (_abi.SUMMARY_DTYPE.itemsize // 8)
+            self.summary_dev = torch.zeros(swords, dtype=torch.int64, device=f"cuda:{self.device}")
+            self.summary_pinned = torch.zeros(swords, dtype=torch.int64).pin_memory()
             self.n_matchups = n_matchups
 
     def load_matchups(self, matchups, use_noise=True):
@@ -103,3 +106,14 @@ class ShardedSimulator:
         self.hist_pinned.copy_(self.hist_dev, non_blocking=True)
         self.torch.cuda.current_stream().synchronize()
         return self.hist_pinned.numpy().view(np.uint64).view(_abi.HIST_DTYPE).copy()
+
+    def simulate_summary(self, n_sims_total: int, seed: int, sim_lo: int = 0, tables_host=None, count_pa: bool = True) -> np.ndarray:
+        """Sweep-shaped end-to-end call: as `simulate`, but the all-reduced histograms are reduced on the device
+        (`mlbsim_summarize`) and only SUMMARY_DTYPE[n_matchups] (320 B each) crosses PCIe."""
+        if tables_host is not None:
+            self.load_tables(tables_host, self.sim.matchups if len(self.sim.matchups) == len(np.atleast_1d(tables_host)) else None)
+        self.run_device(n_sims_total, seed, sim_lo, count_pa)
+        self.ctx.summarize(self.hist_dev.data_ptr(), self.n_matchups, self.summary_dev.data_ptr())
+        self.summary_pinned.copy_(self.summary_dev, non_blocking=True)
+        self.torch.cuda.current_stream().synchronize()
+        return self.summary_pinned.numpy().view(np.uint64).view(_abi.SUMMARY_DTYPE).copy()

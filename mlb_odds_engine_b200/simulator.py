@@ -118,6 +118,15 @@ class GpuSimulator:
         rec = self.ctx.run_native_host(matchup_lo, hi, sim_lo, sim_lo + int(n_sims), int(seed), 0 if count_pa else 1)
         return [RunHistogram(rec[i], self.matchups[matchup_lo + i]) for i in range(hi - matchup_lo)]
 
+    def simulate_summary(self, n_sims: int, seed: int = 0, sim_lo: int = 0, matchup_lo: int = 0,
+                         matchup_hi: int | None = None, count_pa: bool = True) -> np.ndarray:
+        """Same games as `simulate`, reduced on the device to one SUMMARY_DTYPE record per matchup (outcome counts,
+        run moments, win counts): 320 B per matchup come back instead of 165 KB — the shape of a sweep."""
+        if self._tables is None:
+            raise RuntimeError("load_matchups() first")
+        hi = self.ctx.n_tables if matchup_hi is None else matchup_hi
+        return self.ctx.run_native_summary_host(matchup_lo, hi, sim_lo, sim_lo + int(n_sims), int(seed), 0 if count_pa else 1)
+
     def simulate_persim(self, n_sims: int, seed: int = 0, sim_lo: int = 0, matchup: int = 0) -> np.ndarray:
         """One record per sim (REPLAY_GAME_DTYPE) — the same games `simulate` counts."""
         return self.ctx.run_persim(matchup, sim_lo, sim_lo + int(n_sims), int(seed))

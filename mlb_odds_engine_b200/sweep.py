@@ -81,24 +81,32 @@ def pooled_rates(row: dict) -> dict:
 
 def run_sweep(matchups: list[dict], n_sims: int = 100_000, seed: int = 0, sim: GpuSimulator | None = None,
               use_noise: bool = True) -> list[dict]:
-    """Per grid point: outcome rates per batting side (what the tools print from PA_RECAP_LOG,
-    tools/test_stuff_plus_sensitivity.py:71-77), mean runs and home-win probability."""
+    """Per grid point: outcome counts and rates per batting side (what the tools print from PA_RECAP_LOG,
+    tools/test_stuff_plus_sensitivity.py:71-77), mean runs, run SDs and home-win probability — from the device-side
+    summaries (`mlbsim_summarize`), so a 1 024-point sweep moves 320 KB over PCIe instead of 168 MB."""
     own = sim is None
     sim = sim or GpuSimulator(0)
     sim.load_matchups(matchups, use_noise=use_noise)
-    hists = sim.simulate(n_sims, seed=seed)
-    rows = []
-    for h in hists:
-        pa = h.rec["pa"][:, :7].astype(np.float64)
-        home_mean, away_mean = h.mean_scores()
-        rows.append({
-            "counts": {team: {o: int(pa[s, i]) for i, o in enumerate(_abi.OUTCOMES)}
-                       for s, team in ((0, "AWAY"), (1, "HOME"))},
-            "rates": {team: {o: float(pa[s, i] / max(pa[s].sum(), 1.0)) for i, o in enumerate(_abi.OUTCOMES)}
-                      for s, team in ((0, "AWAY"), (1, "HOME"))},
-            "pa_per_game": float(pa.sum() / h.n_games),
-            "home_runs_mean": home_mean, "away_runs_mean": away_mean, "home_win": h.home_win_prob(),
-        })
+    rows = [summary_row(r) for r in sim.simulate_summary(n_sims, seed=seed)]
     if own:
         sim.close()
     return rows
+
+
+def summary_row(r) -> dict:
+    """One SUMMARY_DTYPE record -> the row `run_sweep` reports."""
+    n = max(int(r["n_games"]), 1)
+    pa = r["pa"][:, :7].astype(np.float64)
+    away_mean, home_mean = (float(r["sum_runs"][_abi.N_CAPS - 1][s]) / n for s in (0, 1))
+    away_sd, home_sd = (max(float(r["sum_sq"][s]) / n - m * m, 0.0) ** 0.5 for s, m in ((0, away_mean), (1, home_mean)))
+    return {
+        "counts": {team: {o: int(pa[s, i]) for i, o in enumerate(_abi.OUTCOMES)} for s, team in ((0, "AWAY"), (1, "HOME"))},
+        "rates": {team: {o: float(pa[s, i] / max(pa[s].sum(), 1.0)) for i, o in enumerate(_abi.OUTCOMES)}
+                  for s, team in ((0, "AWAY"), (1, "HOME"))},
+        "pa_per_game": float(pa.sum() / n),
+        "home_runs_mean": home_mean, "away_runs_mean": away_mean, "home_runs_sd": home_sd, "away_runs_sd": away_sd,
+        "home_win": float(int(r["home_wins"]) / n), "away_win": float(int(r["away_wins"]) / n),
+        "innings_mean": float(int(r["sum_innings"]) / n),
+        "segment_runs_mean": {f"f{cap}": {"away": float(r["sum_runs"][c][0]) / n, "home": float(r["sum_runs"][c][1]) / n}
+                              for c, cap in enumerate(_abi.CAPS[:-1])},
+    }

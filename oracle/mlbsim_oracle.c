@@ -628,3 +628,4 @@ size_t oracle_sizeof_params(void) { return sizeof(mlbsim_params); }
 size_t oracle_sizeof_table(void) { return sizeof(mlbsim_table); }
 size_t oracle_sizeof_hist(void) { return sizeof(mlbsim_hist); }
 size_t oracle_sizeof_replay_game(void) { return sizeof(mlbsim_replay_game); }
+size_t oracle_sizeof_summary(void) { return sizeof(mlbsim_summary); }

@@ -50,13 +50,13 @@ def lib():
         L.oracle_native_key.restype = u32
         L.oracle_set_threads.argtypes = [ctypes.c_int]
         L.oracle_get_threads.restype = ctypes.c_int
-        for f in ("params", "table", "hist", "replay_game"):
+        for f in ("params", "table", "hist", "replay_game", "summary"):
             getattr(L, f"oracle_sizeof_{f}").restype = ctypes.c_size_t
         _lib = L
         from mlb_odds_engine_b200 import _abi
 
         _abi.check_sizes(lambda w: [L.oracle_sizeof_params, L.oracle_sizeof_table, L.oracle_sizeof_hist,
-                                    L.oracle_sizeof_replay_game][w]())
+                                    L.oracle_sizeof_replay_game, L.oracle_sizeof_summary][w]())
     return _lib
 
 

@@ -144,3 +144,30 @@ def test_params_roundtrip_fields():
     assert p["bullpen_len"].tolist() == [5, 0] and p["lineup_len"].tolist() == [9, 9]
     hr = g["matchup"]["home_pitcher"]["hr_pa"]["hr_pa_projected"] * 1.12
     assert p["pit_hr"][0, 0] == hr
+
+
+def test_summary_host_statement_on_oracle_histogram():
+    """`_abi.summarize_hist` (what mlbsim_summarize must equal) against per-sim records of the same games."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "oracle"))
+    import oracle as orc
+    from mlb_odds_engine_b200 import _abi, sweep
+
+    t = tables.build_tables([synth.make_matchup()])
+    n = 5000
+    rec = orc.native(t, 0, 0, n, 3).reshape(-1)[0]
+    games = orc.native_persim(t, 0, 0, n, 3)
+    s = _abi.summarize_hist(rec)
+    a, h = games["away_score"].astype(np.int64), games["home_score"].astype(np.int64)
+    assert int(s["n_games"]) == n
+    assert int(s["sum_runs"][4][0]) == a.sum() and int(s["sum_runs"][4][1]) == h.sum()
+    assert int(s["sum_sq"][0]) == (a * a).sum() and int(s["sum_sq"][1]) == (h * h).sum() and int(s["sum_cross"]) == (a * h).sum()
+    assert int(s["home_wins"]) == (h > a).sum() and int(s["away_wins"]) == (a > h).sum()
+    assert int(s["sum_innings"]) == games["n_innings"].astype(np.int64).sum()
+    for c, cap in enumerate((1, 3, 5, 7)):
+        assert int(s["sum_runs"][c][0]) == games["away_runs"][:, :cap].astype(np.int64).sum()
+        assert int(s["sum_runs"][c][1]) == games["home_runs"][:, :cap].astype(np.int64).sum()
+    assert np.array_equal(s["pa"], rec["pa"])
+    row = sweep.summary_row(s)
+    assert abs(row["home_runs_sd"] - h.std()) < 1e-9 and abs(row["innings_mean"] - games["n_innings"].mean()) < 1e-12
+    assert abs(sum(row["rates"]["HOME"].values()) - 1.0) < 1e-12
