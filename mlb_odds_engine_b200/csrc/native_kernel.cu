@@ -17,9 +17,11 @@
 //     from a global counter.  Sim i draws Philox2x32-10 blocks with counter (i, draw number,
 //     kind, matchup) and a key derived from the seed (philox.cuh), so which lane / block / GPU
 //     runs it is irrelevant to its result;
-//   * the per-matchup alias table (16 KB, one word read per PA), the transition LUT (2.6 KB) and
-//     the five joint (away, home) histograms (20 KB of u32 bins) live in shared memory; histograms
-//     are flushed to the uint64 device totals once per (block, matchup);
+//   * the per-matchup alias table (28 KB as staged: rows padded to 16 lineup slots, one word read
+//     per PA), the transition LUT (5 KB) and the five joint (away, home) histograms (20 KB of u32
+//     bins) live in shared memory; histograms are flushed to the uint64 device totals once per
+//     (block, matchup).  The state words are laid out so that table addresses are bit fields of the
+//     state (see the "side context" and "half-inning state" comments below);
 //   * no tensor cores: there is no dense contraction in this path.
 #include <cuda_runtime.h>
 #include <stddef.h>
@@ -99,7 +101,7 @@ constexpr uint32_t DYN_PA_WORD0 = DYN_ALIAS_BYTES / 4u;
 
 }  // namespace
 
-// Statically allocated (44 KB) at global scope so that its PTX symbol keeps this plain name: the
+// Statically allocated (30 KB) at global scope so that its PTX symbol keeps this plain name: the
 // hot loop takes `mov.u32 r, mlbsim_S` (a link-time constant in the .shared space) as its base and
 // every access becomes LDS [Rindex + imm] with no generic->shared conversion in the loop.
 // Dynamic shared memory holds (OPT_PAD16) the alias table re-laid as [side][pitcher][tier][16 slots][8 words]: the low nine bits of a side's
