@@ -19,6 +19,7 @@ struct mlbsim_ctx {
   cudaDeviceProp prop{};
   mlbsim_table* tables_dev = nullptr;
   int n_tables = 0;
+  int tables_cap = 0;
   unsigned long long* counters_dev = nullptr;
   int counters_cap = 0;
   mlbsim_hist* hist_scratch = nullptr;  // used by *_host entry points
@@ -173,11 +174,13 @@ int mlbsim_upload_tables(mlbsim_ctx* ctx, const mlbsim_table* tables, int n_matc
     }
   }
   CK(ctx, cudaSetDevice(ctx->device));
-  if (n_matchups > ctx->n_tables || !ctx->tables_dev) {
+  if (n_matchups > ctx->tables_cap) {
     CK(ctx, cudaStreamSynchronize(ctx->stream));
     cudaFree(ctx->tables_dev);
     ctx->tables_dev = nullptr;
+    ctx->tables_cap = ctx->n_tables = 0;
     CK(ctx, cudaMalloc(&ctx->tables_dev, sizeof(mlbsim_table) * (size_t)n_matchups));
+    ctx->tables_cap = n_matchups;
   }
   if (n_matchups > ctx->counters_cap) {
     CK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -338,10 +341,10 @@ int mlbsim_run_replay_dev(mlbsim_ctx* ctx, const mlbsim_params* params_host, con
     if (params_host->bullpen_len[s] < 0 || params_host->bullpen_len[s] > MLBSIM_MAX_BULLPEN) return fail(ctx, MLBSIM_ERR_ARG, "bullpen_len out of range");
   }
   if (n_games == 0) return MLBSIM_OK;
+  if (n_games >= (1ll << 32)) return fail(ctx, MLBSIM_ERR_ARG, "more than 2^32 - 1 games per replay call");
   CK(ctx, cudaSetDevice(ctx->device));
   CK(ctx, cudaMemcpyAsync(ctx->params_dev, params_host, sizeof(mlbsim_params), cudaMemcpyHostToDevice, ctx->stream));
   ReplayArgs a{ctx->params_dev, tape_dev, tape_offsets_dev, out_dev, (long long)n_games};
-  if (n_games >= (1ll << 32)) return fail(ctx, MLBSIM_ERR_ARG, "more than 2^32 - 1 games per replay call");
   if (ctx->counters_cap < 1) {
     CK(ctx, cudaMalloc(&ctx->counters_dev, sizeof(unsigned long long)));
     ctx->counters_cap = 1;
@@ -426,25 +429,32 @@ int mlbsim_run_persim(mlbsim_ctx* ctx, int matchup, uint64_t sim_lo, uint64_t si
   const uint64_t n = sim_hi - sim_lo;
   if (n == 0) return MLBSIM_OK;
   CK(ctx, cudaSetDevice(ctx->device));
+  // bounded device scratch: records leave in slices of at most 4 Mi sims (704 MB), whatever n is
+  const uint64_t SLICE = 4ull << 20;
+  const uint64_t cap_n = n < SLICE ? n : SLICE;
   mlbsim_replay_game* out_dev = nullptr;
-  CK(ctx, cudaMalloc(&out_dev, sizeof(mlbsim_replay_game) * (size_t)n));
-  PersimArgs a;
-  a.table = ctx->tables_dev + matchup;
-  a.out = out_dev;
-  a.sim_lo = sim_lo;
-  a.n_sims = n;
-  a.matchup_id = (uint32_t)matchup;
-  a.keys = philox2_keys_from_seed(seed);
-  const int threads = 128;
-  uint64_t blocks = (n + threads - 1) / threads;
-  const uint64_t cap = (uint64_t)ctx->prop.multiProcessorCount * 16;
-  if (blocks > cap) blocks = cap;
-  mlbsim_persim_kernel<<<(int)blocks, threads, 0, ctx->stream>>>(a);
-  cudaError_t e = cudaGetLastError();
-  if (e == cudaSuccess) e = cudaMemcpyAsync(out_host, out_dev, sizeof(mlbsim_replay_game) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  CK(ctx, cudaMalloc(&out_dev, sizeof(mlbsim_replay_game) * (size_t)cap_n));
+  cudaError_t e = cudaSuccess;
+  for (uint64_t done = 0; done < n && e == cudaSuccess; done += cap_n) {
+    const uint64_t m = (n - done) < cap_n ? (n - done) : cap_n;
+    PersimArgs a;
+    a.table = ctx->tables_dev + matchup;
+    a.out = out_dev;
+    a.sim_lo = sim_lo + done;
+    a.n_sims = m;
+    a.matchup_id = (uint32_t)matchup;
+    a.keys = philox2_keys_from_seed(seed);
+    const int threads = 128;
+    uint64_t blocks = (m + threads - 1) / threads;
+    const uint64_t cap = (uint64_t)ctx->prop.multiProcessorCount * 16;
+    if (blocks > cap) blocks = cap;
+    mlbsim_persim_kernel<<<(int)blocks, threads, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_host + done, out_dev, sizeof(mlbsim_replay_game) * (size_t)m, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  }
   cudaFree(out_dev);
-  ctx->launches++;
   if (e != cudaSuccess) {
     ctx->err = std::string("mlbsim_run_persim: ") + cudaGetErrorString(e);
     return MLBSIM_ERR_CUDA;
