@@ -75,14 +75,18 @@ typedef struct mlbsim_replay_game {
 } mlbsim_replay_game;
 
 /* ---- native mode: per-matchup integer sampling table -----------------------------------------
- * One PA consumes one Philox4x32-10 block (w0..w3).  The outcome over K BB 1B 2B 3B HR OUT is
- * drawn from w0 with Walker's alias method on 8 columns (column 7 has no mass of its own):
+ * One PA consumes one Philox2x32-10 block (w0, w1).  w0 draws one of EIGHT variants with Walker's
+ * alias method on 8 columns — the seven outcomes K BB 1B 2B 3B HR OUT, with the single split by the
+ * independent 0.8 draw "runner on first takes second" (core/half_inning_simulator.py:105):
+ * variant 2 = single, runner holds; variant 7 (MLBSIM_V_1B_ADV) = single, runner advances:
  *     col = w0 >> 29;  e = alias[side][pit][tier][slot][col];
- *     outcome = ((w0 & 0x1FFFFFFF) < (e >> 3)) ? col : (e & 7)
+ *     variant = ((w0 & 0x1FFFFFFF) < (e >> 3)) ? col : (e & 7)
  * i.e. one table word per PA.  Starters past 75 pitches (fatigue_modeling.py:38; only possible
  * for a staff without a bullpen, MLBSIM_FLAG_FATIGUE) use cumulative 31-bit thresholds instead:
- *     u = w0 >> 1;  outcome = #{ j < 6 : u >= fthr[..][j] + (pitch_count - 75) * fslope[..][j] }   */
-#define MLBSIM_TABLE_MAGIC 0x4d4c4254u /* "MLBT" */
+ *     u = w0 >> 1;  outcome = #{ j < 6 : u >= fthr[..][j] + (pitch_count - 75) * fslope[..][j] }
+ * and take the 0.8 draw from the low 16 bits of w1.                                              */
+#define MLBSIM_TABLE_MAGIC 0x4d4c4232u /* "2BLM": alias rows hold the 8 draw variants */
+#define MLBSIM_V_1B_ADV 7
 #define MLBSIM_ROW_WORDS 8
 #define MLBSIM_FLAG_FATIGUE 1u /* some staff has no bullpen: pitch_count can exceed 75 */
 

@@ -65,12 +65,12 @@ constexpr int FATIGUE_START = 75;            // fatigue_modeling.py:38
 constexpr int SB = 32;                                    // smem joint-histogram bins per team
 constexpr int ALIAS_WORDS = 2 * MLBSIM_MAX_PITCHERS * MLBSIM_N_TIERS * MLBSIM_MAX_LINEUP * MLBSIM_ROW_WORDS;  // 4032
 constexpr int FAT_WORDS = 2 * MLBSIM_N_TIERS * MLBSIM_MAX_LINEUP * MLBSIM_ROW_WORDS;                          // 576
-// transition LUT: one row per (outs*8 + bases): words 0-31 = [outcome (8 slots)][dA][dB] entries, words 32-39 =
-// the sub-draw A threshold of each outcome at this number of outs.  41 words per row (odd): lanes in different
-// (outs, bases) states that look up the same (outcome, dA, dB) hit different banks.
-constexpr int LUT_ROW_WORDS = 41;
-constexpr int LUT_WORDS = 32 * LUT_ROW_WORDS;                                                                  // 1312
-constexpr uint32_t LUT_TA_BYTE = 32u * 4u;
+// transition LUT: one row per (outs*8 + bases): words 0-15 = [draw variant (8)][dA] entries, words 16-23 = the
+// sub-draw A threshold of each variant at this number of outs.  25 words per row (odd): lanes in different
+// (outs, bases) states that look up the same (variant, dA) hit different banks.
+constexpr int LUT_ROW_WORDS = 25;
+constexpr int LUT_WORDS = 32 * LUT_ROW_WORDS;                                                                  // 800
+constexpr uint32_t LUT_TA_BYTE = 16u * 4u;
 constexpr int JOINT_WORDS = MLBSIM_N_CAPS * SB * SB;                                                          // 5120
 
 constexpr int PAD_SLOTS = 16;
@@ -92,7 +92,7 @@ struct __align__(16) Smem {
   uint32_t hdr_flags, L0, L1, nb0, nb1;
   uint32_t go;  // block-uniform "this matchup still has work"
 };
-constexpr int PA_FIELDS = 14;  // [side][outcome]
+constexpr int PA_FIELDS = 16;  // [side][draw variant]: the two single variants are added up at the flush
 // Dynamic shared memory: [padded alias table (OPT_PAD16)] [pa[14][PA_STRIDE]].  The counter stride is the
 // compile-time maximum block size, not blockDim.x, so that `outcome * stride` is an immediate multiply.
 constexpr uint32_t PA_STRIDE = MLBSIM_NATIVE_MAX_THREADS;
@@ -233,7 +233,7 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
   const uint32_t A_RELP = sb + (uint32_t)offsetof(Smem, rel_picks);
   // per-thread PA counters: pa[f][tid], f = side*7 + outcome
   constexpr uint32_t pa_stride = PA_STRIDE * 4u;  // bytes between outcomes
-  constexpr uint32_t pa_side = 7u * pa_stride;    // bytes between sides
+  constexpr uint32_t pa_side = 8u * pa_stride;    // bytes between sides
   const uint32_t pa_mine = smem_dynamic_base() + DYN_ALIAS_BYTES + threadIdx.x * 4u;
 
   // ---- warp-uniform work state ----
@@ -308,7 +308,7 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
       const uint32_t row = (side * (MLBSIM_MAX_PITCHERS * MLBSIM_N_TIERS) + T) * MLBSIM_MAX_LINEUP + slot;
       const uint32_t e = lds32(A_ALIAS + ((row * MLBSIM_ROW_WORDS + col) << 2));
 #endif
-      uint32_t o = ((w0 & 0x1FFFFFFFu) < (e >> 3)) ? col : (e & 7u);
+      uint32_t o = ((w0 & 0x1FFFFFFFu) < (e >> 3)) ? col : (e & 7u);   // draw variant 0..7 (7 = single, runner on first advances)
       if (FATIGUE) {
 #if OPT_PAD16
         side = hidx & 1u;
@@ -322,14 +322,16 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
           o = 0;
 #pragma unroll
           for (int j = 0; j < 6; ++j) o += (u >= lds32(A_FTHR + srow + 4 * j) + ex * lds32(A_FSLOPE + srow + 4 * j)) ? 1u : 0u;
+          // thresholds know seven outcomes: the single's 0.8 draw comes from the low half of w1 here
+          if (o == (uint32_t)MLBSIM_1B && (w1 & 0xFFFFu) < T_080_16) o = MLBSIM_V_1B_ADV;
         }
       }
 
-      // base-running sub-draws from w1: A = full 32-bit compare, B = its low 16 bits
+      // base-running sub-draw A from w1 (full 32-bit compare); sub-draw B arrived inside the variant
       const uint32_t o4 = o << 2;
       const uint32_t lut_row = A_LUT + (hs & HS_ROW);
       const uint32_t tA = lds32(lut_row + LUT_TA_BYTE + o4);
-      const uint32_t ent = lds32(lut_row + (o4 << 2) + (w1 < tA ? 8u : 0u) + ((w1 & 0xFFFFu) < T_080_16 ? 4u : 0u));
+      const uint32_t ent = lds32(lut_row + (o4 << 1) + (w1 < tA ? 4u : 0u));
       hs = (hs & HS_KEEP) + HS_PA_ONE + ent;
 
       if (COUNT_PA) {
@@ -429,14 +431,16 @@ mlbsim_native_kernel(const NativeArgs args) {
   for (int i = tid; i < LUT_WORDS; i += blockDim.x) {
     const int ob = i / LUT_ROW_WORDS, w = i % LUT_ROW_WORDS;
     uint32_t v = 0;
-    if (w < 32) {
-      const int o = w >> 2, dA = (w >> 1) & 1, dB = w & 1;
-      const uint32_t e = transition_entry(o < 7 ? o : MLBSIM_OUT, dA, dB, ob >> 3, ob & 7);
+    if (w < 16) {
+      const int var = w >> 1, dA = w & 1;
+      const int o = var == MLBSIM_V_1B_ADV ? (int)MLBSIM_1B : var, dB = var == MLBSIM_V_1B_ADV;
+      const uint32_t e = transition_entry(o, dA, dB, ob >> 3, ob & 7);
       // re-pack into the state word's fields; the next (outs*8 + bases) becomes the byte offset of its row
       v = (e & 31u) * (uint32_t)(LUT_ROW_WORDS * 4) | (((e >> 16) & 7u) << HS_RUNS_SHIFT) | (((e >> 24) & 1u) << HS_REACHED_SHIFT) |
           (((e >> 30) & 1u) ? HS_3OUT : 0u);
-    } else if (w < 40) {
-      v = subdraw_a_threshold(w - 32, (ob >> 3) == 2);
+    } else if (w < 24) {
+      const int var = w - 16;
+      v = subdraw_a_threshold(var == MLBSIM_V_1B_ADV ? (int)MLBSIM_1B : var, (ob >> 3) == 2);
     }
     S.lut[i] = v;
   }
@@ -503,7 +507,8 @@ mlbsim_native_kernel(const NativeArgs args) {
     if (count_pa) {
       for (int f = 0; f < PA_FIELDS; ++f) {
         const uint32_t v = __reduce_add_sync(0xffffffffu, S_pa[DYN_PA_WORD0 + f * PA_STRIDE + tid]);
-        if (lane == 0 && v) atomicAdd(&H[H_PA + (f / 7) * 8 + (f % 7)], (unsigned long long)v);
+        const int var = f & 7;
+        if (lane == 0 && v) atomicAdd(&H[H_PA + (f >> 3) * 8 + (var == MLBSIM_V_1B_ADV ? (int)MLBSIM_1B : var)], (unsigned long long)v);
       }
     }
     __syncthreads();
@@ -573,6 +578,7 @@ mlbsim_persim_kernel(const PersimArgs args) {
           if (sl == 0 && n > 0) tto[side] += 1;
           const int tier = (tto[side] >= 4 ? 4 : tto[side]) - 1;
           int o;
+          bool dB;
           if ((T->flags & MLBSIM_FLAG_FATIGUE) && pit[side] == 0 && pc[side] > FATIGUE_START) {
             const uint32_t* row = T->fthr[side][tier][sl];
             const int32_t* sp = T->fslope[side][tier][sl];
@@ -581,13 +587,16 @@ mlbsim_persim_kernel(const PersimArgs args) {
             o = 0;
 #pragma unroll
             for (int j = 0; j < 6; ++j) o += (u >= row[j] + e * (uint32_t)sp[j]) ? 1 : 0;
+            dB = (w1 & 0xFFFFu) < T_080_16;
           } else {
             const uint32_t col = w0 >> 29;
             const uint32_t e = T->alias[side][pit[side]][tier][sl][col];
             o = ((w0 & 0x1FFFFFFFu) < (e >> 3)) ? (int)col : (int)(e & 7u);
+            dB = o == MLBSIM_V_1B_ADV;
+            if (dB) o = MLBSIM_1B;
           }
           const uint32_t tA = subdraw_a_threshold(o, outs == 2);
-          const uint32_t ent = transition_entry(o, w1 < tA, (w1 & 0xFFFFu) < T_080_16, outs, bases);
+          const uint32_t ent = transition_entry(o, w1 < tA, dB, outs, bases);
           const int r = (ent >> 16) & 7;
           outs = (ent & 31u) >> 3; bases = ent & 7u; runs += r;
           if ((ent >> 24) & 1u) reached = true;

@@ -335,14 +335,30 @@ def _quantise(cdf):
 
 ALIAS_COLS = 8
 ALIAS_FRAC_BITS = 29
+VARIANT_1B_ADVANCE = 7      # include/mlbsim.h MLBSIM_V_1B_ADV: single on which a runner on 1B takes second
+P_FIRST_TO_SECOND = 0.8     # core/half_inning_simulator.py:105
+
+
+def outcome_variants(probs) -> np.ndarray:
+    """[..., 7] outcome probabilities -> [..., 8] alias-draw variants: the single is split by the independent
+    0.8 draw "runner on first takes second" (half_inning_simulator.py:105), so that draw costs the kernel nothing:
+    variant 2 = single, runner holds (0.2), variant 7 = single, runner advances (0.8)."""
+    probs = np.asarray(probs, dtype=np.float64)
+    out = np.empty(probs.shape[:-1] + (8,))
+    out[..., :7] = probs
+    adv = probs[..., 2] * P_FIRST_TO_SECOND
+    out[..., 7] = adv
+    out[..., 2] = probs[..., 2] - adv
+    return out
 
 
 def alias_row(p) -> np.ndarray:
-    """Walker/Vose alias table for the 7 outcome probabilities `p` on 8 columns (column 7 carries
+    """Walker/Vose alias table for 7 or 8 probabilities `p` on 8 columns (with 7, column 7 carries
     no mass of its own).  Entry = cut << 3 | alias with cut in [0, 2^29): a draw w0 picks column
     w0 >> 29 and keeps the column's own outcome iff (w0 & (2^29 - 1)) < cut.  Deterministic."""
+    n_own = len(p)
     q = np.zeros(ALIAS_COLS)
-    q[:7] = np.asarray(p, dtype=np.float64) * ALIAS_COLS / float(np.sum(p))
+    q[:n_own] = np.asarray(p, dtype=np.float64) * ALIAS_COLS / float(np.sum(p))
     cut = np.ones(ALIAS_COLS)
     alias = np.arange(ALIAS_COLS)
     small = [i for i in range(ALIAS_COLS) if q[i] < 1.0]
@@ -356,15 +372,15 @@ def alias_row(p) -> np.ndarray:
         (small if q[g] < 1.0 else large).append(g)
     for i in small + large:      # leftovers are full columns up to rounding
         cut[i] = 1.0
-        alias[i] = i if i < 7 else int(np.argmax(p))
+        alias[i] = i if i < n_own else int(np.argmax(p))
     one = 1 << ALIAS_FRAC_BITS
     out = np.zeros(ALIAS_COLS, dtype=np.uint32)
     for i in range(ALIAS_COLS):
         c = int(math.floor(cut[i] * one + 0.5))
         a = int(alias[i])
         if c >= one:             # full column: encode as "always alias" with alias = own outcome
-            c, a = 0, (i if i < 7 else a)
-        if i == 7:
+            c, a = 0, (i if i < n_own else a)
+        if i >= n_own:
             c = 0
         c = max(c, 0)
         out[i] = (c << 3) | a
@@ -372,12 +388,12 @@ def alias_row(p) -> np.ndarray:
 
 
 def alias_rows(P) -> np.ndarray:
-    """`alias_row` for N rows at once ([N, 7] probabilities -> [N, 8] uint32): the same stack discipline
+    """`alias_row` for N rows at once ([N, 7 or 8] probabilities -> [N, 8] uint32): the same stack discipline
     (highest column first) run in lock step over all rows, so the result is identical entry for entry."""
     P = np.asarray(P, dtype=np.float64)
-    N = len(P)
+    N, n_own = P.shape
     q = np.zeros((N, ALIAS_COLS))
-    q[:, :7] = P * ALIAS_COLS / P.sum(axis=1)[:, None]
+    q[:, :n_own] = P * ALIAS_COLS / P.sum(axis=1)[:, None]
     cut = np.ones((N, ALIAS_COLS))
     alias = np.tile(np.arange(ALIAS_COLS), (N, 1))
     small = np.zeros((N, ALIAS_COLS), dtype=np.int64)
@@ -414,24 +430,31 @@ def alias_rows(P) -> np.ndarray:
             r = np.nonzero(depth > j)[0]
             col = stack[r, j]
             cut[r, col] = 1.0
-            alias[r, col] = np.where(col < 7, col, top[r])
+            alias[r, col] = np.where(col < n_own, col, top[r])
     one = 1 << ALIAS_FRAC_BITS
     c = np.floor(cut * one + 0.5).astype(np.int64)
     cols = np.arange(ALIAS_COLS)[None, :]
     full = c >= one
-    a = np.where(full & (cols < 7), cols, alias)
-    c = np.where(full | (cols == 7), 0, np.maximum(c, 0))
+    a = np.where(full & (cols < n_own), cols, alias)
+    c = np.where(full | (cols >= n_own), 0, np.maximum(c, 0))
     return ((c << 3) | a).astype(np.uint32)
 
 
-def alias_probabilities(row) -> np.ndarray:
-    """Exact outcome probabilities an alias row encodes (for tests)."""
+def alias_variant_probabilities(row) -> np.ndarray:
+    """Exact probabilities of the 8 draw variants an alias row encodes (for tests)."""
     one = float(1 << ALIAS_FRAC_BITS)
     p = np.zeros(8)
     for col in range(ALIAS_COLS):
         c, a = int(row[col]) >> 3, int(row[col]) & 7
         p[col] += c / one / ALIAS_COLS
         p[a] += (1.0 - c / one) / ALIAS_COLS
+    return p
+
+
+def alias_probabilities(row) -> np.ndarray:
+    """Exact probabilities of the 7 outcomes a table row encodes (both single variants count as 1B)."""
+    p = alias_variant_probabilities(row)
+    p[2] += p[VARIANT_1B_ADVANCE]
     return p[:7]
 
 
@@ -509,7 +532,7 @@ def build_tables(matchups, use_noise=True) -> np.ndarray:
         out["lineup_len"][i] = m.lineup_len
         out["bullpen_len"][i] = m.bullpen_len
     I, S, P, T, B = (np.concatenate(x) for x in zip(*where))
-    alias[I, S, P, T, B] = alias_rows(np.concatenate(rows))
+    alias[I, S, P, T, B] = alias_rows(outcome_variants(np.concatenate(rows)))
     out["magic"] = _abi.TABLE_MAGIC
     out["alias"], out["fthr"], out["fslope"] = alias, fthr, fslope
     return out

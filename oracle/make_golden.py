@@ -134,11 +134,12 @@ def main():
     ap.add_argument("--stats", action="store_true", help="also regenerate the statistical fixtures (minutes)")
     ap.add_argument("--stats-games", type=int, default=200000)
     ap.add_argument("--only", default=None)
+    ap.add_argument("--no-replay", action="store_true", help="leave the replay fixtures alone (with --stats)")
     args = ap.parse_args()
     os.makedirs(GOLDEN, exist_ok=True)
     sc = scenarios()
     for i, (name, (m, noise, n)) in enumerate(sc.items()):
-        if args.only and args.only != name:
+        if args.no_replay or (args.only and args.only != name):
             continue
         make_replay(name, m, noise, n, seed=1000 + i)
     if args.stats:
@@ -212,6 +213,8 @@ def make_distribution_fixture(n_sims=10000, seed=20250404, game_id="2025-04-04-T
         "pitchers": starters,
         "bullpens": {"home": matchup["home_bullpen"], "away": matchup["away_bullpen"]},
     }
+    import tempfile
+    os.chdir(tempfile.mkdtemp(prefix="mlbsim_golden_"))   # the reference reads and writes CWD-relative paths
     os.makedirs("logs", exist_ok=True)
     shutil.copy(os.path.join(rh.REFERENCE_ROOT, "logs", "calibration_offset.json"), "logs/calibration_offset.json")
     rds.simulate_distribution(game_id, 9.5, no_weather=True, export_json="./dist_out.json", n_simulations=n_sims)

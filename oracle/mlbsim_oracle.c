@@ -535,7 +535,7 @@ static void native_game(const mlbsim_table* T, uint32_t matchup, uint32_t key, u
         if (n == 0) w1_first = w[1]; /* bases empty: this w1 never reaches the transition -> end-of-half draw */
         if (sl == 0 && n > 0) st[side].tto += 1;
         int tier = (st[side].tto >= 4 ? 4 : st[side].tto) - 1;
-        int o;
+        int o, dB;
         if ((T->flags & MLBSIM_FLAG_FATIGUE) && st[side].pit == 0 && st[side].pc > 75) {
           /* starter past 75 pitches: cumulative thresholds + per-pitch slope */
           const uint32_t* row = T->fthr[side][tier][sl];
@@ -544,14 +544,18 @@ static void native_game(const mlbsim_table* T, uint32_t matchup, uint32_t key, u
           uint32_t u = w[0] >> 1;
           o = 0;
           for (int j = 0; j < 6; ++j) o += (u >= row[j] + e * (uint32_t)sp[j]);
+          dB = (w[1] & 0xFFFFu) < T_080_16; /* runner on first takes second on a single: low half of w1 */
         } else {
-          /* Walker alias draw: one table word per PA */
+          /* Walker alias draw over the eight variants: one table word per PA; the single arrives already split
+             by the 0.8 draw (variant 7 = single on which the runner on first advances) */
           uint32_t col = w[0] >> 29;
           uint32_t e = T->alias[side][st[side].pit][tier][sl][col];
           o = ((w[0] & 0x1FFFFFFFu) < (e >> 3)) ? (int)col : (int)(e & 7u);
+          dB = (o == MLBSIM_V_1B_ADV);
+          if (dB) o = MLBSIM_1B;
         }
         uint32_t tA = (o == MLBSIM_1B) ? (outs == 2 ? T_046 : T_040) : (o == MLBSIM_2B) ? T_040 : T_DP;
-        int dA = w[1] < tA, dB = (w[1] & 0xFFFFu) < T_080_16;
+        int dA = w[1] < tA;
         uint32_t t = native_transition(o, dA, dB, outs, bases);
         int r = (t >> 3) & 7;
         bases = t & 7; outs += t >> 6; runs += r;
