@@ -65,12 +65,12 @@ constexpr int FATIGUE_START = 75;            // fatigue_modeling.py:38
 constexpr int SB = 32;                                    // smem joint-histogram bins per team
 constexpr int ALIAS_WORDS = 2 * MLBSIM_MAX_PITCHERS * MLBSIM_N_TIERS * MLBSIM_MAX_LINEUP * MLBSIM_ROW_WORDS;  // 4032
 constexpr int FAT_WORDS = 2 * MLBSIM_N_TIERS * MLBSIM_MAX_LINEUP * MLBSIM_ROW_WORDS;                          // 576
-// transition LUT: one row per (outs*8 + bases): words 0-15 = [draw variant (8)][dA] entries, words 16-23 = the
-// sub-draw A threshold of each variant at this number of outs.  25 words per row (odd): lanes in different
-// (outs, bases) states that look up the same (variant, dA) hit different banks.
-constexpr int LUT_ROW_WORDS = 25;
-constexpr int LUT_WORDS = 32 * LUT_ROW_WORDS;                                                                  // 800
-constexpr uint32_t LUT_TA_BYTE = 16u * 4u;
+// transition LUT: one row per (outs*8 + bases), eight 16-byte groups per row, one per draw variant:
+// {sub-draw A threshold at this number of outs, entry if A fails, entry if A succeeds, 0} — one LDS.128 per PA.
+// Row stride 36 words: consecutive rows start one 16-byte bank group apart, so lanes in different
+// (outs, bases) states that look up the same variant do not collide.
+constexpr int LUT_ROW_WORDS = 36;
+constexpr int LUT_WORDS = 32 * LUT_ROW_WORDS;                                                                  // 1152
 constexpr int JOINT_WORDS = MLBSIM_N_CAPS * SB * SB;                                                          // 5120
 
 constexpr int PAD_SLOTS = 16;
@@ -131,6 +131,11 @@ __device__ __forceinline__ uint32_t smem_dynamic_base() {
 __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
   uint32_t v;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
   return v;
 }
 __device__ __forceinline__ void red_inc_shared(uint32_t addr) { asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr)); }
@@ -327,11 +332,10 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
         }
       }
 
-      // base-running sub-draw A from w1 (full 32-bit compare); sub-draw B arrived inside the variant
-      const uint32_t o4 = o << 2;
-      const uint32_t lut_row = A_LUT + (hs & HS_ROW);
-      const uint32_t tA = lds32(lut_row + LUT_TA_BYTE + o4);
-      const uint32_t ent = lds32(lut_row + (o4 << 1) + (w1 < tA ? 4u : 0u));
+      // base-running sub-draw A from w1 (full 32-bit compare against the group's threshold); sub-draw B
+      // arrived inside the variant
+      const uint4 g = lds128(A_LUT + (hs & HS_ROW) + (o << 4));
+      const uint32_t ent = w1 < g.x ? g.z : g.y;
       hs = (hs & HS_KEEP) + HS_PA_ONE + ent;
 
       if (COUNT_PA) {
@@ -431,16 +435,17 @@ mlbsim_native_kernel(const NativeArgs args) {
   for (int i = tid; i < LUT_WORDS; i += blockDim.x) {
     const int ob = i / LUT_ROW_WORDS, w = i % LUT_ROW_WORDS;
     uint32_t v = 0;
-    if (w < 16) {
-      const int var = w >> 1, dA = w & 1;
+    if (w < 32) {
+      const int var = w >> 2, k = w & 3;
       const int o = var == MLBSIM_V_1B_ADV ? (int)MLBSIM_1B : var, dB = var == MLBSIM_V_1B_ADV;
-      const uint32_t e = transition_entry(o, dA, dB, ob >> 3, ob & 7);
-      // re-pack into the state word's fields; the next (outs*8 + bases) becomes the byte offset of its row
-      v = (e & 31u) * (uint32_t)(LUT_ROW_WORDS * 4) | (((e >> 16) & 7u) << HS_RUNS_SHIFT) | (((e >> 24) & 1u) << HS_REACHED_SHIFT) |
-          (((e >> 30) & 1u) ? HS_3OUT : 0u);
-    } else if (w < 24) {
-      const int var = w - 16;
-      v = subdraw_a_threshold(var == MLBSIM_V_1B_ADV ? (int)MLBSIM_1B : var, (ob >> 3) == 2);
+      if (k == 0) {
+        v = subdraw_a_threshold(o, (ob >> 3) == 2);
+      } else if (k < 3) {
+        const uint32_t e = transition_entry(o, k - 1, dB, ob >> 3, ob & 7);
+        // re-pack into the state word's fields; the next (outs*8 + bases) becomes the byte offset of its row
+        v = (e & 31u) * (uint32_t)(LUT_ROW_WORDS * 4) | (((e >> 16) & 7u) << HS_RUNS_SHIFT) | (((e >> 24) & 1u) << HS_REACHED_SHIFT) |
+            (((e >> 30) & 1u) ? HS_3OUT : 0u);
+      }
     }
     S.lut[i] = v;
   }
