@@ -78,12 +78,12 @@ constexpr int ALIAS_PAD_WORDS = 2 * MLBSIM_MAX_PITCHERS * MLBSIM_N_TIERS * PAD_S
 constexpr int ALIAS_PAD_SIDE_BYTES = ALIAS_PAD_WORDS / 2 * 4;                                                  // 14336
 
 struct __align__(16) Smem {
+  uint32_t lut[LUT_WORDS];   // first: its rows are addressed by absolute 14-bit shared addresses kept in the state word
 #if !OPT_PAD16
   uint32_t alias[ALIAS_WORDS];
 #endif
   uint32_t fthr[FAT_WORDS];
   int32_t fslope[FAT_WORDS];
-  uint32_t lut[LUT_WORDS];
   uint32_t joint[JOINT_WORDS];
   uint32_t innings[MLBSIM_INN_BINS];
   uint32_t rel_games[16];
@@ -162,11 +162,11 @@ constexpr uint32_t CX_PC_BITS = 0xFFFFFFFFu;
 #endif
 
 // ---- half-inning state word -------------------------------------------------------------------
-// byte offset of the LUT row of (outs*8 + bases) [12:2] | three outs [14] | lane has no game [15] |
+// shared-memory address of the LUT row of (outs*8 + bases) [13:2] | three outs [14] | lane has no game [15] |
 // runs [20:16] | reached_count [25:21] | n_pa + 2 [31:26]: the count starts at 2, so "no PA yet in this
 // half" is `hs < 3 << 26` and the 30th PA carries into bit 31 (the 30-PA cap).  Every field but the count
 // is written by adding the LUT entry: hs' = (hs & ~HS_ROW) + HS_PA_ONE + entry.
-constexpr uint32_t HS_ROW = 0x1FFCu;
+constexpr uint32_t HS_ROW = 0x3FFCu;   // absolute .shared address: the LUT sits in the first 16 KB of the window (checked at kernel start)
 constexpr uint32_t HS_3OUT = 1u << 14;
 constexpr uint32_t HS_DEAD = 1u << 15;                   // (a dead lane holds exactly this value)
 constexpr int HS_RUNS_SHIFT = 16;
@@ -232,6 +232,7 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
   const uint32_t A_FTHR = sb + (uint32_t)offsetof(Smem, fthr);
   const uint32_t A_FSLOPE = sb + (uint32_t)offsetof(Smem, fslope);
   const uint32_t A_LUT = sb + (uint32_t)offsetof(Smem, lut);
+  const uint32_t hs_new_half = HS_NEW_HALF | A_LUT;   // row of (0 outs, bases empty)
   const uint32_t A_JOINT = sb + (uint32_t)offsetof(Smem, joint);
   const uint32_t A_INN = sb + (uint32_t)offsetof(Smem, innings);
   const uint32_t A_RELG = sb + (uint32_t)offsetof(Smem, rel_games);
@@ -282,7 +283,7 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
 #else
         cur = 0; oth = 0;
 #endif
-        sc = 0; hidx = 0; hs = HS_NEW_HALF; used = 0; pa_addr = pa_mine;
+        sc = 0; hidx = 0; hs = hs_new_half; used = 0; pa_addr = pa_mine;
       }
       const uint32_t want = __popc(need);
       chunk_next += want < avail ? want : avail;
@@ -300,7 +301,8 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
 
       // The first PA of a half has empty bases, so its w1 never reaches the transition: keep it
       // as this half's end-of-inning (misc / ghost run) draw.
-      if (hs < HS_FIRST_PA_BELOW) w1_first = w1;
+      // (a half always starts at step 0 of a round: new halves come out of the boundary pass, new games out of the refill)
+      if (rep == 0 && hs < HS_FIRST_PA_BELOW) w1_first = w1;
 
       // Walker alias draw: one shared-memory word per PA
       const uint32_t col = w0 >> 29;
@@ -334,7 +336,7 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
 
       // base-running sub-draw A from w1 (full 32-bit compare against the group's threshold); sub-draw B
       // arrived inside the variant
-      const uint4 g = lds128(A_LUT + (hs & HS_ROW) + (o << 4));
+      const uint4 g = lds128((hs & HS_ROW) + (o << 4));
       const uint32_t ent = w1 < g.x ? g.z : g.y;
       hs = (hs & HS_KEEP) + HS_PA_ONE + ent;
 
@@ -354,7 +356,8 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
         // reference's `batter_idx > 0` is false.
         const uint32_t t = cur + CX_NEXT_PA;
         uint32_t fix = t >> CX_BIAS_SHIFT;   // back to the first batter
-        if ((hs & HS_OVER) != 0u || (cur & CX_TIER_MASK) == CX_TIER_MASK) fix -= CX_TIER_ONE;
+        // (slot and tier bits both zero after the step <=> the carry left a saturated tier)
+        if ((hs & HS_OVER) != 0u || (t & (CX_SLOT | CX_TIER_MASK)) == 0u) fix -= CX_TIER_ONE;
         cur = (t & CX_SLOT) == 0u ? t + fix : t;
       }
 #else
@@ -388,7 +391,7 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
         const uint32_t a_ = sc & 0xFFFFu, h_ = sc >> 16;
         const bool over = ((side != 0u) & (hidx >= 17u) & (a_ != h_)) | ((hidx == 16u) & (h_ > a_));
         if (!over) {
-          hs = HS_NEW_HALF;
+          hs = hs_new_half;
           ++hidx;
           const uint32_t t = cur; cur = oth; oth = t;
           if (COUNT_PA) pa_addr = side ? pa_mine : pa_mine + pa_side;
@@ -432,6 +435,8 @@ mlbsim_native_kernel(const NativeArgs args) {
   const bool count_pa = (args.flags & 1u) == 0;
 
   // transition LUT + sub-draw thresholds: derived once per block from the branchy semantics above
+  const uint32_t lut_base = smem_static_base() + (uint32_t)offsetof(Smem, lut);
+  if (lut_base + LUT_WORDS * 4u > HS_ROW + 4u) __trap();   // the state word keeps LUT row addresses in 14 bits
   for (int i = tid; i < LUT_WORDS; i += blockDim.x) {
     const int ob = i / LUT_ROW_WORDS, w = i % LUT_ROW_WORDS;
     uint32_t v = 0;
@@ -443,7 +448,7 @@ mlbsim_native_kernel(const NativeArgs args) {
       } else if (k < 3) {
         const uint32_t e = transition_entry(o, k - 1, dB, ob >> 3, ob & 7);
         // re-pack into the state word's fields; the next (outs*8 + bases) becomes the byte offset of its row
-        v = (e & 31u) * (uint32_t)(LUT_ROW_WORDS * 4) | (((e >> 16) & 7u) << HS_RUNS_SHIFT) | (((e >> 24) & 1u) << HS_REACHED_SHIFT) |
+        v = (lut_base + (e & 31u) * (uint32_t)(LUT_ROW_WORDS * 4)) | (((e >> 16) & 7u) << HS_RUNS_SHIFT) | (((e >> 24) & 1u) << HS_REACHED_SHIFT) |
             (((e >> 30) & 1u) ? HS_3OUT : 0u);
       }
     }
