@@ -6,7 +6,9 @@
 #include "../../include/mlbsim.h"
 #include "philox.cuh"
 
+#ifndef MLBSIM_NATIVE_MAX_THREADS
 #define MLBSIM_NATIVE_MAX_THREADS 640
+#endif
 
 struct NativeArgs {
   const mlbsim_table* tables;    // device, n_matchups entries (already offset to matchup_lo)
