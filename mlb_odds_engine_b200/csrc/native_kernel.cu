@@ -307,6 +307,16 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
       // Walker alias draw: one shared-memory word per PA
       const uint32_t col = w0 >> 29;
 #if OPT_PAD16
+#ifdef MLBSIM_DEBUG_BOUNDS   // (compute-sanitizer stand-in: scripts/debug_bounds.sh runs the GPU suite with these traps)
+      {
+        const uint32_t a = alias_base + ((cur & CX_ROW) << 5) + (col << 2);
+        const uint32_t pit = (cur >> CX_PIT_SHIFT) & 7u, nbp = (hidx & 1u) ? nb1 : nb0, Lc = (hidx & 1u) ? L1 : L0;
+        if (a < A_ALIAS || a >= A_ALIAS + (uint32_t)ALIAS_PAD_WORDS * 4u || (a & 3u)) __trap();
+        if ((cur & CX_SLOT) < 16u - Lc || pit > nbp || (cur >> CX_BIAS_SHIFT) != 16u - Lc) __trap();
+        if ((hs & HS_ROW) < A_LUT || (hs & HS_ROW) > A_LUT + 23u * LUT_ROW_WORDS * 4u || ((hs & HS_ROW) - A_LUT) % (LUT_ROW_WORDS * 4u)) __trap();
+        if (alias_base != A_ALIAS + (hidx & 1u) * (uint32_t)ALIAS_PAD_SIDE_BYTES) __trap();
+      }
+#endif
       const uint32_t e = lds32(alias_base + ((cur & CX_ROW) << 5) + (col << 2));
 #else
       side = hidx & 1u;
