@@ -13,7 +13,7 @@ def main():
     import torch.distributed as dist
 
     import oracle as orc
-    from mlb_odds_engine_b200 import synth
+    from mlb_odds_engine_b200 import _abi, synth
     from mlb_odds_engine_b200.dist import ShardedSimulator
 
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -32,6 +32,16 @@ def main():
             if tot[m].tobytes() != want.tobytes():
                 ok = False
                 print(f"matchup {m}: all-reduced histogram differs from the oracle", flush=True)
+    # sweep-shaped call: all-reduced histograms summarised on the device, every rank gets the job totals
+    summ = S.simulate_summary(n, seed, sim_lo=77)
+    for m in range(3):
+        if summ[m].tobytes() != _abi.summarize_hist(tot[m]).tobytes():
+            ok = False
+            print(f"rank {dist.get_rank()} matchup {m}: device summary differs from the reduced histogram", flush=True)
+    flag = torch.tensor([0 if ok else 1], device=f"cuda:{local}")
+    dist.all_reduce(flag)
+    ok = int(flag.item()) == 0
+    if dist.get_rank() == 0:
         print("nccl worker:", "OK" if ok else "MISMATCH", "world", dist.get_world_size(), flush=True)
     dist.barrier()
     dist.destroy_process_group()
