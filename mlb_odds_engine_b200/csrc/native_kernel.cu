@@ -465,8 +465,36 @@ mlbsim_native_kernel(const NativeArgs args) {
     S.lut[i] = v;
   }
 
-  for (uint32_t step = 0; step < args.n_matchups; ++step) {
-    const uint32_t m = (blockIdx.x + step) % args.n_matchups;
+  // Matchup schedule of a block: first the matchups it owns (blockIdx.x, + gridDim.x, ...: a 1 024-point sweep
+  // spreads over the grid without two blocks staging the same table), then whatever is still unfinished, found by
+  // a block-wide parallel look at the work counters (one load per thread, not one barrier pair per matchup).
+  uint32_t next_owned = blockIdx.x;
+  for (;;) {
+    uint32_t m;
+    if (next_owned < args.n_matchups) {
+      m = next_owned;
+      next_owned += gridDim.x;
+    } else {
+      const uint32_t start = blockIdx.x % args.n_matchups;
+      uint32_t found = 0xFFFFFFFFu;
+      for (uint32_t base = 0; base < args.n_matchups; base += blockDim.x) {
+        const uint32_t k = base + tid;
+        uint32_t c = start + k;
+        if (c >= args.n_matchups) c -= args.n_matchups;
+        const int open = k < args.n_matchups && *(volatile unsigned long long*)&args.counters[c] < (unsigned long long)n_sims;
+        if (__syncthreads_or(open)) {
+          if (tid == 0) S.go = 0xFFFFFFFFu;
+          __syncthreads();
+          if (open) atomicMin(&S.go, k);
+          __syncthreads();
+          found = start + S.go;
+          if (found >= args.n_matchups) found -= args.n_matchups;
+          break;
+        }
+      }
+      if (found == 0xFFFFFFFFu) break;   // every matchup's sims are handed out: the blocks holding them finish them
+      m = found;
+    }
     __syncthreads();  // previous matchup fully flushed; S.go free for reuse
     if (tid == 0) S.go = (*(volatile unsigned long long*)&args.counters[m] < (unsigned long long)n_sims) ? 1u : 0u;
     __syncthreads();
