@@ -195,6 +195,15 @@ int mlbsim_summarize(mlbsim_ctx* ctx, const mlbsim_hist* hist_dev, int n_matchup
 int mlbsim_run_native_summary_host(mlbsim_ctx* ctx, int matchup_lo, int matchup_hi, uint64_t sim_lo, uint64_t sim_hi,
                                    uint64_t seed, mlbsim_summary* summary_host, uint32_t flags);
 
+/* Multi-GPU exchange step: in-place ncclAllReduce(SUM, uint64) of `n_matchups` device
+ * histograms over the caller's communicator, enqueued on the context's stream right behind the kernel (no host
+ * synchronisation in between).  `nccl_comm` is an `ncclComm_t` the caller created (one rank per context / GPU);
+ * the library resolves `ncclAllReduce` from libnccl.so.2 at first use (dlopen; override the path with the
+ * environment variable MLBSIM_NCCL_LIB) and does not link NCCL.  Integer sums: totals are bit-identical for any
+ * number of ranks.  Hosts that already run torch.distributed can all-reduce the same buffer there instead
+ * (mlb_odds_engine_b200/dist.py). */
+int mlbsim_allreduce(mlbsim_ctx* ctx, void* nccl_comm, mlbsim_hist* hist_dev, int n_matchups);
+
 /* Per-sim variant of native mode for small N (the compatibility path under
  * cli/run_distribution_simulator.py:368-389, which reads result["home_score"], ["away_score"],
  * ["innings"][i]{away_runs,home_runs}, ["used_*_relievers"]): the same law, the same Philox

@@ -18,7 +18,7 @@ SYMBOLS = [
     "mlbsim_run_native", "mlbsim_run_native_host", "mlbsim_run_replay", "mlbsim_run_replay_dev",
     "mlbsim_run_persim", "mlbsim_malloc", "mlbsim_free", "mlbsim_memset", "mlbsim_memcpy_h2d", "mlbsim_memcpy_d2h",
     "mlbsim_launch_count", "mlbsim_set_launch_config", "mlbsim_last_kernel_ms",
-    "mlbsim_summarize", "mlbsim_run_native_summary_host",
+    "mlbsim_summarize", "mlbsim_run_native_summary_host", "mlbsim_allreduce",
 ]
 
 ERR_NAMES = {1: "CUDA", 2: "ARG", 3: "TABLE", 4: "NO_DEVICE", 5: "STATE"}
@@ -70,6 +70,7 @@ def load() -> ctypes.CDLL:
         "mlbsim_last_kernel_ms": (i32, [vp, ctypes.POINTER(ctypes.c_float)]),
         "mlbsim_summarize": (i32, [vp, vp, i32, vp]),
         "mlbsim_run_native_summary_host": (i32, [vp, i32, i32, u64, u64, u64, vp, u32]),
+        "mlbsim_allreduce": (i32, [vp, vp, vp, i32]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(L, name)  # AttributeError if the library lacks a declared symbol
@@ -184,6 +185,10 @@ class Context:
         assert out.dtype == _abi.SUMMARY_DTYPE and len(out) == n and out.flags.c_contiguous
         self._ck(self.L.mlbsim_run_native_summary_host(self.h, matchup_lo, matchup_hi, sim_lo, sim_hi, seed, _ptr(out), flags))
         return out
+
+    def allreduce(self, nccl_comm: int, hist_dev: int, n_matchups: int):
+        """In-place sum of device histograms over the caller's ncclComm_t, on the context's stream."""
+        self._ck(self.L.mlbsim_allreduce(self.h, ctypes.c_void_p(nccl_comm), ctypes.c_void_p(hist_dev), n_matchups))
 
     def summarize(self, hist_dev: int, n_matchups: int, summary_dev: int):
         self._ck(self.L.mlbsim_summarize(self.h, ctypes.c_void_p(hist_dev), n_matchups, ctypes.c_void_p(summary_dev)))

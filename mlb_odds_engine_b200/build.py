@@ -65,7 +65,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError(f"nvcc failed on {unit}")
         objs.append(obj)
     tmp = LIB_PATH + ".tmp"
-    r = subprocess.run([nvcc, "-shared", *ARCH, "-o", tmp, *objs], capture_output=True, text=True)
+    r = subprocess.run([nvcc, "-shared", *ARCH, "-o", tmp, *objs, "-ldl"], capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("nvcc link failed")

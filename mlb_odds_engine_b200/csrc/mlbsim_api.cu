@@ -2,6 +2,7 @@
 // No CPU fallback: every compute entry point needs a CUDA device and fails with an error code
 // (never an exception) when something is missing.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <cstdio>
 #include <cstdlib>
@@ -325,6 +326,35 @@ int mlbsim_run_native_summary_host(mlbsim_ctx* ctx, int matchup_lo, int matchup_
   if (rc != MLBSIM_OK) return rc;
   CK(ctx, cudaMemcpyAsync(summary_host, ctx->summary_scratch, sizeof(mlbsim_summary) * (size_t)n_m, cudaMemcpyDeviceToHost, ctx->stream));
   CK(ctx, cudaStreamSynchronize(ctx->stream));
+  return MLBSIM_OK;
+}
+
+// ncclAllReduce(sendbuff, recvbuff, count, datatype, op, comm, stream); ncclUint64 = 5, ncclSum = 0 (nccl.h)
+typedef int (*nccl_allreduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef const char* (*nccl_errstr_fn)(int);
+
+int mlbsim_allreduce(mlbsim_ctx* ctx, void* nccl_comm, mlbsim_hist* hist_dev, int n_matchups) {
+  if (!ctx) return MLBSIM_ERR_ARG;
+  if (!nccl_comm || !hist_dev || n_matchups <= 0) return fail(ctx, MLBSIM_ERR_ARG, "mlbsim_allreduce: bad argument");
+  static nccl_allreduce_fn allreduce = nullptr;
+  static nccl_errstr_fn errstr = nullptr;
+  if (!allreduce) {
+    const char* path = std::getenv("MLBSIM_NCCL_LIB");
+    void* h = dlopen(path && *path ? path : "libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) {
+      ctx->err = std::string("mlbsim_allreduce: cannot load NCCL (") + dlerror() + "); set MLBSIM_NCCL_LIB";
+      return MLBSIM_ERR_STATE;
+    }
+    allreduce = reinterpret_cast<nccl_allreduce_fn>(dlsym(h, "ncclAllReduce"));
+    errstr = reinterpret_cast<nccl_errstr_fn>(dlsym(h, "ncclGetErrorString"));
+    if (!allreduce) return fail(ctx, MLBSIM_ERR_STATE, "mlbsim_allreduce: ncclAllReduce not found in the NCCL library");
+  }
+  CK(ctx, cudaSetDevice(ctx->device));
+  const int rc = allreduce(hist_dev, hist_dev, (size_t)n_matchups * MLBSIM_HIST_WORDS, /*ncclUint64*/ 5, /*ncclSum*/ 0, nccl_comm, ctx->stream);
+  if (rc != 0) {
+    ctx->err = std::string("ncclAllReduce: ") + (errstr ? errstr(rc) : "error ") + " (" + std::to_string(rc) + ")";
+    return MLBSIM_ERR_CUDA;
+  }
   return MLBSIM_OK;
 }
 
