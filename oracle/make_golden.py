@@ -143,7 +143,8 @@ def main():
             continue
         make_replay(name, m, noise, n, seed=1000 + i)
     if args.stats:
-        for i, name in enumerate(["hetero_bullpen_noise", "hetero_nobullpen_noise", "neutral_calibration", "odd_onesided"]):
+        for i, name in enumerate(["hetero_bullpen_noise", "hetero_nobullpen_noise", "neutral_calibration", "odd_onesided",
+                                  "short_degenerate", "hetero_bullpen_nonoise"]):
             if args.only and args.only != name:
                 continue
             m, noise, _ = sc[name]
