@@ -139,26 +139,30 @@ class GpuSimulator:
 
 def result_dicts(games: np.ndarray, matchup: tables.Matchup | None = None) -> list[dict]:
     """Per-sim records -> the dicts `simulate_game` returns, restricted to the fields the driver
-    consumes (core/game_simulator.py:134-144; SURVEY.md Appendix B addendum)."""
-    out = []
+    consumes (core/game_simulator.py:134-144; SURVEY.md Appendix B addendum).  Columns are converted to Python
+    lists once, so 10 000 records cost tens of milliseconds."""
     names = matchup.bullpen_names if matchup is not None else None
-    for g in games:
-        k = int(g["n_innings"])
-        kk = min(k, _abi.REPLAY_MAX_INNINGS)
-        innings = [{"inning": i + 1, "away_runs": int(g["away_runs"][i]), "home_runs": int(g["home_runs"][i])}
-                   for i in range(kk)]
+    home, away = games["home_score"].tolist(), games["away_score"].tolist()
+    n_inn = np.minimum(games["n_innings"], _abi.REPLAY_MAX_INNINGS).tolist()
+    a_runs, h_runs = games["away_runs"].tolist(), games["home_runs"].tolist()
+    n_used = np.minimum(games["n_used"], _abi.REPLAY_MAX_USED).tolist()
+    used_cols = (games["used_home"].tolist(), games["used_away"].tolist())
+    recaps = games["pa"].astype(np.int64).sum(axis=1)[:, :7].tolist()
+    out = []
+    for g in range(len(games)):
+        ar, hr = a_runs[g], h_runs[g]
+        innings = [{"inning": i + 1, "away_runs": ar[i], "home_runs": hr[i]} for i in range(n_inn[g])]
         used = []
-        for s, key in ((0, "used_home"), (1, "used_away")):
-            idx = [int(x) for x in g[key][: min(int(g["n_used"][s]), _abi.REPLAY_MAX_USED)]]
+        for s in (0, 1):
+            idx = used_cols[s][g][: n_used[g][s]]
             used.append([names[s][i] for i in idx] if names is not None else idx)
-        total = int(g["home_score"]) + int(g["away_score"])
-        margin = abs(int(g["home_score"]) - int(g["away_score"]))
+        total, margin = home[g] + away[g], abs(home[g] - away[g])
         # game_type: core/game_simulator.py:123-132
         game_type = ("Pitcher's Duel" if total <= 3 else "Blowout" if margin >= 7
                      else "Tight Offensive Battle" if margin == 1 and total >= 6 else "Balanced")
-        recap = {o: int(g["pa"][0][i]) + int(g["pa"][1][i]) for i, o in enumerate(_abi.OUTCOMES)}
         out.append({
-            "home_score": int(g["home_score"]), "away_score": int(g["away_score"]), "innings": innings,
-            "used_home_relievers": used[0], "used_away_relievers": used[1], "game_type": game_type, "recap": recap,
+            "home_score": home[g], "away_score": away[g], "innings": innings,
+            "used_home_relievers": used[0], "used_away_relievers": used[1], "game_type": game_type,
+            "recap": dict(zip(_abi.OUTCOMES, recaps[g])),
         })
     return out
