@@ -352,6 +352,26 @@ def main():
     e2e_value = games / float(e2e_s.item())
     assert int(out["n_games"].sum()) == n_m * total_per_step
 
+    # ---------------- parity figures of BASELINE.json's metric (untimed): the last e2e step vs the reference ----------------
+    parity = None
+    fixture = os.path.join(ROOT, "tests", "golden", "stats_bench_texhou.npz")
+    if rank == 0 and args.workload == "single" and os.path.exists(fixture):
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from helpers import chi2_two_sample, load_stats, win_over_stats, z_two_proportions
+
+        g = load_stats("bench_texhou")
+        n_gpu = int(out["n_games"][0])
+        parity = {"vs": f"tests/golden/stats_bench_texhou.npz ({g['n']} games of the unmodified reference, same matchup)",
+                  "gpu_games": n_gpu, "ref_games": g["n"], "joint_runs_pmf_chi2": {}, "probabilities": {}}
+        for c, cap in enumerate(("f1", "f3", "f5", "f7", "full")):
+            chi2, dof, pval = chi2_two_sample(g["joint"][c], out["joint"][0][c])
+            parity["joint_runs_pmf_chi2"][cap] = {"chi2": round(chi2, 1), "dof": dof, "p": round(pval, 4)}
+        ref_ev, gpu_ev = win_over_stats(g["joint"][4]), win_over_stats(out["joint"][0][4])
+        for k in ("home_win", "home_minus_1.5", "over_7.5", "over_8.5", "over_9.5"):
+            pg, pr = gpu_ev[k] / n_gpu, ref_ev[k] / g["n"]
+            parity["probabilities"][k] = {"gpu": round(pg, 5), "ref": round(pr, 5), "delta": round(pg - pr, 5),
+                                          "z": round(float(z_two_proportions(gpu_ev[k], n_gpu, ref_ev[k], g["n"])), 2)}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -404,6 +424,7 @@ def main():
                    "threads_per_block": args.threads_per_block or 640, "table_build_ms_once": 1e3 * t_build},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(tbl.nbytes),
                 "d2h_bytes_per_step": int(n_m * e2e_out_bytes)},
+        "parity": parity,
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,

@@ -80,6 +80,8 @@ def scenarios():
     nn["home_bullpen"] = None
     nn["away_bullpen"] = None
     out["nonoise_nobullpen"] = (nn, False, 60)
+    # the matchup bench.py times (BASELINE configs[0]/[1]): lets the bench line carry its own parity figures
+    out["bench_texhou"] = (synth.make_matchup("2025-04-04-TEX@HOU"), True, 40)
     return out
 
 
@@ -144,7 +146,7 @@ def main():
         make_replay(name, m, noise, n, seed=1000 + i)
     if args.stats:
         for i, name in enumerate(["hetero_bullpen_noise", "hetero_nobullpen_noise", "neutral_calibration", "odd_onesided",
-                                  "short_degenerate", "hetero_bullpen_nonoise"]):
+                                  "short_degenerate", "hetero_bullpen_nonoise", "bench_texhou"]):
             if args.only and args.only != name:
                 continue
             m, noise, _ = sc[name]
