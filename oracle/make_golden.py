@@ -145,6 +145,7 @@ def main():
             continue
         make_replay(name, m, noise, n, seed=1000 + i)
     if args.stats:
+        # (stats_bench_texhou.npz holds 2 x 10^6 games: this batch plus an independent one with seed 991, merged by hand)
         for i, name in enumerate(["hetero_bullpen_noise", "hetero_nobullpen_noise", "neutral_calibration", "odd_onesided",
                                   "short_degenerate", "hetero_bullpen_nonoise", "bench_texhou"]):
             if args.only and args.only != name:
