@@ -66,8 +66,9 @@ def workload(args):
         from mlb_odds_engine_b200 import sweep
 
         base = synth.make_matchup("2025-04-04-TEX@HOU", bullpens=False)   # the tools/ scripts simulate without bullpens
-        ms, _ = sweep.grid_matchups(base, "home", k_rate=np.linspace(0.14, 0.34, 16), bb_rate=np.linspace(0.04, 0.12, 8),
-                                    hr_pa_projected=np.linspace(0.015, 0.06, 8))
+        axes = dict(k_rate=np.linspace(0.14, 0.34, 16), bb_rate=np.linspace(0.04, 0.12, 8), hr_pa_projected=np.linspace(0.015, 0.06, 8))
+        ms, _ = sweep.grid_matchups(base, "home", **axes)    # dicts: only the CPU-baseline legs read them
+        args._grid = (base, axes)                            # the GPU arm builds its tables with sweep.grid_tables
         sims = args.sims or 100_000
         name = f"sensitivity sweep: 1024 grid points (k_rate x bb_rate x hr_pa) x {_count(sims)} sims per GPU per step (BASELINE configs[4])"
     return ms, sims, name
@@ -267,7 +268,11 @@ def main():
     import scipy.special, scipy.stats  # noqa: F401,E401  (one-off import cost kept out of the build time below)
     tables._CLIP_CACHE.clear()
     t_build = time.perf_counter()
-    tbl = tables.build_tables(ms)
+    if getattr(args, "_grid", None):
+        from mlb_odds_engine_b200 import sweep
+        tbl = sweep.grid_tables(args._grid[0], "home", **args._grid[1])[0]
+    else:
+        tbl = tables.build_tables(ms)
     t_build = time.perf_counter() - t_build
     tbl_pinned = torch.from_numpy(tbl.view(np.uint8).reshape(-1).copy()).pin_memory()
     tbl_host = tbl_pinned.numpy().view(_abi.TABLE_DTYPE)

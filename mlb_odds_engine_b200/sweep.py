@@ -15,7 +15,7 @@ import itertools
 
 import numpy as np
 
-from . import _abi, assets
+from . import _abi, assets, tables
 from .simulator import GpuSimulator
 
 # pitcher fields that reach the simulation only through `project_hr_pa` (core/project_hr_pa.py:57-89)
@@ -49,6 +49,58 @@ def grid_matchups(base: dict, side: str = "home", project: bool = False, **axes)
     return out, points
 
 
+def grid_tables(base: dict, side: str = "home", project: bool = False, use_noise: bool = True, **axes):
+    """The device tables of `grid_matchups(base, side, project, **axes)` without materialising one dict per grid
+    point: the base matchup is parsed once, the swept pitcher's numbers are written into stacked arrays and
+    `tables.tables_from_arrays` builds every table in one pass (1 024 points: ~0.35 s instead of ~1.2 s).
+    Byte-identical to `tables.build_tables(grid_matchups(...)[0])`.  Returns (TABLE_DTYPE[n], points)."""
+    names = list(axes)
+    if project and "hr_pa_projected" in names:
+        raise ValueError("hr_pa_projected cannot be a grid axis when project=True (it is recomputed)")
+    combos = list(itertools.product(*(axes[n] for n in names)))
+    points = [dict(zip(names, (float(v) for v in c))) for c in combos]
+    G = len(combos)
+    M = tables.as_matchup(base, use_noise)
+    A = tables.stack_matchups([M])
+    A = {k: np.repeat(v, G, axis=0) for k, v in A.items()}
+    s = 0 if side == "home" else 1            # the home staff pitches to the away lineup: batting side 0
+    pit = dict(M.staffs[s][0])
+    col = {n: np.array([c[j] for c in combos], dtype=np.float64) for j, n in enumerate(names)}
+    if "k_rate" in col:
+        A["pit_k"][:, s, 0] = col["k_rate"]
+    if "bb_rate" in col:
+        A["pit_bb"][:, s, 0] = col["bb_rate"]
+    if project:
+        cols = {}
+        for f in assets._BATCH_DEFAULTS:
+            if f in col:
+                cols[f] = col[f]
+            elif f in pit:
+                cols[f] = np.full(G, assets._float_or(pit[f], float("nan")) if f in ("barrel_batted_rate", "exit_velocity_avg", "launch_angle_avg")
+                                  else pit[f], dtype=np.float64)
+        if "league_avg_hr_pa" in col or "league_avg_hr_pa" in pit:
+            cols["league_avg_hr_pa"] = col.get("league_avg_hr_pa", np.full(G, pit.get("league_avg_hr_pa", 0.0)))
+        A["pit_hr"][:, s, 0] = assets.project_hr_pa_batch(role=pit.get("role", "SP"), **cols) * M.weather_hr
+    elif "hr_pa_projected" in col:
+        A["pit_hr"][:, s, 0] = col["hr_pa_projected"] * M.weather_hr
+    contact = [f for f in ("exit_velocity_avg", "launch_angle_avg", "fielder_rating") if f in col]
+    if contact:   # the BIP hit probabilities of this pitcher change too (core/bip_resolution.py:20-57)
+        L = M.lineup_len[s]
+        cache = {}
+        for g in range(G):
+            ev = col["exit_velocity_avg"][g] if "exit_velocity_avg" in col else pit.get("exit_velocity_avg")
+            la = col["launch_angle_avg"][g] if "launch_angle_avg" in col else pit.get("launch_angle_avg")
+            fr = col["fielder_rating"][g] if "fielder_rating" in col else pit.get("fielder_rating", 50)
+            key = (ev, la, fr)
+            if key not in cache:
+                cache[key] = np.array([[tables.bip_hit_probability(t, ev, la, M.speed[s, b], fr) for t in tables.BIP_TYPES]
+                                       for b in range(L)])
+            A["hit_prob"][g, s, 0, :L] = cache[key]
+    # (axes the hot path never reads — Stuff+, ISO, HR/FB without project=True — leave every table equal to the base
+    # table, as in the reference)
+    return tables.tables_from_arrays(A), points
+
+
 def sensitivity_matchups(field: str, values, project: bool = False) -> list[dict]:
     """The matchups of `tools/test_<field>_sensitivity.py:10-66`: nine copies of the league-average batter on
     both sides, the same template pitcher (K 22.5 %, BB 8.2 %, no `hr_pa` ⇒ the 0.046 default, no EV / LA) on both
@@ -79,14 +131,17 @@ def pooled_rates(row: dict) -> dict:
     return {o: (100.0 * c / total if total else 0.0) for o, c in n.items()}
 
 
-def run_sweep(matchups: list[dict], n_sims: int = 100_000, seed: int = 0, sim: GpuSimulator | None = None,
+def run_sweep(matchups, n_sims: int = 100_000, seed: int = 0, sim: GpuSimulator | None = None,
               use_noise: bool = True) -> list[dict]:
     """Per grid point: outcome counts and rates per batting side (what the tools print from PA_RECAP_LOG,
     tools/test_stuff_plus_sensitivity.py:71-77), mean runs, run SDs and home-win probability — from the device-side
     summaries (`mlbsim_summarize`), so a 1 024-point sweep moves 320 KB over PCIe instead of 168 MB."""
     own = sim is None
     sim = sim or GpuSimulator(0)
-    sim.load_matchups(matchups, use_noise=use_noise)
+    if isinstance(matchups, np.ndarray) and matchups.dtype == _abi.TABLE_DTYPE:   # prebuilt tables (`grid_tables`)
+        sim.load_tables(matchups)
+    else:
+        sim.load_matchups(matchups, use_noise=use_noise)
     rows = [summary_row(r) for r in sim.simulate_summary(n_sims, seed=seed)]
     if own:
         sim.close()

@@ -209,24 +209,29 @@ _CLIP_CACHE: dict = {}
 
 def _expect_clip_cached(k, bb):
     """`_expect_clip` with a (k, bb) -> value memo: slates and sweeps repeat most (batter, pitcher, tier)
-    combinations (a sweep over one pitcher leaves the other 13 pitchers' rows untouched)."""
-    out = np.empty(len(k))
+    combinations (a sweep over one pitcher leaves the other 13 pitchers' rows untouched).  Distinct pairs of the
+    batch are found first, so a repeated pair is integrated once."""
+    z = np.empty(len(k), dtype=np.complex128)   # (k, bb) as one sortable scalar: both doubles are kept exactly
+    z.real, z.imag = k, bb
+    pairs, inverse = np.unique(z, return_inverse=True)
+    uk, ub = np.ascontiguousarray(pairs.real), np.ascontiguousarray(pairs.imag)
+    vals = np.empty(len(pairs))
     miss = []
-    for i, key in enumerate(zip(k.tolist(), bb.tolist())):
+    for i, key in enumerate(zip(uk.tolist(), ub.tolist())):
         v = _CLIP_CACHE.get(key)
         if v is None:
             miss.append(i)
         else:
-            out[i] = v
+            vals[i] = v
     if miss:
         mi = np.array(miss)
-        vals = _expect_clip(k[mi], bb[mi])
-        out[mi] = vals
+        new = _expect_clip(uk[mi], ub[mi])
+        vals[mi] = new
         if len(_CLIP_CACHE) > 2_000_000:
             _CLIP_CACHE.clear()
-        for i, v in zip(miss, vals.tolist()):
-            _CLIP_CACHE[(float(k[i]), float(bb[i]))] = v
-    return out
+        for i, v in zip(miss, new.tolist()):
+            _CLIP_CACHE[(float(uk[i]), float(ub[i]))] = v
+    return vals[inverse.reshape(-1)]
 
 
 _GL = None
@@ -309,7 +314,8 @@ def outcome_cdf_batch(m: Matchup, side, pit, tier, slot, pitch_count, use_noise=
     h = np.diff(np.concatenate([[0.0], cdf_hit]))
     f = np.diff(np.concatenate([[0.0], cdf_fb]))
     hr = np.clip(m.pit_hr[side, pit], 0.0, 1.0)
-    ph = m.hit_prob[side, pit, slot] @ w_bip
+    hp = m.hit_prob[side, pit, slot]
+    ph = hp[..., 0] * w_bip[0] + hp[..., 1] * w_bip[1] + hp[..., 2] * w_bip[2] + hp[..., 3] * w_bip[3]   # fixed order
     s1 = (1 - hr) * (ph * h[0] + (1 - ph) * INFIELD_FALLBACK * f[0])
     s2 = (1 - hr) * (ph * h[1] + (1 - ph) * INFIELD_FALLBACK * f[1])
     s3 = (1 - hr) * ph * h[2]
@@ -504,35 +510,91 @@ def build_table(m, use_noise=None) -> np.ndarray:
     return build_tables([m])[0]
 
 
-def build_tables(matchups, use_noise=True) -> np.ndarray:
-    """Tables for a batch of matchups (dicts take `use_noise` as the default for a missing key).  The noise integral
-    and the alias construction each run once over the rows of all matchups."""
-    ms = [m if isinstance(m, Matchup) else as_matchup(m, use_noise) for m in matchups]
-    out = np.zeros(len(ms), dtype=_abi.TABLE_DTYPE)
-    if not ms:
+def stack_matchups(ms) -> dict:
+    """Per-matchup numbers of `Matchup` objects stacked along a leading axis: the input of `tables_from_arrays`."""
+    return {
+        "lineup_len": np.array([m.lineup_len for m in ms], dtype=np.int64).reshape(len(ms), 2),
+        "bullpen_len": np.array([m.bullpen_len for m in ms], dtype=np.int64).reshape(len(ms), 2),
+        "use_noise": np.array([bool(m.use_noise) for m in ms], dtype=bool),
+        "k_mod": np.array([m.k_mod for m in ms], dtype=np.float64),
+        "bb_mod": np.array([m.bb_mod for m in ms], dtype=np.float64),
+        "bat_k": np.stack([m.bat_k for m in ms]), "bat_bb": np.stack([m.bat_bb for m in ms]),
+        "pit_k": np.stack([m.pit_k for m in ms]), "pit_bb": np.stack([m.pit_bb for m in ms]),
+        "pit_hr": np.stack([m.pit_hr for m in ms]), "hit_prob": np.stack([m.hit_prob for m in ms]),
+    }
+
+
+def _cdf_tensor(A, valid, fl):
+    """Cumulative outcome law of every valid (matchup, side, pitcher, tier, slot) row at fatigue level `fl`
+    (0 = at most 75 pitches): the arithmetic of `outcome_cdf_batch`, same operations in the same order, evaluated
+    on the gathered rows.  Returns float64 [n_valid, 6]."""
+    M, S, P, T, B = np.nonzero(valid)
+    pen = np.asarray(TTO_PENALTY)[T]
+    ak = A["pit_k"][M, S, P] * (1 - pen) * (1.0 - 0.02 * fl)
+    ab = A["pit_bb"][M, S, P] * (1 + pen) * (1.0 + 0.03 * fl)
+    k = (A["bat_k"][M, S, B] + ak) / 2 * A["k_mod"][M]
+    bb = (A["bat_bb"][M, S, B] + ab) / 2 * A["bb_mod"][M]
+    noise = A["use_noise"][M]
+    pk = np.empty(len(M))
+    pkbb = np.empty(len(M))
+    for flag in (True, False):
+        sel = noise == flag
+        if sel.any():
+            pk[sel], pkbb[sel] = _p_k_or_bb_batch(k[sel], bb[sel], flag)
+    contact = 1.0 - pkbb
+    cdf_bip, cdf_hit, cdf_fb = contact_cdfs()
+    w_bip = np.diff(np.concatenate([[0.0], cdf_bip]))
+    h = np.diff(np.concatenate([[0.0], cdf_hit]))
+    f = np.diff(np.concatenate([[0.0], cdf_fb]))
+    hr = np.clip(A["pit_hr"][M, S, P], 0.0, 1.0)
+    hp = A["hit_prob"][M, S, P, B]
+    ph = hp[..., 0] * w_bip[0] + hp[..., 1] * w_bip[1] + hp[..., 2] * w_bip[2] + hp[..., 3] * w_bip[3]   # fixed order
+    s1 = (1 - hr) * (ph * h[0] + (1 - ph) * INFIELD_FALLBACK * f[0])
+    s2 = (1 - hr) * (ph * h[1] + (1 - ph) * INFIELD_FALLBACK * f[1])
+    s3 = (1 - hr) * ph * h[2]
+    c = np.stack([pk, pkbb, pkbb + contact * s1, pkbb + contact * (s1 + s2), pkbb + contact * (s1 + s2 + s3),
+                  pkbb + contact * (s1 + s2 + s3 + hr)], axis=1)
+    return np.minimum(np.maximum.accumulate(c, axis=1), 1.0), (M, S, P, T, B)
+
+
+def tables_from_arrays(A: dict) -> np.ndarray:
+    """`mlbsim_table` records (include/mlbsim.h) for a batch of matchups given as stacked arrays (`stack_matchups`):
+    alias rows for every reachable (side, pitcher, TTO tier, lineup slot) and, for starters that are never replaced,
+    31-bit thresholds with pitch-count slopes.  One pass of the noise integral and one of the alias construction
+    over the rows of the whole batch; no per-matchup Python."""
+    n = len(A["use_noise"])
+    out = np.zeros(n, dtype=_abi.TABLE_DTYPE)
+    if n == 0:
         return out
-    if len(ms) > 1:
-        _warm_clip_cache(ms)
-    alias = np.zeros((len(ms),) + _abi.TABLE_DTYPE["alias"].shape, dtype=np.uint32)   # unused rows: always K (never reached)
-    fthr = np.full((len(ms),) + _abi.TABLE_DTYPE["fthr"].shape, 2147483648, dtype=np.uint32)
-    fslope = np.zeros((len(ms),) + _abi.TABLE_DTYPE["fslope"].shape, dtype=np.int32)
-    where, rows = [], []
-    for i, m in enumerate(ms):
-        S, P, T, B = _table_rows(m)
-        c0 = outcome_cdf_batch(m, S, P, T, B, np.zeros(len(S)))
-        rows.append(np.diff(np.concatenate([np.zeros((len(S), 1)), c0, np.ones((len(S), 1))], axis=1), axis=1))
-        where.append((np.full(len(S), i), S, P, T, B))
-        fat = _fatigue_rows(m, S, P)
-        if len(fat):
-            out["flags"][i] |= _abi.FLAG_FATIGUE
-            c1 = outcome_cdf_batch(m, S[fat], P[fat], T[fat], B[fat], np.full(len(fat), FATIGUE_START + SLOPE_SPAN))
-            q0, q1 = _quantise(c0[fat]), _quantise(c1)
-            fthr[i, S[fat], T[fat], B[fat], :6] = q0
-            fslope[i, S[fat], T[fat], B[fat], :6] = np.round((q1.astype(np.int64) - q0.astype(np.int64)) / SLOPE_SPAN)
-        out["lineup_len"][i] = m.lineup_len
-        out["bullpen_len"][i] = m.bullpen_len
-    I, S, P, T, B = (np.concatenate(x) for x in zip(*where))
-    alias[I, S, P, T, B] = alias_rows(outcome_variants(np.concatenate(rows)))
+    P_, T_, B_ = _abi.MAX_PITCHERS, _abi.N_TIERS, _abi.MAX_LINEUP
+    pit = np.arange(P_)[None, None, :, None, None]
+    slot = np.arange(B_)[None, None, None, None, :]
+    valid = (pit <= A["bullpen_len"][:, :, None, None, None]) & (slot < A["lineup_len"][:, :, None, None, None])
+    valid = np.broadcast_to(valid, (n, 2, P_, T_, B_))
+    alias = np.zeros((n,) + _abi.TABLE_DTYPE["alias"].shape, dtype=np.uint32)   # unused rows: always K (never reached)
+    fthr = np.full((n,) + _abi.TABLE_DTYPE["fthr"].shape, 2147483648, dtype=np.uint32)
+    fslope = np.zeros((n,) + _abi.TABLE_DTYPE["fslope"].shape, dtype=np.int32)
+    c0, where = _cdf_tensor(A, valid, 0.0)
+    probs = np.diff(np.concatenate([np.zeros((len(c0), 1)), c0, np.ones((len(c0), 1))], axis=1), axis=1)
+    alias[where] = alias_rows(outcome_variants(probs))
+    # a starter without a bullpen is never replaced: his pitch count passes 75 (core/fatigue_modeling.py:38)
+    fat = valid & (pit == 0) & (A["bullpen_len"][:, :, None, None, None] == 0)
+    if fat.any():
+        c1, (M, S, P, T, B) = _cdf_tensor(A, fat, max(0.0, SLOPE_SPAN / 25))
+        c0f, _ = _cdf_tensor(A, fat, 0.0)
+        q0, q1 = _quantise(c0f), _quantise(c1)
+        fthr[M, S, T, B, :6] = q0
+        fslope[M, S, T, B, :6] = np.round((q1.astype(np.int64) - q0.astype(np.int64)) / SLOPE_SPAN)
+        out["flags"][np.unique(M)] |= _abi.FLAG_FATIGUE
     out["magic"] = _abi.TABLE_MAGIC
+    out["lineup_len"], out["bullpen_len"] = A["lineup_len"], A["bullpen_len"]
     out["alias"], out["fthr"], out["fslope"] = alias, fthr, fslope
     return out
+
+
+def build_tables(matchups, use_noise=True) -> np.ndarray:
+    """Tables for a batch of matchups (dicts take `use_noise` as the default for a missing key)."""
+    ms = [m if isinstance(m, Matchup) else as_matchup(m, use_noise) for m in matchups]
+    if not ms:
+        return np.zeros(0, dtype=_abi.TABLE_DTYPE)
+    return tables_from_arrays(stack_matchups(ms))
