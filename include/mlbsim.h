@@ -173,8 +173,10 @@ int mlbsim_upload_tables(mlbsim_ctx* ctx, const mlbsim_table* tables, int n_matc
 /* Native-RNG mode: for every uploaded matchup m in [matchup_lo, matchup_hi) simulate the sims
  * [sim_lo, sim_hi) — the loop of cli/run_distribution_simulator.py:368-382 — and ADD the results
  * into hist_dev[m - matchup_lo] (device memory, caller-allocated, caller-zeroed).  Sim i of
- * matchup m draws from Philox4x32-10 with key = seed and counter (i_lo, i_hi, pa_seq, m), so its
- * outcome does not depend on the launch geometry or the number of GPUs.  Asynchronous on the
+ * matchup m draws one Philox2x32-10 block per plate appearance with counter
+ * (i[31:0], pa_number[12:0] | m << 14 | i[37:32] << 26) and a 32-bit key derived from `seed`
+ * (word 0 of Philox4x32-10 over a fixed domain-separation counter), so its outcome does not depend
+ * on the launch geometry or the number of GPUs.  Limits: m < 4096, i < 2^38.  Asynchronous on the
  * context's stream.  `flags` bit 0: 0 = also count PA outcomes (default), 1 = skip them. */
 int mlbsim_run_native(mlbsim_ctx* ctx, int matchup_lo, int matchup_hi, uint64_t sim_lo, uint64_t sim_hi,
                       uint64_t seed, mlbsim_hist* hist_dev, uint32_t flags);
