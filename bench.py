@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--threads-per-block", type=int, default=0)
     ap.add_argument("--blocks-per-sm", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-workloads", action="store_true", help="skip the extra BASELINE workloads block (tuning runs)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
 

@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define MLBSIM_ABI_VERSION 3
+#define MLBSIM_ABI_VERSION 4
 
 /* ---- model dimensions ------------------------------------------------------------------- */
 #define MLBSIM_MAX_LINEUP 9   /* len(lineup); 9 in every caller (half_inning_simulator.py:175) */
@@ -59,6 +59,7 @@ typedef struct mlbsim_params {
 #define MLBSIM_ST_INNINGS_OVERFLOW 1 /* more innings than recorded; scores still exact */
 #define MLBSIM_ST_USED_OVERFLOW 2
 #define MLBSIM_ST_TAPE_UNDERRUN 4 /* the tape ended before the game did */
+#define MLBSIM_ST_TRUNCATED 8     /* native / per-sim mode: still tied after MLBSIM_MAX_INNINGS innings */
 
 typedef struct mlbsim_replay_game {
   int32_t home_score, away_score;
@@ -105,6 +106,12 @@ typedef struct mlbsim_table {
 #define MLBSIM_HIST_BINS 64 /* runs per team, last bin = ">= 63" */
 #define MLBSIM_N_CAPS 5     /* first 1, 3, 5, 7 innings, full game (run_distribution_simulator.py:414) */
 #define MLBSIM_INN_BINS 32  /* innings played, last bin = ">= 31" */
+/* Termination guard.  The reference loops while the score is tied (core/game_simulator.py:110-111: no inning cap), so
+ * a matchup in which neither side can score never returns there.  Here a game that is still tied after
+ * MLBSIM_MAX_INNINGS innings stops, is binned like any other game and is counted in mlbsim_hist.n_truncated (the Python
+ * layer raises when that is non-zero).  128 innings x 2 halves x 30 plate appearances (half_inning_simulator.py:160)
+ * = 7 680 < 2^13, so the plate-appearance field of the Philox counter cannot carry into the matchup field. */
+#define MLBSIM_MAX_INNINGS 128
 
 typedef struct mlbsim_hist {
   uint64_t joint[MLBSIM_N_CAPS][MLBSIM_HIST_BINS][MLBSIM_HIST_BINS]; /* [cap][away][home] */
@@ -114,7 +121,8 @@ typedef struct mlbsim_hist {
                                (run_distribution_simulator.py:391-397) */
   uint64_t rel_picks[2][8]; /* total picks of reliever i */
   uint64_t n_games;
-  uint64_t reserved[7];
+  uint64_t n_truncated;     /* games stopped by the termination guard below while still tied (counted in n_games too) */
+  uint64_t reserved[6];
 } mlbsim_hist;
 
 #define MLBSIM_HIST_WORDS (sizeof(mlbsim_hist) / 8)
@@ -133,7 +141,8 @@ typedef struct mlbsim_summary {
   uint64_t home_wins;         /* full game: sims with home > away */
   uint64_t away_wins;
   uint64_t sum_innings;       /* sum over sims of innings played (bin 31 counts as 31) */
-  uint64_t reserved[7];
+  uint64_t n_truncated;       /* copy of mlbsim_hist.n_truncated */
+  uint64_t reserved[6];
 } mlbsim_summary;
 
 /* ---- error codes --------------------------------------------------------------------------- */
@@ -176,7 +185,8 @@ int mlbsim_upload_tables(mlbsim_ctx* ctx, const mlbsim_table* tables, int n_matc
  * matchup m draws one Philox2x32-10 block per plate appearance with counter
  * (i[31:0], pa_number[12:0] | m << 14 | i[37:32] << 26) and a 32-bit key derived from `seed`
  * (word 0 of Philox4x32-10 over a fixed domain-separation counter), so its outcome does not depend
- * on the launch geometry or the number of GPUs.  Limits: m < 4096, i < 2^38.  Asynchronous on the
+ * on the launch geometry or the number of GPUs.  Limits: m < 4096, i < 2^38, < 2^13 plate appearances per game
+ * (guaranteed by MLBSIM_MAX_INNINGS).  Asynchronous on the
  * context's stream.  `flags` bit 0: 0 = also count PA outcomes (default), 1 = skip them. */
 int mlbsim_run_native(mlbsim_ctx* ctx, int matchup_lo, int matchup_hi, uint64_t sim_lo, uint64_t sim_hi,
                       uint64_t seed, mlbsim_hist* hist_dev, uint32_t flags);

@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import numpy as np
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 MAX_LINEUP = 9
 MAX_BULLPEN = 6
@@ -31,6 +31,8 @@ FLAG_FATIGUE = 1
 ST_INNINGS_OVERFLOW = 1
 ST_USED_OVERFLOW = 2
 ST_TAPE_UNDERRUN = 4
+ST_TRUNCATED = 8
+MAX_INNINGS = 128
 
 PARAMS_DTYPE = np.dtype(
     [
@@ -93,7 +95,8 @@ HIST_DTYPE = np.dtype(
         ("rel_games", "<u8", (2, 8)),
         ("rel_picks", "<u8", (2, 8)),
         ("n_games", "<u8"),
-        ("reserved", "<u8", (7,)),
+        ("n_truncated", "<u8"),
+        ("reserved", "<u8", (6,)),
     ],
     align=True,
 )
@@ -110,7 +113,8 @@ SUMMARY_DTYPE = np.dtype(
         ("home_wins", "<u8"),
         ("away_wins", "<u8"),
         ("sum_innings", "<u8"),
-        ("reserved", "<u8", (7,)),
+        ("n_truncated", "<u8"),
+        ("reserved", "<u8", (6,)),
     ],
     align=True,
 )
@@ -126,6 +130,7 @@ def summarize_hist(rec: np.ndarray) -> np.ndarray:
     a = np.arange(HIST_BINS, dtype=object)[:, None]
     h = np.arange(HIST_BINS, dtype=object)[None, :]
     out["n_games"] = rec["n_games"]
+    out["n_truncated"] = rec["n_truncated"]
     out["pa"] = rec["pa"]
     for c in range(N_CAPS):
         out["sum_runs"][c, 0] = int((j[c] * a).sum())

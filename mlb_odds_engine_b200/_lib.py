@@ -9,7 +9,8 @@ import numpy as np
 
 from . import _abi
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmlbsim_b200.so")
+# MLBSIM_LIB: load a tuning variant of the same library instead (scripts/build_variants.py); never a different backend
+LIB_PATH = os.environ.get("MLBSIM_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmlbsim_b200.so")
 
 # every symbol include/mlbsim.h declares (tests/test_abi.py checks header <-> list <-> library)
 SYMBOLS = [
@@ -28,6 +29,21 @@ class MlbsimError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"mlbsim error {code} ({ERR_NAMES.get(code, '?')}): {msg}")
         self.code = code
+
+
+class GameDidNotTerminate(RuntimeError):
+    """A simulated game was still tied after MLBSIM_MAX_INNINGS innings (include/mlbsim.h): neither side can score in
+    this matchup.  The reference loops forever there (core/game_simulator.py:110-111); this build stops and reports."""
+
+
+def check_terminated(rec: np.ndarray) -> None:
+    """Raise if any histogram / summary record counts truncated games."""
+    t = np.asarray(rec["n_truncated"]).reshape(-1)
+    if t.any():
+        bad = np.nonzero(t)[0]
+        raise GameDidNotTerminate(
+            f"{int(t.sum())} simulated games were still tied after {_abi.MAX_INNINGS} innings "
+            f"(matchup index {bad[:8].tolist()}{'...' if len(bad) > 8 else ''}): a matchup in which neither side can score")
 
 
 _lib = None
@@ -176,6 +192,7 @@ class Context:
             out = np.zeros(n, dtype=_abi.HIST_DTYPE)
         assert out.dtype == _abi.HIST_DTYPE and len(out) == n and out.flags.c_contiguous
         self._ck(self.L.mlbsim_run_native_host(self.h, matchup_lo, matchup_hi, sim_lo, sim_hi, seed, _ptr(out), flags))
+        check_terminated(out)
         return out
 
     def run_native_summary_host(self, matchup_lo, matchup_hi, sim_lo, sim_hi, seed, flags=0, out=None) -> np.ndarray:
@@ -184,6 +201,7 @@ class Context:
             out = np.zeros(n, dtype=_abi.SUMMARY_DTYPE)
         assert out.dtype == _abi.SUMMARY_DTYPE and len(out) == n and out.flags.c_contiguous
         self._ck(self.L.mlbsim_run_native_summary_host(self.h, matchup_lo, matchup_hi, sim_lo, sim_hi, seed, _ptr(out), flags))
+        check_terminated(out)
         return out
 
     def allreduce(self, nccl_comm: int, hist_dev: int, n_matchups: int):

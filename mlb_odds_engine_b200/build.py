@@ -49,28 +49,32 @@ def is_stale() -> bool:
     return max(_mtime(s) for s in srcs) > _mtime(LIB_PATH)
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
-    if not force and not is_stale():
+def build_library(force: bool = False, verbose: bool = False, defs: list[str] | None = None, out: str | None = None) -> str:
+    """Default: the product library.  `defs` / `out`: a tuning variant (extra -D switches) written to another path with
+    its own object directory (scripts/build_variants.py; loaded through the MLBSIM_LIB environment variable)."""
+    lib_path = out or LIB_PATH
+    obj_dir = OBJ_DIR if out is None else os.path.join(OBJ_DIR, os.path.splitext(os.path.basename(out))[0])
+    if out is None and not force and not is_stale():
         return LIB_PATH
     nvcc = _nvcc()
-    os.makedirs(OBJ_DIR, exist_ok=True)
+    os.makedirs(obj_dir, exist_ok=True)
     objs = []
     for unit, extra in UNITS.items():
-        obj = os.path.join(OBJ_DIR, unit.replace(".cu", ".o"))
-        cmd = [nvcc, *COMMON, *extra, "-Xptxas", "-v", "-c", os.path.join(CSRC, unit), "-o", obj]
+        obj = os.path.join(obj_dir, unit.replace(".cu", ".o"))
+        cmd = [nvcc, *COMMON, *(defs or []), *extra, "-Xptxas", "-v", "-c", os.path.join(CSRC, unit), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if verbose or r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed on {unit}")
         objs.append(obj)
-    tmp = LIB_PATH + ".tmp"
+    tmp = lib_path + ".tmp"
     r = subprocess.run([nvcc, "-shared", *ARCH, "-o", tmp, *objs, "-ldl"], capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("nvcc link failed")
-    os.replace(tmp, LIB_PATH)
-    return LIB_PATH
+    os.replace(tmp, lib_path)
+    return lib_path
 
 
 if __name__ == "__main__":

@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 
@@ -22,7 +23,8 @@ struct mlbsim_ctx {
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
   cudaDeviceProp prop{};
-  mlbsim_table* tables_dev = nullptr;
+  mlbsim_table* tables_dev = nullptr;          // as uploaded (the per-sim kernel reads these)
+  mlbsim_staged_table* staged_dev = nullptr;   // shared-memory image of each table (the native kernel bulk-copies these)
   int n_tables = 0;
   int tables_cap = 0;
   unsigned long long* counters_dev = nullptr;
@@ -32,8 +34,10 @@ struct mlbsim_ctx {
   mlbsim_summary* summary_scratch = nullptr;
   int summary_scratch_cap = 0;
   mlbsim_params* params_dev = nullptr;
+  mlbsim_params params_stage{};   // context-owned pageable copy: the caller's buffer is free as soon as a replay call returns
   int threads_per_block = 0;
   int blocks_per_sm = 0;
+  int occ_threads = -1, occ_blocks = 0;   // cached occupancy query of the native kernel
   uint64_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
@@ -89,7 +93,7 @@ int mlbsim_init(int device, mlbsim_ctx** out) {
   ctx->device = device;
   auto bail = [&](const char* what, cudaError_t ce) {
     g_init_error = std::string(what) + ": " + cudaGetErrorString(ce);
-    delete ctx;
+    mlbsim_destroy(ctx);   // releases whatever was created so far
     return MLBSIM_ERR_CUDA;
   };
   if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
@@ -121,6 +125,7 @@ void mlbsim_destroy(mlbsim_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
   cudaFree(ctx->tables_dev);
+  cudaFree(ctx->staged_dev);
   cudaFree(ctx->counters_dev);
   cudaFree(ctx->hist_scratch);
   cudaFree(ctx->summary_scratch);
@@ -182,9 +187,12 @@ int mlbsim_upload_tables(mlbsim_ctx* ctx, const mlbsim_table* tables, int n_matc
   if (n_matchups > ctx->tables_cap) {
     CK(ctx, cudaStreamSynchronize(ctx->stream));
     cudaFree(ctx->tables_dev);
+    cudaFree(ctx->staged_dev);
     ctx->tables_dev = nullptr;
+    ctx->staged_dev = nullptr;
     ctx->tables_cap = ctx->n_tables = 0;
     CK(ctx, cudaMalloc(&ctx->tables_dev, sizeof(mlbsim_table) * (size_t)n_matchups));
+    CK(ctx, cudaMalloc(&ctx->staged_dev, sizeof(mlbsim_staged_table) * (size_t)n_matchups));
     ctx->tables_cap = n_matchups;
   }
   if (n_matchups > ctx->counters_cap) {
@@ -196,6 +204,9 @@ int mlbsim_upload_tables(mlbsim_ctx* ctx, const mlbsim_table* tables, int n_matc
   }
   ctx->n_tables = n_matchups;
   CK(ctx, cudaMemcpyAsync(ctx->tables_dev, tables, sizeof(mlbsim_table) * (size_t)n_matchups, cudaMemcpyHostToDevice, ctx->stream));
+  mlbsim_stage_tables_kernel<<<n_matchups, 256, 0, ctx->stream>>>(ctx->tables_dev, ctx->staged_dev, n_matchups);
+  CK(ctx, cudaGetLastError());
+  ctx->launches++;
   CK(ctx, cudaStreamSynchronize(ctx->stream));
   return MLBSIM_OK;
 }
@@ -211,13 +222,17 @@ static int launch_native(mlbsim_ctx* ctx, int matchup_lo, int matchup_hi, uint64
   const int n_m = matchup_hi - matchup_lo;
   const int threads = ctx->threads_per_block ? ctx->threads_per_block : MLBSIM_NATIVE_MAX_THREADS;
   const size_t smem = mlbsim_native_smem_bytes(threads);
-  int occ = 0;
-  CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mlbsim_native_kernel, threads, smem));
+  if (ctx->occ_threads != threads) {   // one occupancy query per block size, not one per launch
+    int occ = 0;
+    CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mlbsim_native_kernel, threads, smem));
+    ctx->occ_threads = threads;
+    ctx->occ_blocks = occ;
+  }
+  const int occ = ctx->occ_blocks;
   if (occ < 1) return fail(ctx, MLBSIM_ERR_CUDA, "native kernel does not fit on an SM");
   int bps = ctx->blocks_per_sm ? ctx->blocks_per_sm : occ;
   if (bps > occ) bps = occ;
-  const int grid = ctx->prop.multiProcessorCount * bps;
-  const uint64_t total_warps = (uint64_t)grid * (threads / 32);
+  const int full_grid = ctx->prop.multiProcessorCount * bps;
 
   ctx->timed = false;
   bool first = true;
@@ -226,8 +241,13 @@ static int launch_native(mlbsim_ctx* ctx, int matchup_lo, int matchup_hi, uint64
   uint64_t lo = sim_lo;
   do {
     const uint64_t n = (sim_hi - lo) < MAX_PER_LAUNCH ? (sim_hi - lo) : MAX_PER_LAUNCH;
+    // grid sized to the work: a small call (the reference's default is 10 000 sims) does not pay table staging, LUT
+    // construction and a 20 KB histogram flush in every one of 296 blocks for a handful of games each
+    const uint64_t work_blocks = (n * (uint64_t)n_m + (uint64_t)threads - 1) / (uint64_t)threads;
+    const int grid = (int)(work_blocks < (uint64_t)full_grid ? (work_blocks ? work_blocks : 1) : (uint64_t)full_grid);
+    const uint64_t total_warps = (uint64_t)grid * (threads / 32);
     NativeArgs a;
-    a.tables = ctx->tables_dev + matchup_lo;
+    a.tables = ctx->staged_dev + matchup_lo;
     a.hist = reinterpret_cast<unsigned long long*>(hist_dev);
     a.counters = ctx->counters_dev;
     a.sim_lo = lo;
@@ -336,19 +356,23 @@ typedef const char* (*nccl_errstr_fn)(int);
 int mlbsim_allreduce(mlbsim_ctx* ctx, void* nccl_comm, mlbsim_hist* hist_dev, int n_matchups) {
   if (!ctx) return MLBSIM_ERR_ARG;
   if (!nccl_comm || !hist_dev || n_matchups <= 0) return fail(ctx, MLBSIM_ERR_ARG, "mlbsim_allreduce: bad argument");
+  // resolved once per process, whichever context (host thread) gets here first
+  static std::once_flag once;
   static nccl_allreduce_fn allreduce = nullptr;
   static nccl_errstr_fn errstr = nullptr;
-  if (!allreduce) {
+  static std::string load_error;
+  std::call_once(once, [] {
     const char* path = std::getenv("MLBSIM_NCCL_LIB");
     void* h = dlopen(path && *path ? path : "libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
     if (!h) {
-      ctx->err = std::string("mlbsim_allreduce: cannot load NCCL (") + dlerror() + "); set MLBSIM_NCCL_LIB";
-      return MLBSIM_ERR_STATE;
+      load_error = std::string("mlbsim_allreduce: cannot load NCCL (") + dlerror() + "); set MLBSIM_NCCL_LIB";
+      return;
     }
     allreduce = reinterpret_cast<nccl_allreduce_fn>(dlsym(h, "ncclAllReduce"));
     errstr = reinterpret_cast<nccl_errstr_fn>(dlsym(h, "ncclGetErrorString"));
-    if (!allreduce) return fail(ctx, MLBSIM_ERR_STATE, "mlbsim_allreduce: ncclAllReduce not found in the NCCL library");
-  }
+    if (!allreduce) load_error = "mlbsim_allreduce: ncclAllReduce not found in the NCCL library";
+  });
+  if (!allreduce) return fail(ctx, MLBSIM_ERR_STATE, load_error.c_str());
   CK(ctx, cudaSetDevice(ctx->device));
   const int rc = allreduce(hist_dev, hist_dev, (size_t)n_matchups * MLBSIM_HIST_WORDS, /*ncclUint64*/ 5, /*ncclSum*/ 0, nccl_comm, ctx->stream);
   if (rc != 0) {
@@ -378,7 +402,11 @@ int mlbsim_run_replay_dev(mlbsim_ctx* ctx, const mlbsim_params* params_host, con
   if (n_games == 0) return MLBSIM_OK;
   if (n_games >= (1ll << 32)) return fail(ctx, MLBSIM_ERR_ARG, "more than 2^32 - 1 games per replay call");
   CK(ctx, cudaSetDevice(ctx->device));
-  CK(ctx, cudaMemcpyAsync(ctx->params_dev, params_host, sizeof(mlbsim_params), cudaMemcpyHostToDevice, ctx->stream));
+  // The caller may reuse params_host as soon as this returns, whatever kind of memory it is: copy it into the
+  // context first.  The context's copy is pageable, so cudaMemcpyAsync returns only after it has been staged for DMA
+  // and a second call cannot overwrite it under a copy still in flight.
+  std::memcpy(&ctx->params_stage, params_host, sizeof(mlbsim_params));
+  CK(ctx, cudaMemcpyAsync(ctx->params_dev, &ctx->params_stage, sizeof(mlbsim_params), cudaMemcpyHostToDevice, ctx->stream));
   ReplayArgs a{ctx->params_dev, tape_dev, tape_offsets_dev, out_dev, (long long)n_games};
   if (ctx->counters_cap < 1) {
     CK(ctx, cudaMalloc(&ctx->counters_dev, sizeof(unsigned long long)));
@@ -408,8 +436,6 @@ int mlbsim_run_replay_dev(mlbsim_ctx* ctx, const mlbsim_params* params_host, con
   CK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
   ctx->timed = true;
   ctx->launches++;
-  // params_host may be reused by the caller right away: the H2D copy above must have landed
-  // (pageable source => the copy is already staged when cudaMemcpyAsync returns)
   return MLBSIM_OK;
 }
 

@@ -32,13 +32,24 @@
 #include "native_kernel.h"
 #include "philox.cuh"
 
-// tuning switches (scripts/variant_sweep.sh rebuilds with -D... and measures on the GPU box;
-// results in profiles/r01_variants.txt)
+// tuning switches (scripts/variant_sweep.sh builds one library per set of -D switches; results under profiles/)
 #ifndef OPT_UNROLL
 #define OPT_UNROLL 4   /* plate appearances per round: one refill check and one boundary pass per round */
 #endif
-#ifndef OPT_PAD16
-#define OPT_PAD16 1    /* alias rows padded to 16 lineup slots + biased slot counter: row address = ctx bits, lineup wrap = carry */
+#ifndef OPT_PA_WARP
+#define OPT_PA_WARP 0  /* 1: PA outcome counters per warp (16 words, same-address lanes merged by ATOMS.POPC.INC) instead of per thread */
+#endif
+#ifndef OPT_GATE_LAST
+#define OPT_GATE_LAST 0  /* G > 0: skip the last PA step of a round when fewer than G lanes are still inside their half */
+#endif
+#ifndef OPT_REFILL_EVERY
+#define OPT_REFILL_EVERY 1  /* look for finished lanes every k-th round only */
+#endif
+#ifndef OPT_WRAP_ROUND
+#define OPT_WRAP_ROUND 1  /* 1: lineup wrap fixed up once per round (repeated table rows), 0: after every plate appearance */
+#endif
+#ifndef OPT_TMA
+#define OPT_TMA 1      /* 1: tables reach shared memory as cp.async.bulk copies of the pre-laid-out device image (mbarrier completion) */
 #endif
 #ifndef NATIVE_LB_THREADS
 #define NATIVE_LB_THREADS MLBSIM_NATIVE_MAX_THREADS
@@ -60,54 +71,50 @@ constexpr uint32_t T_END_GHOST = 42949673u;  // 0.01              ghost run only
 constexpr int MAX_PA_PER_HALF = 30;          // half_inning_simulator.py:160
 constexpr int PITCH_LIMIT = 90;              // game_simulator.py:8
 constexpr int FATIGUE_START = 75;            // fatigue_modeling.py:38
+constexpr uint32_t LAST_HIDX = 2u * MLBSIM_MAX_INNINGS - 1u;   // termination guard: bottom half of inning MLBSIM_MAX_INNINGS
 
 // ---- shared-memory layout ---------------------------------------------------------------------
 constexpr int SB = 32;                                    // smem joint-histogram bins per team
-constexpr int ALIAS_WORDS = 2 * MLBSIM_MAX_PITCHERS * MLBSIM_N_TIERS * MLBSIM_MAX_LINEUP * MLBSIM_ROW_WORDS;  // 4032
-constexpr int FAT_WORDS = 2 * MLBSIM_N_TIERS * MLBSIM_MAX_LINEUP * MLBSIM_ROW_WORDS;                          // 576
+constexpr int FAT_WORDS = MLBSIM_STAGED_FAT_WORDS;        // 576
 // transition LUT: one row per (outs*8 + bases), eight 16-byte groups per row, one per draw variant:
-// {sub-draw A threshold at this number of outs, entry if A fails, entry if A succeeds, 0} — one LDS.128 per PA.
+// {sub-draw A threshold at this number of outs, state delta if A fails, state delta if A succeeds, 0} — one LDS.128 per PA.
 // Row stride 36 words: consecutive rows start one 16-byte bank group apart, so lanes in different
 // (outs, bases) states that look up the same variant do not collide.
 constexpr int LUT_ROW_WORDS = 36;
 constexpr int LUT_WORDS = 32 * LUT_ROW_WORDS;                                                                  // 1152
 constexpr int JOINT_WORDS = MLBSIM_N_CAPS * SB * SB;                                                          // 5120
-
-constexpr int PAD_SLOTS = 16;
-constexpr int ALIAS_PAD_WORDS = 2 * MLBSIM_MAX_PITCHERS * MLBSIM_N_TIERS * PAD_SLOTS * MLBSIM_ROW_WORDS;          // 7168
-constexpr int ALIAS_PAD_SIDE_BYTES = ALIAS_PAD_WORDS / 2 * 4;                                                  // 14336
+constexpr int ALIAS_WORDS = MLBSIM_STAGED_ALIAS_WORDS;                                                        // 7680 (30 KB)
 
 struct __align__(16) Smem {
   uint32_t lut[LUT_WORDS];   // first: its rows are addressed by absolute 14-bit shared addresses kept in the state word
-#if !OPT_PAD16
-  uint32_t alias[ALIAS_WORDS];
-#endif
-  uint32_t fthr[FAT_WORDS];
+  uint32_t alias[ALIAS_WORDS];   // static, so that the hot loop's LDS carries its address as an immediate
+  uint32_t fthr[FAT_WORDS];  // (fthr and fslope are contiguous: one bulk copy)
   int32_t fslope[FAT_WORDS];
-  uint32_t joint[JOINT_WORDS];
   uint32_t innings[MLBSIM_INN_BINS];
   uint32_t rel_games[16];
   uint32_t rel_picks[16];
-  uint32_t n_games;
-  uint32_t hdr_flags, L0, L1, nb0, nb1;
+  uint32_t truncated;
   uint32_t go;  // block-uniform "this matchup still has work"
+  unsigned long long mbar;   // completion barrier of the table copies
 };
 constexpr int PA_FIELDS = 16;  // [side][draw variant]: the two single variants are added up at the flush
-// Dynamic shared memory: [padded alias table (OPT_PAD16)] [pa[14][PA_STRIDE]].  The counter stride is the
-// compile-time maximum block size, not blockDim.x, so that `outcome * stride` is an immediate multiply.
+// Dynamic shared memory: [five 32x32 joint histograms] [PA outcome counters].  Per-thread counters: pa[16][PA_STRIDE], the
+// stride being the compile-time maximum block size, not blockDim.x, so that `variant * stride` is an immediate multiply;
+// per-warp counters (OPT_PA_WARP): pa[warp][16].
 constexpr uint32_t PA_STRIDE = MLBSIM_NATIVE_MAX_THREADS;
-constexpr uint32_t DYN_ALIAS_BYTES = OPT_PAD16 ? (uint32_t)ALIAS_PAD_WORDS * 4u : 0u;
-constexpr uint32_t DYN_PA_WORD0 = DYN_ALIAS_BYTES / 4u;
+constexpr uint32_t ALIAS_BYTES = (uint32_t)ALIAS_WORDS * 4u;
+constexpr uint32_t DYN_JOINT_BYTES = (uint32_t)JOINT_WORDS * 4u;
+constexpr uint32_t DYN_PA_WORD0 = DYN_JOINT_BYTES / 4u;
+constexpr uint32_t DYN_PA_BYTES = OPT_PA_WARP ? (uint32_t)(MLBSIM_NATIVE_MAX_THREADS / 32) * PA_FIELDS * 4u : (uint32_t)PA_FIELDS * 4u * PA_STRIDE;
 
 }  // namespace
 
-// Statically allocated (30 KB) at global scope so that its PTX symbol keeps this plain name: the
+// Statically allocated (42 KB) at global scope so that its PTX symbol keeps this plain name: the
 // hot loop takes `mov.u32 r, mlbsim_S` (a link-time constant in the .shared space) as its base and
 // every access becomes LDS [Rindex + imm] with no generic->shared conversion in the loop.
-// Dynamic shared memory holds (OPT_PAD16) the alias table re-laid as [side][pitcher][tier][16 slots][8 words]: the low nine bits of a side's
-// context word ARE the row number, and rows sit at slot + 16 - L so that running off the end of the
-// lineup is a carry out of the slot field into the tier field; then pa[14][PA_STRIDE], the per-thread PA outcome
-// counters (column = thread: bank = lane, so their read-modify-write is conflict-free).
+// It holds the alias table laid out [side][pitcher 8][tier 4][16 slots][8 words]: ten bits of a side's context word
+// ARE the row number, and rows sit at slot + 16 - L so that running off the end of the lineup is a carry out of the
+// slot field into the tier field.  Dynamic shared memory: the joint histograms, then the PA outcome counters.
 __shared__ Smem mlbsim_S;
 extern __shared__ __align__(16) uint32_t mlbsim_S_pa[];
 
@@ -140,32 +147,67 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 }
 __device__ __forceinline__ void red_inc_shared(uint32_t addr) { asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr)); }
 
+// ---- bulk-copy engine (TMA, 1-D form) + mbarrier ------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t arrivals) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(arrivals) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t mbar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+               "r"(mbar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(mbar),
+      "r"(parity)
+      : "memory");
+}
+
 // ---- per-side context word (one per batting side; `cur` = side at bat, `oth` = the other) -------
-// slot[3:0] | tier[5:4] | pit[8:6] | pitch_count[31:9]      pitch_count is the top field, so
-// "pitch_count > n" is a plain unsigned compare of the whole word against ((n + 1) << 9).
-constexpr uint32_t CX_SLOT = 0xFu;
-constexpr uint32_t CX_TIER_ONE = 1u << 4;
-constexpr uint32_t CX_TIER_MASK = 3u << 4;
-constexpr uint32_t CX_TIER_GE2 = 2u << 4;
-constexpr int CX_T_SHIFT = 4;  // (ctx >> 4) & 31 = pit*4 + tier
-constexpr int CX_PIT_SHIFT = 6;
-constexpr int CX_PC_SHIFT = 9;
-constexpr uint32_t CX_NEXT_PA = (1u << CX_PC_SHIFT) + 1u;  // one more pitch, next batter
-#if OPT_PAD16
-// OPT_PAD16: slot field holds slot + (16 - L) ("biased"), and bias[31:28] = 16 - L rides in the top
-// nibble (pitch_count keeps 19 bits).  ctx & CX_ROW = row number in the padded alias table.
+// slot'[8:5] | tier[10:9] | pit[13:11] | side[14] | pitch_count[27:15] | bias[31:28]
+//   * ctx & CX_ROW_BYTES IS the byte offset of the alias row in the staged table of both sides (a row is 32 bytes; the
+//     side bit never changes): one LOP3, no per-lane base register;
+//   * slot' = slot + 16 - L ("biased"; L = lineup length, bias = 16 - L rides in the top nibble): stepping past the last
+//     batter carries out of the slot field into the tier field — the TTO increment of half_inning_simulator.py:177-178.
+//     The first three rows of every (pitcher, tier) group — padding, since real rows start at `bias` >= 7 — repeat the
+//     first three batters of the group the carry comes from (stage kernel below), so that a round of four plate
+//     appearances never has to look at the wrap: one fix-up per ROUND puts the slot back to `bias` (WRAP_STEP = false);
+//   * pitch_count is the top field below the bias, so "pitch_count > n" is an unsigned compare of
+//     (ctx & CX_PC_BITS) against ((n + 1) << CX_PC_SHIFT).  13 bits: MLBSIM_MAX_INNINGS keeps a game below 7 680 PAs.
+constexpr int CX_SLOT_SHIFT = 5;
+constexpr uint32_t CX_SLOT = 0xFu << CX_SLOT_SHIFT;
+constexpr uint32_t CX_TIER_ONE = 1u << 9;
+constexpr uint32_t CX_TIER_MASK = 3u << 9;
+constexpr uint32_t CX_TIER_GE2 = 2u << 9;
+constexpr int CX_T_SHIFT = 9;  // (ctx >> 9) & 31 = pit*4 + tier
+constexpr int CX_PIT_SHIFT = 11;
+constexpr int CX_SIDE_SHIFT = 14;
+constexpr uint32_t CX_SIDE = 1u << CX_SIDE_SHIFT;
+constexpr int CX_PC_SHIFT = 15;
+constexpr uint32_t CX_NEXT_PA = (1u << CX_PC_SHIFT) + (1u << CX_SLOT_SHIFT);  // one more pitch, next batter
 constexpr int CX_BIAS_SHIFT = 28;
 constexpr uint32_t CX_PC_BITS = (1u << CX_BIAS_SHIFT) - 1u;   // mask that drops the bias nibble
-constexpr uint32_t CX_ROW = 0x1FFu;
-#else
-constexpr uint32_t CX_PC_BITS = 0xFFFFFFFFu;
-#endif
+constexpr uint32_t CX_ROW_BYTES = 0x7FE0u;                    // side | pit | tier | slot', already scaled by the 32-byte row
+constexpr int WRAP_DUP_ROWS = OPT_UNROLL - 1;                 // plate appearances that can follow a wrap inside one round
+static_assert(WRAP_DUP_ROWS >= 1 && WRAP_DUP_ROWS <= 16 - MLBSIM_MAX_LINEUP, "repeated rows must fit below the smallest bias");
 
 // ---- half-inning state word -------------------------------------------------------------------
 // shared-memory address of the LUT row of (outs*8 + bases) [13:2] | three outs [14] | lane has no game [15] |
 // runs [20:16] | reached_count [25:21] | n_pa + 2 [31:26]: the count starts at 2, so "no PA yet in this
-// half" is `hs < 3 << 26` and the 30th PA carries into bit 31 (the 30-PA cap).  Every field but the count
-// is written by adding the LUT entry: hs' = (hs & ~HS_ROW) + HS_PA_ONE + entry.
+// half" is `hs < 3 << 26` and the 30th PA carries into bit 31 (the 30-PA cap).  A plate appearance is ONE ADD:
+// the LUT entry of (row, variant, sub-draw A) holds new row address - this row's address + runs + reached + three-outs
+// flag + one PA, so hs' = hs + entry.
 constexpr uint32_t HS_ROW = 0x3FFCu;   // absolute .shared address: the LUT sits in the first 16 KB of the window (checked at kernel start)
 constexpr uint32_t HS_3OUT = 1u << 14;
 constexpr uint32_t HS_DEAD = 1u << 15;                   // (a dead lane holds exactly this value)
@@ -177,7 +219,6 @@ constexpr uint32_t HS_PA_ONE = 1u << HS_PA_SHIFT;
 constexpr uint32_t HS_NEW_HALF = (32u - MAX_PA_PER_HALF) << HS_PA_SHIFT;
 constexpr uint32_t HS_FIRST_PA_BELOW = HS_NEW_HALF + HS_PA_ONE;   // hs < this  <=>  no PA played yet in this half
 constexpr uint32_t HS_OVER = (1u << 31) | HS_3OUT;      // 30 PAs, or three outs
-constexpr uint32_t HS_KEEP = ~HS_ROW;
 
 // threshold of sub-draw A: double play (K/OUT), runner on 2B scores on a single (0.46 with two
 // outs: 0.4 + 0.6*0.1), runner on 1B scores on a double
@@ -211,40 +252,63 @@ constexpr size_t H_PA = H_INN + MLBSIM_INN_BINS;
 constexpr size_t H_RELG = H_PA + 16;
 constexpr size_t H_RELP = H_RELG + 16;
 constexpr size_t H_N = H_RELP + 16;
+constexpr size_t H_TRUNC = H_N + 1;
 
 // One matchup, all the sims this warp can grab.  FATIGUE: some staff has no bullpen (pitch counts
 // pass 75); COUNT_PA: keep the PA_RECAP_LOG outcome counters.
-template <bool FATIGUE, bool COUNT_PA>
+// Lineup wrap.  The biased slot runs from 16 - L to 15; one step further the add has carried into the tier field
+// (that carry IS the TTO increment: the next PA of this half starts a new pass through the lineup) and the slot field
+// counts 0, 1, 2 ... from the first batter again.  This puts the slot back to bias + that count and takes the tier
+// increment back when the tier was already 4+ (tier bits zero after the carry: it ran on into the pitcher field, and
+// -TIER_ONE borrows it back), or when the wrap was the very last PA of the half: the next half then starts at index 0,
+// where the reference's `batter_idx > 0` is false.  Lanes that did not wrap pass through unchanged.
+__device__ __forceinline__ uint32_t wrap_fix(uint32_t cur, uint32_t hs) {
+  const uint32_t low = cur & CX_SLOT;
+  const uint32_t bias = (cur >> (CX_BIAS_SHIFT - CX_SLOT_SHIFT)) & CX_SLOT;   // bias << CX_SLOT_SHIFT
+  uint32_t fix = bias;
+  if ((cur & CX_TIER_MASK) == 0u || ((hs & HS_OVER) != 0u && low == 0u)) fix -= CX_TIER_ONE;
+  return low < bias ? cur + fix : cur;
+}
+
+// WRAP_STEP: put the lineup slot back after every plate appearance instead of once per round (needed when a lineup is
+// shorter than four batters, and on the fatigue path, whose threshold rows are addressed by the true (tier, slot)).
+template <bool FATIGUE, bool COUNT_PA, bool WRAP_STEP>
 __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned long long* const H,
                                              unsigned long long* const counter, const uint32_t rng_matchup, const uint32_t L0,
                                              const uint32_t L1, const uint32_t nb0, const uint32_t nb1) {
   const int lane = threadIdx.x & 31;
   const uint32_t n_sims = args.n_sims;
   const uint32_t sb = smem_static_base();
-#if OPT_PAD16
-  const uint32_t A_ALIAS = smem_dynamic_base();                                  // padded table: start of dynamic smem
-  const uint32_t init0 = (16u - L0) * ((1u << CX_BIAS_SHIFT) + 1u);             // bias nibble + biased slot 0
-  const uint32_t init1 = (16u - L1) * ((1u << CX_BIAS_SHIFT) + 1u);
-  uint32_t alias_base = A_ALIAS;                                                  // rows of the side at bat
-#else
   const uint32_t A_ALIAS = sb + (uint32_t)offsetof(Smem, alias);
-#endif
+  const uint32_t init0 = (16u - L0) * ((1u << CX_BIAS_SHIFT) + (1u << CX_SLOT_SHIFT));   // bias nibble + biased slot 0, side 0
+  const uint32_t init1 = (16u - L1) * ((1u << CX_BIAS_SHIFT) + (1u << CX_SLOT_SHIFT)) | CX_SIDE;
   const uint32_t A_FTHR = sb + (uint32_t)offsetof(Smem, fthr);
   const uint32_t A_FSLOPE = sb + (uint32_t)offsetof(Smem, fslope);
   const uint32_t A_LUT = sb + (uint32_t)offsetof(Smem, lut);
   const uint32_t hs_new_half = HS_NEW_HALF | A_LUT;   // row of (0 outs, bases empty)
-  const uint32_t A_JOINT = sb + (uint32_t)offsetof(Smem, joint);
+  const uint32_t A_JOINT = smem_dynamic_base();
   const uint32_t A_INN = sb + (uint32_t)offsetof(Smem, innings);
   const uint32_t A_RELG = sb + (uint32_t)offsetof(Smem, rel_games);
   const uint32_t A_RELP = sb + (uint32_t)offsetof(Smem, rel_picks);
-  // per-thread PA counters: pa[f][tid], f = side*7 + outcome
-  constexpr uint32_t pa_stride = PA_STRIDE * 4u;  // bytes between outcomes
+  const uint32_t A_TRUNC = sb + (uint32_t)offsetof(Smem, truncated);
+#if OPT_PA_WARP
+  // per-warp PA counters: pa[warp][side*8 + variant]
+  constexpr uint32_t pa_stride = 4u;    // bytes between variants
+  constexpr uint32_t pa_side = 32u;     // bytes between sides
+  const uint32_t pa_mine = smem_dynamic_base() + DYN_JOINT_BYTES + (threadIdx.x >> 5) * (PA_FIELDS * 4u);
+#else
+  // per-thread PA counters: pa[f][tid], f = side*8 + variant (column = thread: bank = lane, conflict-free)
+  constexpr uint32_t pa_stride = PA_STRIDE * 4u;  // bytes between variants
   constexpr uint32_t pa_side = 8u * pa_stride;    // bytes between sides
-  const uint32_t pa_mine = smem_dynamic_base() + DYN_ALIAS_BYTES + threadIdx.x * 4u;
+  const uint32_t pa_mine = smem_dynamic_base() + DYN_JOINT_BYTES + threadIdx.x * 4u;
+#endif
 
   // ---- warp-uniform work state ----
   uint32_t chunk_next = 0, chunk_end = 0;
   bool exhausted = false;
+#if OPT_REFILL_EVERY > 1
+  uint32_t round_no = 0;
+#endif
 
   // ---- lane state ----
   uint32_t c0 = 0, c1 = 0;   // Philox counter: c0 = sim_lo, c1 = PA number | matchup | sim_hi
@@ -258,7 +322,14 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
 
   for (;;) {
     // ---------------- refill / termination (warp-synchronous) ----------------
+#if OPT_REFILL_EVERY > 1
+    // a finished lane may sit out up to OPT_REFILL_EVERY - 1 rounds; the bookkeeping below then runs less often.
+    // A warp with no live lane at all looks every round (it would spin otherwise).
+    const bool look = (round_no++ % OPT_REFILL_EVERY) == 0u || !__any_sync(0xffffffffu, hs != HS_DEAD);
+    if (look && __any_sync(0xffffffffu, hs == HS_DEAD)) {
+#else
     if (__any_sync(0xffffffffu, hs == HS_DEAD)) {
+#endif
       const uint32_t need = __ballot_sync(0xffffffffu, hs == HS_DEAD);
       if (chunk_next >= chunk_end && !exhausted) {
         unsigned long long base = 0;
@@ -278,11 +349,7 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
         const unsigned long long sim = (unsigned long long)args.sim_lo + (chunk_next + rank);
         c0 = (uint32_t)sim;
         c1 = ((uint32_t)(sim >> 32) << RNG_SIMHI_SHIFT) | rng_matchup;
-#if OPT_PAD16
-        cur = init0; oth = init1; alias_base = A_ALIAS;
-#else
-        cur = 0; oth = 0;
-#endif
+        cur = init0; oth = init1;
         sc = 0; hidx = 0; hs = hs_new_half; used = 0; pa_addr = pa_mine;
       }
       const uint32_t want = __popc(need);
@@ -290,9 +357,12 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
       if (exhausted && !__any_sync(0xffffffffu, hs != HS_DEAD)) break;
     }
 
-    uint32_t w1 = 0, side = 0;
+    uint32_t w1 = 0;
 #pragma unroll
-    for (int rep = 0; rep < OPT_UNROLL; ++rep)
+    for (int rep = 0; rep < OPT_UNROLL; ++rep) {
+#if OPT_GATE_LAST > 0
+      if (rep == OPT_UNROLL - 1 && __popc(__ballot_sync(0xffffffffu, (hs & (HS_OVER | HS_DEAD)) == 0u)) < OPT_GATE_LAST) break;
+#endif
     if ((hs & (HS_OVER | HS_DEAD)) == 0u) {   // live lane whose half inning is still running
       // ---------------- one plate appearance ----------------
       uint32_t w0;
@@ -304,35 +374,28 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
       // (a half always starts at step 0 of a round: new halves come out of the boundary pass, new games out of the refill)
       if (rep == 0 && hs < HS_FIRST_PA_BELOW) w1_first = w1;
 
-      // Walker alias draw: one shared-memory word per PA
+      // Walker alias draw: one shared-memory word per PA.  Entry = cut29 << 3 | alias; the column is kept iff
+      // (w0 << 3) < entry — the low 29 bits of w0 against the cut, the entry's alias bits breaking the (2^-29) tie.
       const uint32_t col = w0 >> 29;
-#if OPT_PAD16
+      const uint32_t row = cur & CX_ROW_BYTES;
 #ifdef MLBSIM_DEBUG_BOUNDS   // (compute-sanitizer stand-in: scripts/debug_bounds.sh runs the GPU suite with these traps)
       {
-        const uint32_t a = alias_base + ((cur & CX_ROW) << 5) + (col << 2);
-        const uint32_t pit = (cur >> CX_PIT_SHIFT) & 7u, nbp = (hidx & 1u) ? nb1 : nb0, Lc = (hidx & 1u) ? L1 : L0;
-        if (a < A_ALIAS || a >= A_ALIAS + (uint32_t)ALIAS_PAD_WORDS * 4u || (a & 3u)) __trap();
-        if ((cur & CX_SLOT) < 16u - Lc || pit > nbp || (cur >> CX_BIAS_SHIFT) != 16u - Lc) __trap();
+        const uint32_t sd = hidx & 1u, Lc = sd ? L1 : L0, nbp = sd ? nb1 : nb0, bias = 16u - Lc;
+        const uint32_t slotp = (cur & CX_SLOT) >> CX_SLOT_SHIFT, pit = (cur >> CX_PIT_SHIFT) & 7u;
+        if (row + (col << 2) >= ALIAS_BYTES) __trap();
+        if ((cur >> CX_BIAS_SHIFT) != bias || ((cur >> CX_SIDE_SHIFT) & 1u) != sd) __trap();
+        if (WRAP_STEP ? (slotp < bias || pit > nbp) : (slotp < bias && (slotp >= (uint32_t)WRAP_DUP_ROWS || rep == 0))) __trap();
         if ((hs & HS_ROW) < A_LUT || (hs & HS_ROW) > A_LUT + 23u * LUT_ROW_WORDS * 4u || ((hs & HS_ROW) - A_LUT) % (LUT_ROW_WORDS * 4u)) __trap();
-        if (alias_base != A_ALIAS + (hidx & 1u) * (uint32_t)ALIAS_PAD_SIDE_BYTES) __trap();
+        if ((c1 & 0x1FFFu) == 0u) __trap();   // the PA field of the Philox counter wrapped
       }
 #endif
-      const uint32_t e = lds32(alias_base + ((cur & CX_ROW) << 5) + (col << 2));
-#else
-      side = hidx & 1u;
-      const uint32_t slot = cur & CX_SLOT;
-      const uint32_t T = (cur >> CX_T_SHIFT) & 31u;  // pit*4 + tier
-      const uint32_t row = (side * (MLBSIM_MAX_PITCHERS * MLBSIM_N_TIERS) + T) * MLBSIM_MAX_LINEUP + slot;
-      const uint32_t e = lds32(A_ALIAS + ((row * MLBSIM_ROW_WORDS + col) << 2));
-#endif
-      uint32_t o = ((w0 & 0x1FFFFFFFu) < (e >> 3)) ? col : (e & 7u);   // draw variant 0..7 (7 = single, runner on first advances)
+      const uint32_t e = lds32(A_ALIAS + row + (col << 2));
+      uint32_t o = ((w0 << 3) < e) ? col : (e & 7u);   // draw variant 0..7 (7 = single, runner on first advances)
       if (FATIGUE) {
-#if OPT_PAD16
-        side = hidx & 1u;
-        const uint32_t slot = (cur & CX_SLOT) - (cur >> CX_BIAS_SHIFT);
         const uint32_t T = (cur >> CX_T_SHIFT) & 31u;  // pit*4 + tier
-#endif
         if (T < 4u && (cur & CX_PC_BITS) >= ((uint32_t)(FATIGUE_START + 1) << CX_PC_SHIFT)) {  // starter past 75 pitches
+          const uint32_t side = (cur >> CX_SIDE_SHIFT) & 1u;
+          const uint32_t slot = ((cur & CX_SLOT) >> CX_SLOT_SHIFT) - (cur >> CX_BIAS_SHIFT);
           const uint32_t ex = ((cur & CX_PC_BITS) >> CX_PC_SHIFT) - FATIGUE_START;
           const uint32_t srow = (((side * MLBSIM_N_TIERS + T) * MLBSIM_MAX_LINEUP + slot) * MLBSIM_ROW_WORDS) << 2;
           const uint32_t u = w0 >> 1;
@@ -345,49 +408,24 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
       }
 
       // base-running sub-draw A from w1 (full 32-bit compare against the group's threshold); sub-draw B
-      // arrived inside the variant
+      // arrived inside the variant.  The entry is a delta of the whole state word.
       const uint4 g = lds128((hs & HS_ROW) + (o << 4));
-      const uint32_t ent = w1 < g.x ? g.z : g.y;
-      hs = (hs & HS_KEEP) + HS_PA_ONE + ent;
+      hs += w1 < g.x ? g.z : g.y;
 
-      if (COUNT_PA) {
-        const uint32_t pa = pa_addr + o * pa_stride;
-        red_inc_shared(pa);   // own column: conflict-free; measured +2 % over ld / add / st
-      }
+      if (COUNT_PA) red_inc_shared(pa_addr + o * pa_stride);
 
       // next batter, one more pitch (pitch_count counts PAs: half_inning_simulator.py:218-220)
-#if OPT_PAD16
-      {
-        // The biased slot runs from 16 - L to 15, so stepping past the last batter carries into the
-        // tier field: that carry IS the TTO increment (half_inning_simulator.py:177-178: the next PA
-        // of this half starts a new pass through the lineup).  It is taken back when the tier was
-        // already 4+ (the carry ran on into the pitcher field; -0x10 borrows it back), or when the
-        // wrap coincides with the end of the half: the next half then starts at index 0, where the
-        // reference's `batter_idx > 0` is false.
-        const uint32_t t = cur + CX_NEXT_PA;
-        uint32_t fix = t >> CX_BIAS_SHIFT;   // back to the first batter
-        // (slot and tier bits both zero after the step <=> the carry left a saturated tier)
-        if ((hs & HS_OVER) != 0u || (t & (CX_SLOT | CX_TIER_MASK)) == 0u) fix -= CX_TIER_ONE;
-        cur = (t & CX_SLOT) == 0u ? t + fix : t;
-      }
-#else
       cur += CX_NEXT_PA;
-      const uint32_t L = side ? L1 : L0;
-      const bool wrapped = (cur & CX_SLOT) == L;
-      if (wrapped) cur -= L;
-
-      if ((hs & HS_OVER) == 0u) {
-        // TTO (half_inning_simulator.py:177-178): the next PA of this half starts a new pass
-        // through the lineup.  A wrap that coincides with the end of the half does not count:
-        // the next half then starts at index 0, where the reference's `batter_idx > 0` is false.
-        if (wrapped && (cur & CX_TIER_MASK) != CX_TIER_MASK) cur += CX_TIER_ONE;
-      }
-#endif
+      if (WRAP_STEP) cur = wrap_fix(cur, hs);
     }
+    }
+    // Stepping past the last batter carried into the tier field and left the slot in the repeated rows 0..2 of the next
+    // group: put it back to `bias` once per round.
+    if (!WRAP_STEP) cur = wrap_fix(cur, hs);
     if ((hs & HS_OVER) != 0u) {   // (a dead lane has only HS_DEAD set)
       {
         // ---------------- end of half inning ----------------
-        side = hidx & 1u;
+        const uint32_t side = hidx & 1u;
         uint32_t runs = (hs >> HS_RUNS_SHIFT) & 31u;
         // misc / ghost run (half_inning_simulator.py:12-25): rare (2 %), only if a runner reached.
         // T_END_BOTH < T_END_GHOST < T_END_ANY, so one compare screens all three.
@@ -397,24 +435,22 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
         sc += runs << (side * 16u);
         // first 1/3/5/7 innings: committed when the bottom half of that inning ends (hidx = 1, 5, 9, 13)
         if ((hidx & 3u) == 1u && hidx < 16u) commit_joint(A_JOINT, H, hidx >> 2, sc & 0xFFFFu, sc >> 16);
-        // game_simulator.py:72 (bottom of the 9th skipped when the home team leads) and :110-111
+        // game_simulator.py:72 (bottom of the 9th skipped when the home team leads) and :110-111; termination guard:
+        // the bottom of inning MLBSIM_MAX_INNINGS ends the game whatever the score
         const uint32_t a_ = sc & 0xFFFFu, h_ = sc >> 16;
-        const bool over = ((side != 0u) & (hidx >= 17u) & (a_ != h_)) | ((hidx == 16u) & (h_ > a_));
+        const bool over = ((side != 0u) & (hidx >= 17u) & ((a_ != h_) | (hidx >= LAST_HIDX))) | ((hidx == 16u) & (h_ > a_));
         if (!over) {
           hs = hs_new_half;
           ++hidx;
           const uint32_t t = cur; cur = oth; oth = t;
           if (COUNT_PA) pa_addr = side ? pa_mine : pa_mine + pa_side;
-#if OPT_PAD16
-          alias_base = side ? A_ALIAS : A_ALIAS + (uint32_t)ALIAS_PAD_SIDE_BYTES;
-#endif
           // should_replace_pitcher (game_simulator.py:8-12) for the staff that now takes the mound
           const uint32_t nb = side ? nb0 : nb1;  // `side` is the half that just ended
           if (nb != 0u && ((cur & CX_TIER_GE2) != 0u || (cur & CX_PC_BITS) >= ((uint32_t)(PITCH_LIMIT + 1) << CX_PC_SHIFT))) {
             // stationary law of simulate_reliever_chain: uniform, with replacement.  The half ended on
             // an out, whose transition ignores the low half of w1 (only singles read it).
             const uint32_t idx = ((w1 & 0xFFFFu) * nb) >> 16;
-            cur = (cur & (CX_SLOT | ~CX_PC_BITS)) | ((idx + 1u) << CX_PIT_SHIFT);
+            cur = (cur & (CX_SLOT | CX_SIDE | ~CX_PC_BITS)) | ((idx + 1u) << CX_PIT_SHIFT);
             const uint32_t bit = idx + (side ? 0u : 8u);
             // "sims in which reliever i appeared" (run_distribution_simulator.py:391-397): count his first
             // appearance in this game here rather than walking the mask when the game ends
@@ -424,9 +460,10 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
           }
         } else {
           // ---------------- game over: commit ----------------
-          commit_joint(A_JOINT, H, 4u, sc & 0xFFFFu, sc >> 16);
+          commit_joint(A_JOINT, H, 4u, a_, h_);
           const uint32_t inn = (hidx >> 1) + 1u;
           red_inc_shared(A_INN + ((inn < MLBSIM_INN_BINS - 1 ? inn : MLBSIM_INN_BINS - 1) << 2));
+          if (a_ == h_) red_inc_shared(A_TRUNC);
           hs = HS_DEAD;
         }
       }
@@ -436,6 +473,48 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
 }
 
 }  // namespace
+
+// Lays one mlbsim_table out the way the native kernel's shared memory wants it (run once per upload):
+// alias rows [side][pit 8][tier][16 slots][8 words] with the row of batter s at slot' = s + 16 - L(side); the first
+// WRAP_DUP_ROWS rows of a group repeat the first batters of the group whose lineup wrap carries into it (see the context
+// word): the group's own batters when tier > 0 (the carry was a TTO increment), the batters of (pit - 1, tier 4+) when
+// tier == 0 (the carry ran out of a saturated tier into the pitcher field).  Everything else is zero.  Fatigue
+// thresholds and slopes follow, then the header words.  The native kernel stages a matchup with two bulk copies.
+extern "C" __global__ void __launch_bounds__(256)
+mlbsim_stage_tables_kernel(const mlbsim_table* __restrict__ tables, mlbsim_staged_table* __restrict__ staged, int n) {
+  const int m = blockIdx.x;
+  if (m >= n) return;
+  const mlbsim_table* T = tables + m;
+  mlbsim_staged_table* D = staged + m;
+  const uint32_t* src = &T->alias[0][0][0][0][0];
+  for (int i = threadIdx.x; i < MLBSIM_STAGED_ALIAS_WORDS; i += blockDim.x) {
+    // destination word i: row = i / 8 = ((side*8 + pit)*4 + tier)*16 + slot'
+    const uint32_t w = (uint32_t)i & 7u, row = (uint32_t)i >> 3, pslot = row & 15u, tier = (row >> 4) & 3u, pit = (row >> 6) & 7u, side = row >> 9;
+    const uint32_t L = T->lineup_len[side], bias = 16u - L;
+    uint32_t sp = pit, st = tier, sb = 0xFFFFFFFFu;   // source (pitcher, tier, batter); batter 0xFFFFFFFF = none
+    if (pslot >= bias) {
+      sb = pslot - bias;
+    } else if (pslot < (uint32_t)WRAP_DUP_ROWS && pslot < L && (pit | tier) != 0u) {
+      sb = pslot;
+      if (tier == 0u) { sp = pit - 1u; st = MLBSIM_N_TIERS - 1; }
+    }
+    uint32_t v = 0;
+    if (sb != 0xFFFFFFFFu && sp < (uint32_t)MLBSIM_MAX_PITCHERS)
+      v = src[((((side * MLBSIM_MAX_PITCHERS + sp) * MLBSIM_N_TIERS + st) * MLBSIM_MAX_LINEUP) + sb) * MLBSIM_ROW_WORDS + w];
+    D->alias[i] = v;
+  }
+  const uint32_t* fs = &T->fthr[0][0][0][0];
+  const int32_t* ss = &T->fslope[0][0][0][0];
+  for (int i = threadIdx.x; i < MLBSIM_STAGED_FAT_WORDS; i += blockDim.x) {
+    D->fthr[i] = fs[i];
+    D->fslope[i] = ss[i];
+  }
+  if (threadIdx.x == 0) {
+    D->hdr[0] = T->flags; D->hdr[1] = T->lineup_len[0]; D->hdr[2] = T->lineup_len[1];
+    D->hdr[3] = T->bullpen_len[0]; D->hdr[4] = T->bullpen_len[1];
+    D->hdr[5] = D->hdr[6] = D->hdr[7] = 0;
+  }
+}
 
 extern "C" __global__ void __launch_bounds__(NATIVE_LB_THREADS, NATIVE_LB_BLOCKS)
 mlbsim_native_kernel(const NativeArgs args) {
@@ -457,13 +536,19 @@ mlbsim_native_kernel(const NativeArgs args) {
         v = subdraw_a_threshold(o, (ob >> 3) == 2);
       } else if (k < 3) {
         const uint32_t e = transition_entry(o, k - 1, dB, ob >> 3, ob & 7);
-        // re-pack into the state word's fields; the next (outs*8 + bases) becomes the byte offset of its row
-        v = (lut_base + (e & 31u) * (uint32_t)(LUT_ROW_WORDS * 4)) | (((e >> 16) & 7u) << HS_RUNS_SHIFT) | (((e >> 24) & 1u) << HS_REACHED_SHIFT) |
-            (((e >> 30) & 1u) ? HS_3OUT : 0u);
+        // delta of the state word: (address of the next (outs*8 + bases) row - address of this row) + runs + reached
+        // + three-outs flag + one plate appearance; hs += v is the whole transition
+        v = ((e & 31u) - (uint32_t)ob) * (uint32_t)(LUT_ROW_WORDS * 4) + (((e >> 16) & 7u) << HS_RUNS_SHIFT) + (((e >> 24) & 1u) << HS_REACHED_SHIFT) +
+            (((e >> 30) & 1u) ? HS_3OUT : 0u) + HS_PA_ONE;
       }
     }
     S.lut[i] = v;
   }
+#if OPT_TMA
+  const uint32_t mbar = smem_static_base() + (uint32_t)offsetof(Smem, mbar);
+  uint32_t mbar_phase = 0;
+  if (tid == 0) mbar_init(mbar, 1);
+#endif
 
   // Matchup schedule of a block: first the matchups it owns (blockIdx.x, + gridDim.x, ...: a 1 024-point sweep
   // spreads over the grid without two blocks staging the same table), then whatever is still unfinished, found by
@@ -495,63 +580,81 @@ mlbsim_native_kernel(const NativeArgs args) {
       if (found == 0xFFFFFFFFu) break;   // every matchup's sims are handed out: the blocks holding them finish them
       m = found;
     }
-    __syncthreads();  // previous matchup fully flushed; S.go free for reuse
+    __syncthreads();  // previous matchup fully flushed (shared memory free for the next table); S.go free for reuse
     if (tid == 0) S.go = (*(volatile unsigned long long*)&args.counters[m] < (unsigned long long)n_sims) ? 1u : 0u;
     __syncthreads();
     if (!S.go) continue;
 
     // ---- stage this matchup's table; clear block-local accumulators ----
+    const mlbsim_staged_table* T = args.tables + m;
+    const uint32_t hdr_flags = __ldg(&T->hdr[0]);
+    const uint32_t L0 = __ldg(&T->hdr[1]), L1 = __ldg(&T->hdr[2]), nb0 = __ldg(&T->hdr[3]), nb1 = __ldg(&T->hdr[4]);
+    const bool fatigue = (hdr_flags & MLBSIM_FLAG_FATIGUE) != 0;
     {
-      const mlbsim_table* T = args.tables + m;
-      const uint4* src = reinterpret_cast<const uint4*>(T->alias);
-#if OPT_PAD16
-      // compact [side][pit][tier][9][8] -> padded [side][pit][tier][16][8], row of slot s at s + 16 - L(side)
-      uint4* dst = reinterpret_cast<uint4*>(S_pa);
-      const uint32_t bias0 = 16u - T->lineup_len[0], bias1 = 16u - T->lineup_len[1];
-      for (int i = tid; i < ALIAS_WORDS / 4; i += blockDim.x) {
-        const uint32_t r = (uint32_t)i >> 1, group = r / MLBSIM_MAX_LINEUP, slot = r - group * MLBSIM_MAX_LINEUP;
-        const uint32_t bias = group >= (uint32_t)(MLBSIM_MAX_PITCHERS * MLBSIM_N_TIERS) ? bias1 : bias0;
-        const uint32_t pslot = slot + bias;
-        if (pslot < (uint32_t)PAD_SLOTS) dst[((group * PAD_SLOTS + pslot) << 1) + (i & 1)] = __ldg(src + i);
+#if OPT_TMA
+      // One elected thread arms the barrier with the byte count and hands the copies to the bulk-copy engine; every
+      // thread clears accumulators meanwhile and then waits on the barrier's phase.
+      if (tid == 0) {
+        const uint32_t bytes = ALIAS_BYTES + (fatigue ? 2u * FAT_WORDS * 4u : 0u);
+        fence_proxy_async();   // the previous matchup's generic-proxy accesses to these buffers are ordered before the async writes
+        mbar_arrive_expect_tx(mbar, bytes);
+        bulk_copy_g2s(smem_static_base() + (uint32_t)offsetof(Smem, alias), T->alias, ALIAS_BYTES, mbar);
+        if (fatigue) bulk_copy_g2s(smem_static_base() + (uint32_t)offsetof(Smem, fthr), T->fthr, 2u * FAT_WORDS * 4u, mbar);
       }
 #else
+      const uint4* src = reinterpret_cast<const uint4*>(T->alias);
       uint4* dst = reinterpret_cast<uint4*>(S.alias);
       for (int i = tid; i < ALIAS_WORDS / 4; i += blockDim.x) dst[i] = __ldg(src + i);
-#endif
-      if (T->flags & MLBSIM_FLAG_FATIGUE) {
+      if (fatigue) {
         const uint4* fsrc = reinterpret_cast<const uint4*>(T->fthr);
         uint4* fdst = reinterpret_cast<uint4*>(S.fthr);
         for (int i = tid; i < 2 * FAT_WORDS / 4; i += blockDim.x) fdst[i] = __ldg(fsrc + i);  // fthr then fslope
       }
-      for (int i = tid; i < JOINT_WORDS; i += blockDim.x) S.joint[i] = 0;
+#endif
+      for (int i = tid; i < JOINT_WORDS; i += blockDim.x) S_pa[i] = 0;   // joint histograms: start of dynamic smem
       if (tid < MLBSIM_INN_BINS) S.innings[tid] = 0;
       if (tid < 16) { S.rel_games[tid] = 0; S.rel_picks[tid] = 0; }
+      if (tid == 0) S.truncated = 0;
       if (count_pa) {
+#if OPT_PA_WARP
+        if (tid < (int)(DYN_PA_BYTES / 4u)) S_pa[DYN_PA_WORD0 + tid] = 0u;
+#else
         for (int f = 0; f < PA_FIELDS; ++f) S_pa[DYN_PA_WORD0 + f * PA_STRIDE + tid] = 0u;
+#endif
       }
-      if (tid == 0) {
-        S.n_games = 0;
-        S.hdr_flags = T->flags; S.L0 = T->lineup_len[0]; S.L1 = T->lineup_len[1];
-        S.nb0 = T->bullpen_len[0]; S.nb1 = T->bullpen_len[1];
-      }
+#if OPT_TMA
+      mbar_wait(mbar, mbar_phase);
+      mbar_phase ^= 1u;
+#endif
     }
     __syncthreads();
 
-    const bool fatigue = (S.hdr_flags & MLBSIM_FLAG_FATIGUE) != 0;
-    const uint32_t L0 = S.L0, L1 = S.L1, nb0 = S.nb0, nb1 = S.nb1;
     const uint32_t rng_matchup = (args.matchup_base + m) << RNG_MATCHUP_SHIFT;
     unsigned long long* const H = args.hist + (size_t)m * MLBSIM_HIST_WORDS;
     unsigned long long* const counter = args.counters + m;
 
+    const bool short_lineup = !OPT_WRAP_ROUND || (L0 < L1 ? L0 : L1) <= (uint32_t)WRAP_DUP_ROWS;   // more than one wrap per round possible
     if (fatigue) {
-      if (count_pa) play_matchup<true, true>(args, H, counter, rng_matchup, L0, L1, nb0, nb1);
-      else play_matchup<true, false>(args, H, counter, rng_matchup, L0, L1, nb0, nb1);
+      if (count_pa) play_matchup<true, true, true>(args, H, counter, rng_matchup, L0, L1, nb0, nb1);
+      else play_matchup<true, false, true>(args, H, counter, rng_matchup, L0, L1, nb0, nb1);
+    } else if (short_lineup) {
+      if (count_pa) play_matchup<false, true, true>(args, H, counter, rng_matchup, L0, L1, nb0, nb1);
+      else play_matchup<false, false, true>(args, H, counter, rng_matchup, L0, L1, nb0, nb1);
     } else {
-      if (count_pa) play_matchup<false, true>(args, H, counter, rng_matchup, L0, L1, nb0, nb1);
-      else play_matchup<false, false>(args, H, counter, rng_matchup, L0, L1, nb0, nb1);
+      if (count_pa) play_matchup<false, true, false>(args, H, counter, rng_matchup, L0, L1, nb0, nb1);
+      else play_matchup<false, false, false>(args, H, counter, rng_matchup, L0, L1, nb0, nb1);
     }
 
-    // ---- block flush: shared u32 bins / per-thread counters -> device u64 totals ----
+    // ---- block flush: shared u32 bins / PA counters -> device u64 totals ----
+#if OPT_PA_WARP
+    __syncthreads();
+    if (count_pa && tid < PA_FIELDS) {
+      uint32_t v = 0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += S_pa[DYN_PA_WORD0 + w * PA_FIELDS + tid];
+      const int var = tid & 7;
+      if (v) atomicAdd(&H[H_PA + (tid >> 3) * 8 + (var == MLBSIM_V_1B_ADV ? (int)MLBSIM_1B : var)], (unsigned long long)v);
+    }
+#else
     if (count_pa) {
       for (int f = 0; f < PA_FIELDS; ++f) {
         const uint32_t v = __reduce_add_sync(0xffffffffu, S_pa[DYN_PA_WORD0 + f * PA_STRIDE + tid]);
@@ -560,8 +663,9 @@ mlbsim_native_kernel(const NativeArgs args) {
       }
     }
     __syncthreads();
+#endif
     for (int i = tid; i < JOINT_WORDS; i += blockDim.x) {
-      const uint32_t v = S.joint[i];
+      const uint32_t v = S_pa[i];
       if (v) {
         const int c = i / (SB * SB), a = (i / SB) % SB, h = i % SB;
         atomicAdd(&H[((size_t)c * MLBSIM_HIST_BINS + a) * MLBSIM_HIST_BINS + h], (unsigned long long)v);
@@ -572,6 +676,7 @@ mlbsim_native_kernel(const NativeArgs args) {
       if (v) atomicAdd(&H[H_INN + tid], (unsigned long long)v);
       const uint32_t games = __reduce_add_sync(0xffffffffu, v);   // every finished game sits in exactly one innings bin
       if (tid == 0 && games) atomicAdd(&H[H_N], (unsigned long long)games);
+      if (tid == 0 && S.truncated) atomicAdd(&H[H_TRUNC], (unsigned long long)S.truncated);
     }
     if (tid < 16) {
       if (S.rel_games[tid]) atomicAdd(&H[H_RELG + tid], (unsigned long long)S.rel_games[tid]);
@@ -639,7 +744,7 @@ mlbsim_persim_kernel(const PersimArgs args) {
           } else {
             const uint32_t col = w0 >> 29;
             const uint32_t e = T->alias[side][pit[side]][tier][sl][col];
-            o = ((w0 & 0x1FFFFFFFu) < (e >> 3)) ? (int)col : (int)(e & 7u);
+            o = ((w0 << 3) < e) ? (int)col : (int)(e & 7u);
             dB = o == MLBSIM_V_1B_ADV;
             if (dB) o = MLBSIM_1B;
           }
@@ -664,6 +769,7 @@ mlbsim_persim_kernel(const PersimArgs args) {
         R.status |= MLBSIM_ST_INNINGS_OVERFLOW;
       }
       if (inning >= 9 && score[0] != score[1]) break;
+      if (inning >= MLBSIM_MAX_INNINGS) { R.status |= MLBSIM_ST_TRUNCATED; break; }   // termination guard
       inning += 1;
     }
     R.home_score = score[1]; R.away_score = score[0]; R.n_innings = inning;
@@ -677,5 +783,5 @@ mlbsim_persim_kernel(const PersimArgs args) {
 }
 
 size_t mlbsim_native_smem_bytes(int /*threads_per_block*/) {   // dynamic part only; independent of the block size
-  return (size_t)DYN_ALIAS_BYTES + (size_t)PA_FIELDS * 4u * PA_STRIDE;
+  return (size_t)DYN_JOINT_BYTES + (size_t)DYN_PA_BYTES;
 }

@@ -10,8 +10,19 @@
 #define MLBSIM_NATIVE_MAX_THREADS 640
 #endif
 
+// Device-only image of one matchup, laid out exactly as the native kernel's shared memory wants it (built once per
+// upload by mlbsim_stage_tables_kernel): the kernel stages a matchup with cp.async.bulk copies, no address arithmetic.
+#define MLBSIM_STAGED_ALIAS_WORDS (2 * 8 * MLBSIM_N_TIERS * 16 * MLBSIM_ROW_WORDS) /* [side][pit 8][tier][16 slots][8]: 32 KB */
+#define MLBSIM_STAGED_FAT_WORDS (2 * MLBSIM_N_TIERS * MLBSIM_MAX_LINEUP * MLBSIM_ROW_WORDS)
+struct alignas(16) mlbsim_staged_table {
+  uint32_t alias[MLBSIM_STAGED_ALIAS_WORDS];
+  uint32_t fthr[MLBSIM_STAGED_FAT_WORDS];   // fthr and fslope stay contiguous: one copy
+  int32_t fslope[MLBSIM_STAGED_FAT_WORDS];
+  uint32_t hdr[8];                          // flags, lineup_len[2], bullpen_len[2], 0, 0, 0
+};
+
 struct NativeArgs {
-  const mlbsim_table* tables;    // device, n_matchups entries (already offset to matchup_lo)
+  const mlbsim_staged_table* tables;  // device, n_matchups entries (already offset to matchup_lo)
   unsigned long long* hist;      // device, n_matchups * MLBSIM_HIST_WORDS uint64 counters
   unsigned long long* counters;  // device, n_matchups work counters, zero at launch
   uint64_t sim_lo;               // first sim index of this launch
@@ -43,6 +54,7 @@ struct PersimArgs {
 #ifdef __CUDACC__
 extern "C" __global__ void mlbsim_persim_kernel(const PersimArgs args);
 extern "C" __global__ void mlbsim_native_kernel(const NativeArgs args);
+extern "C" __global__ void mlbsim_stage_tables_kernel(const mlbsim_table* tables, mlbsim_staged_table* staged, int n);
 extern "C" __global__ void mlbsim_replay_kernel(const ReplayArgs args);
 extern "C" __global__ void mlbsim_replay_flat_kernel(const ReplayArgs args, unsigned long long* counter, uint32_t chunk);
 extern "C" __global__ void mlbsim_summary_kernel(const mlbsim_hist* hist, mlbsim_summary* out);

@@ -75,5 +75,6 @@ mlbsim_summary_kernel(const mlbsim_hist* __restrict__ hist, mlbsim_summary* __re
   }
   if (threadIdx.x >= 32 && threadIdx.x < 48) S->pa[(threadIdx.x - 32) >> 3][(threadIdx.x - 32) & 7] = H->pa[(threadIdx.x - 32) >> 3][(threadIdx.x - 32) & 7];
   if (threadIdx.x == 48) S->n_games = H->n_games;
-  if (threadIdx.x >= 64 && threadIdx.x < 71) S->reserved[threadIdx.x - 64] = 0;
+  if (threadIdx.x == 49) S->n_truncated = H->n_truncated;
+  if (threadIdx.x >= 64 && threadIdx.x < 70) S->reserved[threadIdx.x - 64] = 0;
 }

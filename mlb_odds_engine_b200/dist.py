@@ -12,6 +12,7 @@ from __future__ import annotations
 import numpy as np
 
 from . import _abi
+from ._lib import check_terminated
 
 
 def shard_range(sim_lo: int, n_sims: int, rank: int, world: int) -> tuple[int, int]:
@@ -105,7 +106,9 @@ class ShardedSimulator:
         self.run_device(n_sims_total, seed, sim_lo, count_pa)
         self.hist_pinned.copy_(self.hist_dev, non_blocking=True)
         self.torch.cuda.current_stream().synchronize()
-        return self.hist_pinned.numpy().view(np.uint64).view(_abi.HIST_DTYPE).copy()
+        out = self.hist_pinned.numpy().view(np.uint64).view(_abi.HIST_DTYPE).copy()
+        check_terminated(out)
+        return out
 
     def simulate_summary(self, n_sims_total: int, seed: int, sim_lo: int = 0, tables_host=None, count_pa: bool = True) -> np.ndarray:
         """Sweep-shaped end-to-end call: as `simulate`, but the all-reduced histograms are reduced on the device
@@ -116,4 +119,6 @@ class ShardedSimulator:
         self.ctx.summarize(self.hist_dev.data_ptr(), self.n_matchups, self.summary_dev.data_ptr())
         self.summary_pinned.copy_(self.summary_dev, non_blocking=True)
         self.torch.cuda.current_stream().synchronize()
-        return self.summary_pinned.numpy().view(np.uint64).view(_abi.SUMMARY_DTYPE).copy()
+        out = self.summary_pinned.numpy().view(np.uint64).view(_abi.SUMMARY_DTYPE).copy()
+        check_terminated(out)
+        return out

@@ -557,7 +557,12 @@ def _cdf_tensor(A, valid, fl):
     return np.minimum(np.maximum.accumulate(c, axis=1), 1.0), (M, S, P, T, B)
 
 
-def tables_from_arrays(A: dict) -> np.ndarray:
+class MatchupCannotScore(ValueError):
+    """Every reachable plate appearance of BOTH sides is a strikeout or an out: the game can never leave 0-0.  The
+    reference loops forever on such input (core/game_simulator.py:110-111); tables are refused instead."""
+
+
+def tables_from_arrays(A: dict, validate: bool = True) -> np.ndarray:
     """`mlbsim_table` records (include/mlbsim.h) for a batch of matchups given as stacked arrays (`stack_matchups`):
     alias rows for every reachable (side, pitcher, TTO tier, lineup slot) and, for starters that are never replaced,
     31-bit thresholds with pitch-count slopes.  One pass of the noise integral and one of the alias construction
@@ -576,6 +581,13 @@ def tables_from_arrays(A: dict) -> np.ndarray:
     fslope = np.zeros((n,) + _abi.TABLE_DTYPE["fslope"].shape, dtype=np.int32)
     c0, where = _cdf_tensor(A, valid, 0.0)
     probs = np.diff(np.concatenate([np.zeros((len(c0), 1)), c0, np.ones((len(c0), 1))], axis=1), axis=1)
+    if validate:
+        # a matchup terminates with probability 1 iff somebody can reach base (K = column 0, OUT = column 6)
+        can_reach = np.zeros(n, dtype=bool)
+        np.logical_or.at(can_reach, where[0], (probs[:, 0] + probs[:, 6]) < 1.0)
+        if not can_reach.all():
+            raise MatchupCannotScore(f"matchup(s) {np.nonzero(~can_reach)[0][:8].tolist()}: no plate appearance of either side "
+                                     "can put a runner on base, the game would never end")
     alias[where] = alias_rows(outcome_variants(probs))
     # a starter without a bullpen is never replaced: his pitch count passes 75 (core/fatigue_modeling.py:38)
     fat = valid & (pit == 0) & (A["bullpen_len"][:, :, None, None, None] == 0)
@@ -592,9 +604,10 @@ def tables_from_arrays(A: dict) -> np.ndarray:
     return out
 
 
-def build_tables(matchups, use_noise=True) -> np.ndarray:
-    """Tables for a batch of matchups (dicts take `use_noise` as the default for a missing key)."""
+def build_tables(matchups, use_noise=True, validate: bool = True) -> np.ndarray:
+    """Tables for a batch of matchups (dicts take `use_noise` as the default for a missing key).  `validate=False`
+    skips the can-anybody-score check (tests of the kernel's own termination guard)."""
     ms = [m if isinstance(m, Matchup) else as_matchup(m, use_noise) for m in matchups]
     if not ms:
         return np.zeros(0, dtype=_abi.TABLE_DTYPE)
-    return tables_from_arrays(stack_matchups(ms))
+    return tables_from_arrays(stack_matchups(ms), validate=validate)

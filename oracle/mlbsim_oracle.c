@@ -550,7 +550,7 @@ static void native_game(const mlbsim_table* T, uint32_t matchup, uint32_t key, u
              by the 0.8 draw (variant 7 = single on which the runner on first advances) */
           uint32_t col = w[0] >> 29;
           uint32_t e = T->alias[side][st[side].pit][tier][sl][col];
-          o = ((w[0] & 0x1FFFFFFFu) < (e >> 3)) ? (int)col : (int)(e & 7u);
+          o = ((uint32_t)(w[0] << 3) < e) ? (int)col : (int)(e & 7u); /* entry = cut29 << 3 | alias: the alias bits break the 2^-29 tie */
           dB = (o == MLBSIM_V_1B_ADV);
           if (dB) o = MLBSIM_1B;
         }
@@ -578,6 +578,11 @@ static void native_game(const mlbsim_table* T, uint32_t matchup, uint32_t key, u
     }
     if (inning <= 7 && (inning & 1)) { cap_a[inning >> 1] = score[0]; cap_h[inning >> 1] = score[1]; }
     if (inning >= 9 && score[0] != score[1]) break;
+    if (inning >= MLBSIM_MAX_INNINGS) { /* termination guard (include/mlbsim.h): still tied, stop and count */
+      if (local) local->n_truncated++;
+      if (rg) rg->status |= MLBSIM_ST_TRUNCATED;
+      break;
+    }
     inning += 1;
   }
   if (local) {

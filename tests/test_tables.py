@@ -182,3 +182,24 @@ def test_summary_host_statement_on_oracle_histogram():
     row = sweep.summary_row(s)
     assert abs(row["home_runs_sd"] - h.std()) < 1e-9 and abs(row["innings_mean"] - games["n_innings"].mean()) < 1e-12
     assert abs(sum(row["rates"]["HOME"].values()) - 1.0) < 1e-12
+
+
+def test_matchup_that_cannot_score_is_refused():
+    """Every row of both sides a certain out => the game can never end (core/game_simulator.py:110-111 loops while
+    tied); the builder raises instead of handing the kernel a game that only its inning guard would stop."""
+    from mlb_odds_engine_b200 import synth
+
+    m = synth.make_matchup("2025-04-04-TEX@HOU")
+    for side in ("home", "away"):
+        for b in m[f"{side}_lineup"]:
+            b["k_rate"], b["bb_rate"] = 1.0, 0.0
+        for p in [m[f"{side}_pitcher"]] + list(m[f"{side}_bullpen"]):
+            p["k_rate"], p["bb_rate"] = 1.0, 0.0
+    m["env"] = dict(m["env"], umpire={"k_mod": 1.2, "bb_mod": 1.0})
+    with pytest.raises(tables.MatchupCannotScore):
+        tables.build_tables([m], use_noise=False)
+    assert len(tables.build_tables([m], use_noise=False, validate=False)) == 1
+    # one side able to reach base is enough for the game to end
+    for b in m["home_lineup"]:
+        b["k_rate"] = 0.2
+    assert len(tables.build_tables([m], use_noise=False)) == 1
