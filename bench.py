@@ -8,6 +8,12 @@ every matchup of the workload PER GPU (weak scaling: rank r simulates its own sl
 range; histograms are combined with one NCCL all-reduce).  Default workload = BASELINE.json
 configs[1]: the single game 2025-04-04-TEX@HOU on synthetic Batters/Pitchers.csv-schema players,
 joint runs PMF at caps 1/3/5/7/full + PA outcome counters + reliever usage.  Prints ONE JSON line.
+
+Behind the headline the same line carries a `workloads` block (skipped with --no-workloads): BASELINE configs[1-4] as
+FIXED-SIZE jobs split over the N ranks (strong scaling: single game 10M, 15-game slate x 1M, fatigue game 100M by sim
+index; the 1 024-point sweep x 100k by grid-point block), each with games/s, ms per step and the sha256 of a small
+fixed-(seed, sims) result — the digest is the same for every N (results are keyed by (seed, matchup, sim)) and is
+pinned against the CPU oracle twin in tests/golden/bench_digests.json.
 """
 from __future__ import annotations
 
@@ -24,6 +30,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 for p in (ROOT, os.path.join(ROOT, "oracle")):
     if p not in sys.path:
         sys.path.insert(0, p)
+
+import bench_workloads as bw  # noqa: E402
 
 METRIC = "simulated_games_per_sec"
 UNIT = "games/s"
@@ -48,35 +56,21 @@ def parse():
 
 
 def workload(args):
-    from mlb_odds_engine_b200 import synth
-
+    ms = bw.matchups(args.workload)
     if args.workload == "single":
-        ms = [synth.make_matchup("2025-04-04-TEX@HOU")]
         sims = args.sims or 10_000_000
-        name = f"single game 2025-04-04-TEX@HOU x {_count(sims)} sims per GPU per step (BASELINE configs[{0 if sims <= 10_000 else 1}])"
+        name = f"single game {bw.GAME_ID} x {bw.count(sims)} sims per GPU per step (BASELINE configs[{0 if sims <= 10_000 else 1}])"
     elif args.workload == "fatigue":
-        ms = [synth.make_matchup("2025-04-04-TEX@HOU", bullpens=False)]   # starters go the distance: TTO 4+, pitch-count ramp
         sims = args.sims or 10_000_000
-        name = f"fatigue-heavy: single game without bullpens x {_count(sims)} sims per GPU per step (BASELINE configs[3] shape)"
+        name = f"fatigue-heavy: single game without bullpens x {bw.count(sims)} sims per GPU per step (BASELINE configs[3] shape)"
     elif args.workload == "slate":
-        ms = synth.make_slate("2025-04-04", 15)
         sims = args.sims or 1_000_000
-        name = f"15-game slate x {_count(sims)} sims per game per GPU per step (BASELINE configs[2])"
+        name = f"15-game slate x {bw.count(sims)} sims per game per GPU per step (BASELINE configs[2])"
     else:
-        import numpy as np
-        from mlb_odds_engine_b200 import sweep
-
-        base = synth.make_matchup("2025-04-04-TEX@HOU", bullpens=False)   # the tools/ scripts simulate without bullpens
-        axes = dict(k_rate=np.linspace(0.14, 0.34, 16), bb_rate=np.linspace(0.04, 0.12, 8), hr_pa_projected=np.linspace(0.015, 0.06, 8))
-        ms, _ = sweep.grid_matchups(base, "home", **axes)    # dicts: only the CPU-baseline legs read them
-        args._grid = (base, axes)                            # the GPU arm builds its tables with sweep.grid_tables
+        args._grid = bw.sweep_grid()                         # the GPU arm builds its tables with sweep.grid_tables
         sims = args.sims or 100_000
-        name = f"sensitivity sweep: 1024 grid points (k_rate x bb_rate x hr_pa) x {_count(sims)} sims per GPU per step (BASELINE configs[4])"
+        name = f"sensitivity sweep: 1024 grid points (k_rate x bb_rate x hr_pa) x {bw.count(sims)} sims per GPU per step (BASELINE configs[4])"
     return ms, sims, name
-
-
-def _count(n: int) -> str:
-    return f"{n // 1_000_000}M" if n % 1_000_000 == 0 and n else f"{n // 1000}k" if n % 1000 == 0 and n else str(n)
 
 
 class ClockSampler:
@@ -196,49 +190,177 @@ def cpu_port_throughput(matchups, seconds, use_noise=True):
     return done / el, cores, done, el
 
 
+def cpu_reference_throughput(matchups, seconds, procs=None):
+    """The UNMODIFIED reference `simulate_game` (core/game_simulator.py:14-156: the loop body of
+    cli/run_distribution_simulator.py:368-382) on every host core for ~`seconds`: from /root/reference in the build
+    container, from the byte code oracle/make_ref.py compiled into oracle/_ref/ on the GPU box.  None if neither exists."""
+    import ref_harness as rh
+
+    if not rh.reference_available():
+        return None
+    games, busy, procs, _, wall = rh.timed_batch(matchups, seconds, seed=1, procs=procs)
+    return {"value": games / busy, "unit": UNIT, "cores": procs, "kind": "reference",
+            "sample": f"{games} games of the same workload in {busy:.1f} s: the reference's own simulate_game "
+                      f"(core/game_simulator.py, {rh.reference_kind()} of the unmodified checkout) in {procs} processes, "
+                      f"reliever usage counts pre-saturated; {games / busy / procs:.0f} games/s/core"}
+
+
 def run_reference(args):
-    """--impl reference: the reference's CPU algorithm for this path (oracle port: the reference is
-    Python and /root/reference does not exist on the GPU box) on all host threads."""
+    """--impl reference: the reference's own CPU implementation of the path on all host cores — the real Python
+    `simulate_game` when it is available (oracle/_ref byte code on the GPU box), else the C port of its algorithm.
+    Each step is a bounded sample of the workload (a fixed number of games per worker process)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    import multiprocessing as mp
+
     import oracle as orc
+    import ref_harness as rh
     from mlb_odds_engine_b200 import tables
 
     ms, sims, name = workload(args)
-    cores = orc.get_threads()
-    params = [tables.build_params(m) for m in ms]
-    # each step = a bounded sample of the workload: ~2 s of CPU work, less when K is large so that the
-    # whole run (warm-up + K steps) stays around two minutes
-    probe_n = 20_000
-    t = time.perf_counter(); orc.grammar(params[0], 1, 0, probe_n); rate = probe_n / (time.perf_counter() - t)
-    step_seconds = min(2.0, 120.0 / max(1, args.steps + args.warmup))
-    per_step = max(2_000, int(rate * step_seconds / len(params)))
-    lo = 0
-    for _ in range(args.warmup):
-        for p in params:
-            orc.grammar(p, args.seed, lo, lo + per_step)
-        lo += per_step
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        for p in params:
-            orc.grammar(p, args.seed, lo, lo + per_step)
-        lo += per_step
-    dt = time.perf_counter() - t0
-    games = per_step * len(params) * args.steps
+    # the C port beside it (a few seconds): what the algorithm costs without the interpreter
+    pv, pcores, pdone, pel = cpu_port_throughput(ms, 3.0)
+    cpu_port = {"value": pv, "unit": UNIT, "cores": pcores, "kind": "port",
+                "sample": f"{pdone} games in {pel:.1f} s: C port of the reference algorithm (oracle_grammar) on {pcores} threads"}
+    if not rh.reference_available():
+        # fall back to the C port as the reference arm (oracle/_ref was not built: no reference checkout at build time)
+        params = [tables.build_params(m) for m in ms]
+        cores = orc.get_threads()
+        probe_n = 20_000
+        t = time.perf_counter(); orc.grammar(params[0], 1, 0, probe_n); rate = probe_n / (time.perf_counter() - t)
+        step_seconds = min(2.0, 120.0 / max(1, args.steps + args.warmup))
+        per_step = max(2_000, int(rate * step_seconds / len(params)))
+        lo = 0
+        for _ in range(args.warmup):
+            for p in params:
+                orc.grammar(p, args.seed, lo, lo + per_step)
+            lo += per_step
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            for p in params:
+                orc.grammar(p, args.seed, lo, lo + per_step)
+            lo += per_step
+        dt = time.perf_counter() - t0
+        games = per_step * len(params) * args.steps
+        kind, cores_used = "port", cores
+        sample = (f"{games} games: C port of the reference algorithm (oracle_grammar, Beta noise sampled), {cores} threads; "
+                  "oracle/_ref (the reference's byte code) was not available")
+    else:
+        procs = os.cpu_count() or 1
+        rh.load_reference()
+        for m in ms:
+            rh.saturate_reliever_counts(m)
+        # games per worker per step: ~step_seconds of work at the probed single-process rate
+        step_seconds = min(2.0, 120.0 / max(1, args.steps + args.warmup))
+        t = time.perf_counter()
+        rh._fixed_worker((ms[:1], 40, 1, True))
+        rate1 = 40 / (time.perf_counter() - t)
+        per_worker = max(len(ms), int(rate1 * step_seconds * 0.8))
+        per_worker -= per_worker % len(ms)
+        per_worker = max(per_worker, len(ms))
+        with mp.get_context("fork").Pool(procs) as pool:
+            def step(i):
+                return sum(pool.map(rh._fixed_worker, [(ms, per_worker, args.seed * 100_003 + i * procs + w, True) for w in range(procs)]))
+            for i in range(args.warmup):
+                step(i)
+            t0 = time.perf_counter()
+            games = sum(step(args.warmup + i) for i in range(args.steps))
+            dt = time.perf_counter() - t0
+        kind, cores_used = "reference", procs
+        sample = (f"{games} games ({per_worker} per worker process per step, {procs} processes): the reference's own simulate_game "
+                  f"(core/game_simulator.py, {rh.reference_kind()} of the unmodified checkout), reliever usage counts pre-saturated; "
+                  f"{games / dt / procs:.0f} games/s/core")
     v = games / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": name, "sample_per_step": f"{per_step} games per matchup per step ({len(params)} matchups)"},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{games} games: C port of the reference algorithm (oracle_grammar, Beta noise sampled), "
-                                   f"{cores} threads; the Python reference itself runs ~450 games/s/core (BASELINE.md)"},
+        "config": {"workload": name, "matchups": len(ms), "sims_per_matchup_per_gpu_per_step": sims,
+                   "sample_per_step": f"{games // max(1, args.steps)} games per step (bounded sample of the workload)"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores_used, "kind": kind, "sample": sample},
+        "cpu_port": cpu_port,
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+def extra_workloads(args, S_sims, local, world, rank, torch, dist):
+    """BASELINE configs[1-4] as fixed-size jobs over the N ranks (strong scaling), device-timed with CUDA events, max
+    over ranks; plus, per workload, the digest of a small fixed-(seed, sims) result, which must not depend on N."""
+    import numpy as np
+
+    from mlb_odds_engine_b200 import _abi
+    from mlb_odds_engine_b200.dist import ShardedSimulator
+
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "bench_digests.json")) as f:
+            pinned = json.load(f)
+    except Exception:
+        pinned = {}
+    S_blk = None
+    out = {}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")
+    for name, spec in bw.SPEC.items():
+        tbl = bw.build_tables(name)
+        n_m = len(tbl)
+        if spec["shard"] == "matchups":
+            S_blk = S_blk or ShardedSimulator(local, shard="matchups")
+            S = S_blk
+        else:
+            S = S_sims
+        S.load_tables(tbl)
+        sims = spec["sims"]
+        steps, warm = (5, 2) if n_m * sims <= 20_000_000 else (3, 1)
+
+        def one(lo):
+            S.run_device(sims, bw.SEED, sim_lo=lo)
+            if spec["shard"] == "matchups":
+                S.summarize_device()
+
+        for i in range(warm):
+            one(i * sims)
+            flush.fill_(1)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        launches0 = S.ctx.launch_count()
+        evs = []
+        for i in range(steps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            one((warm + i) * sims)
+            e1.record()
+            evs.append((e0, e1))
+            flush.fill_(i & 0xFF)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms_total = torch.tensor([sum(a.elapsed_time(b) for a, b in evs)], dtype=torch.float64, device=f"cuda:{local}")
+        if world > 1:
+            dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
+        ms_total = float(ms_total.item())
+        # digest step: small fixed job, full result back on the host
+        if spec["shard"] == "matchups":
+            rec = S.simulate_summary(spec["digest_sims"], bw.SEED, sim_lo=0)
+        else:
+            rec = S.simulate(spec["digest_sims"], bw.SEED, sim_lo=0)
+        assert int(rec["n_games"].sum()) == n_m * spec["digest_sims"], name
+        d = bw.digest(rec)
+        out[name] = {
+            "baseline_config": spec["config"], "what": spec["what"], "scaling": spec["scaling"], "shard": spec["shard"],
+            "matchups": n_m, "sims_per_matchup": sims, "steps": steps, "warmup": warm,
+            "ms_per_step": ms_total / steps, "games_per_s": n_m * sims * steps / (ms_total * 1e-3),
+            "gpu_launches": int(S.ctx.launch_count() - launches0),
+            "exchange": ("all-gather of %d B summaries" % (n_m * _abi.SUMMARY_DTYPE.itemsize) if spec["shard"] == "matchups"
+                         else "all-reduce of %d B histograms" % (n_m * _abi.HIST_DTYPE.itemsize)) if world > 1 else "none (1 GPU)",
+            "digest": {"sims_per_matchup": spec["digest_sims"], "seed": bw.SEED, "sha256": d,
+                       "matches_oracle_twin": (d == pinned[name]["sha256"]) if name in pinned else None},
+        }
+    if S_blk is not None:
+        S_blk.close()
+    return out
 
 
 def main():
@@ -258,7 +380,9 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("MLBSIM_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
+        # NCCL_DEBUG is left exactly as the caller set it; its log lines go to stderr (unless the caller chose a file)
+        # so that stdout stays the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
 
     from mlb_odds_engine_b200 import _abi, tables
@@ -378,6 +502,11 @@ def main():
             parity["probabilities"][k] = {"gpu": round(pg, 5), "ref": round(pr, 5), "delta": round(pg - pr, 5),
                                           "z": round(float(z_two_proportions(gpu_ev[k], n_gpu, ref_ev[k], g["n"])), 2)}
 
+    # ---------------- the other BASELINE configs as fixed-size jobs over the N ranks (strong scaling) + cross-N digests ----------------
+    workloads = None
+    if not args.no_workloads and args.workload == "single":
+        workloads = extra_workloads(args, S, local, world, rank, torch, dist)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -411,13 +540,15 @@ def main():
                 "note": "tables (18 KB/matchup) and histograms (165 KB/matchup) only; the path is not HBM-bound"},
     }
 
-    cpu_baseline = None
+    # CPU baselines on this box's host cores (rank 0): the reference's own Python simulate_game (oracle/_ref byte code
+    # here, where /root/reference does not exist), and beside it the C port of the same algorithm
+    cpu_baseline = cpu_port = None
     if not args.no_cpu_baseline:
-        v, cores, done, el = cpu_port_throughput(ms, args.cpu_seconds)
-        cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                        "sample": f"{done} games of the same workload in {el:.1f} s: C port of the reference algorithm "
-                                  f"(oracle_grammar: reference draw grammar, Beta noise sampled) on {cores} threads; "
-                                  "the Python reference itself measured 417-485 games/s/core (BASELINE.md)"}
+        v, cores, done, el = cpu_port_throughput(ms, min(4.0, args.cpu_seconds))
+        cpu_port = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                    "sample": f"{done} games of the same workload in {el:.1f} s: C port of the reference algorithm "
+                              f"(oracle_grammar: reference draw grammar, Beta noise sampled) on {cores} threads"}
+        cpu_baseline = cpu_reference_throughput(ms, args.cpu_seconds) or cpu_port
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -435,6 +566,8 @@ def main():
         "clocks": clocks,
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
+        "cpu_port": cpu_port,
+        "workloads": workloads,
         "wall_s_timed_region": t_wall,
         "device": info["name"],
     }

@@ -179,11 +179,17 @@ int mlbsim_synchronize(mlbsim_ctx* ctx);
  * buffer: it may be reused on return. */
 int mlbsim_upload_tables(mlbsim_ctx* ctx, const mlbsim_table* tables, int n_matchups);
 
+/* Matchup sharding ("for the sweep: by matchup block"): a rank that uploads only the tables of its
+ * own block tells the library which global matchup id its table 0 has, so that the Philox counter of uploaded table i
+ * carries id `base + i` and a grid point draws the same games whichever rank owns it.  Default 0; base + n_matchups
+ * must stay <= 4096. */
+int mlbsim_set_matchup_base(mlbsim_ctx* ctx, int base);
+
 /* Native-RNG mode: for every uploaded matchup m in [matchup_lo, matchup_hi) simulate the sims
  * [sim_lo, sim_hi) — the loop of cli/run_distribution_simulator.py:368-382 — and ADD the results
  * into hist_dev[m - matchup_lo] (device memory, caller-allocated, caller-zeroed).  Sim i of
  * matchup m draws one Philox2x32-10 block per plate appearance with counter
- * (i[31:0], pa_number[12:0] | m << 14 | i[37:32] << 26) and a 32-bit key derived from `seed`
+ * (i[31:0], pa_number[12:0] | (base + m) << 14 | i[37:32] << 26) and a 32-bit key derived from `seed`
  * (word 0 of Philox4x32-10 over a fixed domain-separation counter), so its outcome does not depend
  * on the launch geometry or the number of GPUs.  Limits: m < 4096, i < 2^38, < 2^13 plate appearances per game
  * (guaranteed by MLBSIM_MAX_INNINGS).  Asynchronous on the

@@ -19,7 +19,7 @@ SYMBOLS = [
     "mlbsim_run_native", "mlbsim_run_native_host", "mlbsim_run_replay", "mlbsim_run_replay_dev",
     "mlbsim_run_persim", "mlbsim_malloc", "mlbsim_free", "mlbsim_memset", "mlbsim_memcpy_h2d", "mlbsim_memcpy_d2h",
     "mlbsim_launch_count", "mlbsim_set_launch_config", "mlbsim_last_kernel_ms",
-    "mlbsim_summarize", "mlbsim_run_native_summary_host", "mlbsim_allreduce",
+    "mlbsim_summarize", "mlbsim_run_native_summary_host", "mlbsim_allreduce", "mlbsim_set_matchup_base",
 ]
 
 ERR_NAMES = {1: "CUDA", 2: "ARG", 3: "TABLE", 4: "NO_DEVICE", 5: "STATE"}
@@ -87,6 +87,7 @@ def load() -> ctypes.CDLL:
         "mlbsim_summarize": (i32, [vp, vp, i32, vp]),
         "mlbsim_run_native_summary_host": (i32, [vp, i32, i32, u64, u64, u64, vp, u32]),
         "mlbsim_allreduce": (i32, [vp, vp, vp, i32]),
+        "mlbsim_set_matchup_base": (i32, [vp, i32]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(L, name)  # AttributeError if the library lacks a declared symbol
@@ -150,6 +151,10 @@ class Context:
 
     def set_launch_config(self, threads_per_block=0, blocks_per_sm=0):
         self._ck(self.L.mlbsim_set_launch_config(self.h, int(threads_per_block), int(blocks_per_sm)))
+
+    def set_matchup_base(self, base: int):
+        """Global matchup id of uploaded table 0 (matchup sharding: include/mlbsim.h)."""
+        self._ck(self.L.mlbsim_set_matchup_base(self.h, int(base)))
 
     def launch_count(self) -> int:
         return int(self.L.mlbsim_launch_count(self.h))

@@ -27,6 +27,7 @@ struct mlbsim_ctx {
   mlbsim_staged_table* staged_dev = nullptr;   // shared-memory image of each table (the native kernel bulk-copies these)
   int n_tables = 0;
   int tables_cap = 0;
+  int matchup_base = 0;   // global id of uploaded table 0 (matchup sharding)
   unsigned long long* counters_dev = nullptr;
   int counters_cap = 0;
   mlbsim_hist* hist_scratch = nullptr;  // used by *_host entry points
@@ -172,6 +173,13 @@ int mlbsim_set_launch_config(mlbsim_ctx* ctx, int threads_per_block, int blocks_
 
 uint64_t mlbsim_launch_count(const mlbsim_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+int mlbsim_set_matchup_base(mlbsim_ctx* ctx, int base) {
+  if (!ctx) return MLBSIM_ERR_ARG;
+  if (base < 0 || (unsigned)base >= RNG_MAX_MATCHUPS) return fail(ctx, MLBSIM_ERR_ARG, "matchup base outside [0, 4096)");
+  ctx->matchup_base = base;
+  return MLBSIM_OK;
+}
+
 int mlbsim_upload_tables(mlbsim_ctx* ctx, const mlbsim_table* tables, int n_matchups) {
   if (!ctx) return MLBSIM_ERR_ARG;
   if (!tables || n_matchups <= 0) return fail(ctx, MLBSIM_ERR_ARG, "mlbsim_upload_tables: no tables");
@@ -217,7 +225,7 @@ static int launch_native(mlbsim_ctx* ctx, int matchup_lo, int matchup_hi, uint64
   if (matchup_lo < 0 || matchup_hi > ctx->n_tables || matchup_lo >= matchup_hi) return fail(ctx, MLBSIM_ERR_ARG, "matchup range out of bounds");
   if (sim_hi < sim_lo) return fail(ctx, MLBSIM_ERR_ARG, "sim_hi < sim_lo");
   if (sim_hi > RNG_MAX_SIM_INDEX) return fail(ctx, MLBSIM_ERR_ARG, "sim index beyond 2^38 (Philox counter field)");
-  if ((unsigned)matchup_hi > RNG_MAX_MATCHUPS) return fail(ctx, MLBSIM_ERR_ARG, "more than 4096 matchups (Philox counter field)");
+  if ((unsigned)(ctx->matchup_base + matchup_hi) > RNG_MAX_MATCHUPS) return fail(ctx, MLBSIM_ERR_ARG, "matchup id beyond 4096 (Philox counter field)");
   if (!hist_dev) return fail(ctx, MLBSIM_ERR_ARG, "hist pointer is NULL");
   const int n_m = matchup_hi - matchup_lo;
   const int threads = ctx->threads_per_block ? ctx->threads_per_block : MLBSIM_NATIVE_MAX_THREADS;
@@ -253,7 +261,7 @@ static int launch_native(mlbsim_ctx* ctx, int matchup_lo, int matchup_hi, uint64
     a.sim_lo = lo;
     a.n_sims = (uint32_t)n;
     a.n_matchups = (uint32_t)n_m;
-    a.matchup_base = (uint32_t)matchup_lo;
+    a.matchup_base = (uint32_t)(ctx->matchup_base + matchup_lo);
     // chunk: ~NATIVE_FETCHES_PER_WARP fetches per warp when all warps share one matchup, bounded to [32, 1024],
     // multiple of 32.  Smaller chunks shorten the tail (warps that run dry wait at the block barrier).
     uint64_t chunk = (n * (uint64_t)n_m) / (total_warps * NATIVE_FETCHES_PER_WARP + 1);
@@ -486,7 +494,7 @@ int mlbsim_run_persim(mlbsim_ctx* ctx, int matchup, uint64_t sim_lo, uint64_t si
   if (!ctx->tables_dev) return fail(ctx, MLBSIM_ERR_STATE, "mlbsim_run_persim before mlbsim_upload_tables");
   if (matchup < 0 || matchup >= ctx->n_tables) return fail(ctx, MLBSIM_ERR_ARG, "matchup out of range");
   if (sim_hi < sim_lo || !out_host) return fail(ctx, MLBSIM_ERR_ARG, "mlbsim_run_persim: bad argument");
-  if (sim_hi > RNG_MAX_SIM_INDEX || (unsigned)matchup >= RNG_MAX_MATCHUPS) return fail(ctx, MLBSIM_ERR_ARG, "sim or matchup index beyond the Philox counter fields");
+  if (sim_hi > RNG_MAX_SIM_INDEX || (unsigned)(ctx->matchup_base + matchup) >= RNG_MAX_MATCHUPS) return fail(ctx, MLBSIM_ERR_ARG, "sim or matchup index beyond the Philox counter fields");
   const uint64_t n = sim_hi - sim_lo;
   if (n == 0) return MLBSIM_OK;
   CK(ctx, cudaSetDevice(ctx->device));
@@ -503,7 +511,7 @@ int mlbsim_run_persim(mlbsim_ctx* ctx, int matchup, uint64_t sim_lo, uint64_t si
     a.out = out_dev;
     a.sim_lo = sim_lo + done;
     a.n_sims = m;
-    a.matchup_id = (uint32_t)matchup;
+    a.matchup_id = (uint32_t)(ctx->matchup_base + matchup);
     a.keys = philox2_keys_from_seed(seed);
     const int threads = 128;
     uint64_t blocks = (m + threads - 1) / threads;

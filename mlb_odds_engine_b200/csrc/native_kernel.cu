@@ -34,10 +34,11 @@
 
 // tuning switches (scripts/variant_sweep.sh builds one library per set of -D switches; results under profiles/)
 #ifndef OPT_UNROLL
-#define OPT_UNROLL 4   /* plate appearances per round: one refill check and one boundary pass per round */
+#define OPT_UNROLL 5   /* plate appearances per round: one refill check and one boundary pass per round (3/4/5/6 measured: profiles/r02_v15_variants.log) */
 #endif
 #ifndef OPT_PA_WARP
-#define OPT_PA_WARP 0  /* 1: PA outcome counters per warp (16 words, same-address lanes merged by ATOMS.POPC.INC) instead of per thread */
+#define OPT_PA_WARP 1  /* 1: PA outcome counters per warp (16 words, same-address lanes merged by ATOMS.POPC.INC) instead of per thread:
+                          same speed, 40 KB less shared memory per block (profiles/r02_v15_variants.log) */
 #endif
 #ifndef OPT_GATE_LAST
 #define OPT_GATE_LAST 0  /* G > 0: skip the last PA step of a round when fewer than G lanes are still inside their half */

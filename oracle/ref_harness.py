@@ -1,5 +1,6 @@
 """TEST INFRASTRUCTURE — not product code.  Drives the UNMODIFIED reference (imported read-only
-from /root/reference, which exists only in the build container, never on the GPU box) to
+from /root/reference in the build container; on the GPU box, where that path does not exist, from the byte code
+oracle/make_ref.py compiled into oracle/_ref/) to
 
   * record value-level replay tapes of `simulate_game` (SURVEY.md §8(c) "Replay tape"), and
   * batch-run seeded games over worker processes for statistical oracles,
@@ -23,7 +24,9 @@ import types
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get("MLBSIM_REFERENCE_ROOT", "/root/reference")
+_BYTECODE_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+REFERENCE_ROOT = os.environ.get("MLBSIM_REFERENCE_ROOT") or (
+    "/root/reference" if os.path.isdir("/root/reference/core") else _BYTECODE_ROOT)
 OUTCOMES = ["K", "BB", "1B", "2B", "3B", "HR", "OUT"]
 
 _mods = None
@@ -31,6 +34,11 @@ _mods = None
 
 def reference_available() -> bool:
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "core"))
+
+
+def reference_kind() -> str:
+    """'source' (the checkout) or 'bytecode' (oracle/_ref, compiled from it by oracle/make_ref.py)."""
+    return "bytecode" if os.path.realpath(REFERENCE_ROOT) == os.path.realpath(_BYTECODE_ROOT) else "source"
 
 
 def load_reference():
@@ -265,3 +273,83 @@ def stat_batch(matchup, n_games, seed, use_noise=True, procs=None):
         for k in tot:
             tot[k] = tot[k] + p[k]
     return tot
+
+
+# ---------------------------------------------------------------------------------------------
+# timed batch: the reference's own CPU path on all host cores for a bounded time (bench.py's cpu_baseline)
+# ---------------------------------------------------------------------------------------------
+def _timed_worker(args):
+    import time
+
+    matchups, seconds, seed, use_noise, want_stats = args
+    ref = load_reference()
+    reset_reliever_counts()
+    for m in matchups:
+        saturate_reliever_counts(m)
+    random.seed(seed)
+    np.random.seed(seed % (2**32))
+    kws = [_game_kwargs(m, use_noise) for m in matchups]
+    stats = [new_stats() for _ in matchups] if want_stats else None
+    sim = ref.gs.simulate_game
+    n = 0
+    t0 = time.perf_counter()
+    deadline = t0 + seconds
+    while True:
+        for i, kw in enumerate(kws):          # the loop body of cli/run_distribution_simulator.py:368-382
+            if want_stats:
+                for t in ("HOME", "AWAY"):
+                    for o in OUTCOMES:
+                        ref.pa.PA_RECAP_LOG[t][o] = 0
+            res = sim(**kw)
+            if want_stats:
+                accumulate(stats[i], res, matchups[i])
+                stats[i]["pa"][0] += [ref.pa.PA_RECAP_LOG["AWAY"][o] for o in OUTCOMES]
+                stats[i]["pa"][1] += [ref.pa.PA_RECAP_LOG["HOME"][o] for o in OUTCOMES]
+        n += len(kws)
+        if time.perf_counter() >= deadline:
+            break
+    return n, time.perf_counter() - t0, stats
+
+
+def _fixed_worker(args):
+    """`n_games` reference games round-robin over `matchups` (bench.py --impl reference: one step of one worker)."""
+    matchups, n_games, seed, use_noise = args
+    ref = load_reference()
+    for m in matchups:
+        saturate_reliever_counts(m)
+    random.seed(seed)
+    np.random.seed(seed % (2**32))
+    kws = [_game_kwargs(m, use_noise) for m in matchups]
+    sim = ref.gs.simulate_game
+    done = 0
+    while done < n_games:
+        for kw in kws:
+            sim(**kw)
+        done += len(kws)
+    return done
+
+
+def timed_batch(matchups, seconds, seed=1, use_noise=True, procs=None, want_stats=False):
+    """Run the unmodified `simulate_game` round-robin over `matchups` in `procs` forked worker processes (default: every
+    host core) for about `seconds` each.  Returns (games, wall_seconds, procs, stats | None); games / wall_seconds is the
+    reference's CPU throughput on this host."""
+    import multiprocessing as mp
+    import time
+
+    procs = procs or os.cpu_count() or 1
+    load_reference()                      # import once; the workers inherit it through fork
+    jobs = [(matchups, seconds, seed * 1000 + i, use_noise, want_stats) for i in range(procs)]
+    t0 = time.perf_counter()
+    with mp.get_context("fork").Pool(procs) as pool:
+        parts = pool.map(_timed_worker, jobs)
+    wall = time.perf_counter() - t0
+    games = sum(p[0] for p in parts)
+    busy = max(p[1] for p in parts)       # workers start together; the slowest one bounds the batch
+    stats = None
+    if want_stats:
+        stats = [new_stats() for _ in matchups]
+        for p in parts:
+            for i in range(len(matchups)):
+                for k in stats[i]:
+                    stats[i][k] = stats[i][k] + p[2][i][k]
+    return games, busy, procs, stats, wall

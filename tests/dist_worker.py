@@ -23,9 +23,17 @@ def main():
     for m in range(3):
         rec[m] = orc.native(tb[m], m, lo, hi, seed)
     tot = mdist.allreduce_hist_numpy(rec)
+    # matchup-sharded sweep: this rank simulates only its block of the 3 grid points, all sims; summaries are gathered
+    m_lo, m_hi = mdist.shard_range(0, 3, rank, world)
+    local = np.zeros(m_hi - m_lo, dtype=_abi.SUMMARY_DTYPE)
+    for m in range(m_lo, m_hi):
+        local[m - m_lo] = _abi.summarize_hist(orc.native(tb[m], m, 1000, 1000 + n, seed))
+    summ = mdist.allgather_summaries_numpy(local, 3)
     if rank == 0:
         with open(out_path, "wb") as f:
             f.write(tot.tobytes())
+        with open(out_path + ".summ", "wb") as f:
+            f.write(summ.tobytes())
     dist.barrier()
     dist.destroy_process_group()
 

@@ -38,6 +38,22 @@ def main():
         if summ[m].tobytes() != _abi.summarize_hist(tot[m]).tobytes():
             ok = False
             print(f"rank {dist.get_rank()} matchup {m}: device summary differs from the reduced histogram", flush=True)
+    # matchup-sharded sweep: every rank owns a block of the 5 grid points, summaries all-gathered; the result must be
+    # what one GPU computes alone (same games: the Philox counter carries the global matchup id)
+    five = synth.make_slate(n_games=5)
+    five[2]["away_bullpen"] = None
+    from mlb_odds_engine_b200 import tables
+
+    tb = tables.build_tables(five)
+    B = ShardedSimulator(local, shard="matchups")
+    B.load_tables(tb)
+    got = B.simulate_summary(40_000, seed, sim_lo=5)
+    for m in range(5):
+        want = _abi.summarize_hist(orc.native(tb[m], m, 5, 5 + 40_000, seed))
+        if got[m].tobytes() != want.tobytes():
+            ok = False
+            print(f"rank {dist.get_rank()} grid point {m}: matchup-sharded summary differs from the oracle", flush=True)
+    B.close()
     flag = torch.tensor([0 if ok else 1], device=f"cuda:{local}")
     dist.all_reduce(flag)
     ok = int(flag.item()) == 0

@@ -31,9 +31,13 @@ def test_sharded_allreduce_equals_single_rank(world, tmp_path):
                 p.kill()
     got = np.frombuffer(open(out, "rb").read(), dtype=_abi.HIST_DTYPE)
     tb = tables.build_tables(synth.make_slate(n_games=3))
+    summ = np.frombuffer(open(out + ".summ", "rb").read(), dtype=_abi.SUMMARY_DTYPE)
+    assert len(summ) == 3
     for m in range(3):
         want = orc.native(tb[m], m, 1000, 1000 + n, seed)
         assert got[m].tobytes() == want.tobytes()
+        # the matchup-sharded path (blocks of grid points + all-gather of summaries) sees the same games
+        assert summ[m].tobytes() == _abi.summarize_hist(want).tobytes()
 
 
 def test_shard_range_tiles_exactly():

@@ -34,7 +34,7 @@ def test_c_abi_allreduce(tmp_path):
         pytest.skip("needs at least 2 GPUs")
     world = 2 if n < 4 else 4
     id_file = str(tmp_path / "nccl_id")
-    env = dict(os.environ, NCCL_DEBUG="WARN")
+    env = dict(os.environ)   # NCCL_DEBUG stays whatever the caller set
     procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "nccl_capi_worker.py"), str(r), str(world), id_file],
                               stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env) for r in range(world)]
     outs = []
