@@ -198,7 +198,11 @@ def cpu_reference_throughput(matchups, seconds, procs=None):
 
     if not rh.reference_available():
         return None
-    games, busy, procs, _, wall = rh.timed_batch(matchups, seconds, seed=1, procs=procs)
+    try:
+        games, busy, procs, _, wall = rh.timed_batch(matchups, seconds, seed=1, procs=procs)
+    except Exception as e:   # a baseline that cannot run must not take the measurement down with it
+        sys.stderr.write(f"bench.py: the reference could not be run ({type(e).__name__}: {e}); reporting the C port only\n")
+        return None
     return {"value": games / busy, "unit": UNIT, "cores": procs, "kind": "reference",
             "sample": f"{games} games of the same workload in {busy:.1f} s: the reference's own simulate_game "
                       f"(core/game_simulator.py, {rh.reference_kind()} of the unmodified checkout) in {procs} processes, "

@@ -35,9 +35,35 @@ class ResultFeeder:
         return r
 
 
+def argument_fingerprint(kw: dict) -> tuple:
+    """Every value of a `simulate_game` argument set that the hot path reads (the fields `tables.Matchup` parses),
+    as one hashable tuple.  Two argument sets with the same fingerprint simulate the same games; an argument set that
+    is edited in place between calls, or a new set that happens to live at a recycled address, changes it."""
+    def batter(b):
+        return (b.get("k_rate", 0.22), b.get("bb_rate", 0.08), b.get("speed", 50))
+
+    def pitcher(p):
+        hr = p.get("hr_pa", {})
+        return (p.get("k_rate"), p.get("bb_rate"), hr.get("hr_pa_projected", 0.046) if isinstance(hr, dict) else repr(hr),
+                p.get("exit_velocity_avg"), p.get("launch_angle_avg"), p.get("fielder_rating", 50), p.get("name", "Unknown"))
+
+    env = kw.get("env") or {}
+    ump = env.get("umpire", {}) or {}
+    return (
+        tuple(batter(b) for b in kw["home_lineup"]), tuple(batter(b) for b in kw["away_lineup"]),
+        pitcher(kw["home_pitcher"]), pitcher(kw["away_pitcher"]),
+        tuple(pitcher(p) for p in (kw.get("home_bullpen") or [])), tuple(pitcher(p) for p in (kw.get("away_bullpen") or [])),
+        ump.get("k_mod", 1.0), ump.get("bb_mod", 1.0), env.get("weather_hr", 1.0), bool(kw.get("use_noise", True)),
+    )
+
+
 class GpuSimulateGame:
     """`simulate_game` replacement backed by `mlbsim_run_persim` (same signature, core/game_simulator.py:14-25).
-    `debug` / `return_inning_scores` are honoured where they have a GPU-native meaning."""
+    `debug` / `return_inning_scores` are honoured where they have a GPU-native meaning.
+
+    Prefetched results are keyed by the CONTENT of the arguments (`argument_fingerprint`), never by object identity:
+    the next game of a slate, or the same dicts edited in place, get their own simulation.  `reset()` drops the
+    prefetched games explicitly (e.g. to re-simulate the same matchup with the next block of sim indices)."""
 
     def __init__(self, n_prefetch: int = 10_000, seed: int = 0, device: int = 0):
         self.n_prefetch = int(n_prefetch)
@@ -46,15 +72,15 @@ class GpuSimulateGame:
         self._key = None
         self._feeder = None
 
-    def _arg_key(self, kw):
-        return tuple(id(kw.get(k)) for k in ("home_lineup", "away_lineup", "home_pitcher", "away_pitcher", "env",
-                                             "home_bullpen", "away_bullpen")) + (bool(kw.get("use_noise", True)),)
+    def reset(self):
+        self._key = None
+        self._feeder = None
 
     def __call__(self, home_lineup, away_lineup, home_pitcher, away_pitcher, env, home_bullpen=None, away_bullpen=None,
                  debug=False, return_inning_scores=False, use_noise=True):
         kw = dict(home_lineup=home_lineup, away_lineup=away_lineup, home_pitcher=home_pitcher, away_pitcher=away_pitcher,
                   env=env, home_bullpen=home_bullpen, away_bullpen=away_bullpen, use_noise=use_noise)
-        key = self._arg_key(kw)
+        key = argument_fingerprint(kw)
         if key != self._key:
             m = tables.Matchup(**kw)
             self.sim.load_matchups([m])

@@ -133,6 +133,56 @@ def _entry(market, side, prob, odds):
     return {"market": market, "side": side, "sim_prob": round(prob, 4), "fair_odds": round(odds, 2), "source": "simulator"}
 
 
+SNAPSHOT_PATH = os.path.join("backtest", "last_table_snapshot.json")   # cli/run_distribution_simulator.py:25
+
+
+def parse_game_id(game_id: str) -> dict:
+    """{"date", "away", "home", "time"} of 'YYYY-MM-DD-AWAY@HOME[-T1905[-DH1]]' (core/utils.py:920-939, including its
+    fallback for strings it cannot split)."""
+    try:
+        parts = game_id.split("-")
+        if len(parts) < 4:
+            raise ValueError("invalid game_id")
+        away, home = parts[3].split("@")
+        return {"date": "-".join(parts[:3]), "away": away, "home": home, "time": "-".join(parts[4:])}
+    except Exception:
+        return {"date": game_id, "away": "", "home": "", "time": ""}
+
+
+def _eastern():
+    from zoneinfo import ZoneInfo, ZoneInfoNotFoundError
+
+    for name in ("US/Eastern", "America/New_York", "UTC"):      # core/utils.py:29-35
+        try:
+            return ZoneInfo(name)
+        except ZoneInfoNotFoundError:
+            continue
+
+
+def start_time_iso_from_game_id(game_id: str):
+    """What `simulate_distribution` stores as `start_time_iso` when the market-odds file has no entry for the game
+    (cli/run_distribution_simulator.py:243-250): the Eastern start time encoded in the id's -T suffix, or midnight of
+    its date (core/utils.py:1009-1027 `game_id_to_dt`), ISO formatted; None if the id carries no date."""
+    from datetime import datetime
+
+    parts = parse_game_id(game_id)
+    date, token = parts.get("date"), parts.get("time", "")
+    dt = None
+    if token.startswith("T"):
+        digits = "".join(c for c in token.split("-")[0][1:] if c.isdigit())[:4]
+        if len(digits) == 4:
+            try:
+                dt = datetime.strptime(f"{date} {digits}", "%Y-%m-%d %H%M")
+            except Exception:
+                dt = None
+    if dt is None and date:
+        try:
+            dt = datetime.strptime(date, "%Y-%m-%d")
+        except Exception:
+            dt = None
+    return dt.replace(tzinfo=_eastern()).isoformat() if dt else None
+
+
 def _teams(game_id):
     """(away, home) abbreviations from 'YYYY-MM-DD-AWAY@HOME[-T....]' (core/utils.py:920-948)."""
     left, right = game_id.split("@", 1)
@@ -154,6 +204,8 @@ def price_from_histogram(hist, game_id: str, calibration: dict | None = None, st
     rec = hist.rec if hasattr(hist, "rec") else hist
     joint = rec["joint"]
     calibration = calibration or {}
+    if not start_time_iso:      # no odds-file entry: derive it from the id, as the reference does (:248-250)
+        start_time_iso = start_time_iso_from_game_id(game_id)
     team_scaling = calibration.get("team_total_scaling", {})
     hm, hsd = team_scaling.get("home_mean_factor", 1.0), team_scaling.get("home_std_factor", 1.0)
     am, asd = team_scaling.get("away_mean_factor", 1.0), team_scaling.get("away_std_factor", 1.0)
@@ -344,3 +396,12 @@ def write_sim_json(doc: dict, target_path: str) -> None:
         json.dump(doc, f, indent=2)
         tmp = f.name
     os.replace(tmp, target_path)
+
+
+def write_table_snapshot(doc: dict, path: str = SNAPSHOT_PATH) -> None:
+    """The side file `simulate_distribution` rewrites after every game (cli/run_distribution_simulator.py:853-859):
+    {"<market>:<side>": {"fair_odds", "ev_percent"}} of the game just priced."""
+    snap = {f"{e['market']}:{e['side']}": {"fair_odds": e.get("fair_odds"), "ev_percent": e.get("ev_percent")} for e in doc["markets"]}
+    os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
+    with open(path, "w") as f:
+        json.dump(snap, f, indent=2)

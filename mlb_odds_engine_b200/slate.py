@@ -31,37 +31,48 @@ def matchup_from_assets(game_id: str, assets: dict, env: dict | None = None, use
 
 def run_slate(matchups: list[dict], n_sims: int = 10_000, seed: int = 0, calibration: dict | None = None,
               out_dir: str | None = None, safe: bool = False, sim: GpuSimulator | None = None,
-              start_times: dict | None = None) -> dict:
+              start_times: dict | None = None, snapshot_path: str | None = None) -> dict:
     """Simulate every game of the slate in one launch and price it.  `matchups`: simulate_game keyword
-    dicts carrying `game_id`.  Returns {game_id: document}; with `out_dir` also writes
-    `<out_dir>/<date>/<game_id>.json`.  Per-game failures (malformed assets) raise, or with
-    `safe=True` are reported under "failed" and skipped — the semantics of `--safe`
-    (cli/full_slate_runner.py:157-162)."""
+    dicts carrying `game_id` ('YYYY-MM-DD-AWAY@HOME[-Thhmm]').  Returns {game_id: document}; with `out_dir` also writes
+    `<out_dir>/<date>/<game_id>.json`, and with `snapshot_path` the `last_table_snapshot.json` side file the reference
+    rewrites after every game (cli/run_distribution_simulator.py:853-859; the last game of the slate wins, as in the
+    serial loop).  A game that fails — malformed assets, an id without AWAY@HOME, an unwritable path — raises, or with
+    `safe=True` is reported under "failed" and skipped: the semantics of `--safe` (cli/full_slate_runner.py:157-162)."""
     own = sim is None
     sim = sim or GpuSimulator(0)
     built, failed = [], {}
-    for m in matchups:
-        gid = m.get("game_id", f"game{len(built)}")
+    for i, m in enumerate(matchups):
+        gid = m.get("game_id", f"game{i}")
         try:
+            if not all(distribution.parse_game_id(gid)[k] for k in ("date", "away", "home")):
+                raise ValueError(f"game_id {gid!r} is not of the form YYYY-MM-DD-AWAY@HOME[-Thhmm]")
             built.append((gid, tables.as_matchup(m)))
-        except Exception as e:  # what simulate_game would raise on the first PA
+        except Exception as e:  # what simulate_game would raise on the first PA / simulate_distribution on the id
             if not safe:
                 raise
             failed[gid] = f"{type(e).__name__}: {e}"
     docs = {}
-    if built:
-        sim.load_matchups([m for _, m in built])
-        hists = sim.simulate(n_sims, seed=seed)
-        for (gid, _), h in zip(built, hists):
-            doc = distribution.price_from_histogram(h, gid, calibration, (start_times or {}).get(gid))
-            doc["reliever_usage"] = h.reliever_usage()
-            doc["pa_recap"] = h.pa_recap()
-            docs[gid] = doc
-            if out_dir:
-                date_tag = "-".join(gid.split("-")[:3])
-                distribution.write_sim_json(doc, os.path.join(out_dir, date_tag, f"{gid}.json"))
-    if own:
-        sim.close()
+    try:
+        if built:
+            sim.load_matchups([m for _, m in built])
+            hists = sim.simulate(n_sims, seed=seed)
+            for (gid, _), h in zip(built, hists):
+                try:
+                    doc = distribution.price_from_histogram(h, gid, calibration, (start_times or {}).get(gid))
+                    doc["reliever_usage"] = h.reliever_usage()
+                    doc["pa_recap"] = h.pa_recap()
+                    if out_dir:
+                        distribution.write_sim_json(doc, os.path.join(out_dir, distribution.parse_game_id(gid)["date"], f"{gid}.json"))
+                    if snapshot_path:
+                        distribution.write_table_snapshot(doc, snapshot_path)
+                    docs[gid] = doc
+                except Exception as e:
+                    if not safe:
+                        raise
+                    failed[gid] = f"{type(e).__name__}: {e}"
+    finally:
+        if own:
+            sim.close()
     if failed:
         docs["failed"] = failed
     return docs

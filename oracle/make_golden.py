@@ -117,18 +117,30 @@ def make_replay(name, matchup, use_noise, n_games, seed):
     print(f"replay_{name}: {n_games} games, {lens.sum()} draws, mean tape {lens.mean():.1f}, max innings {max_inn}")
 
 
-def make_stats(name, matchup, use_noise, n_games, seed):
+# Fixtures that are the sum of several independent seeded batches: name -> (seeds, games per batch).  The batches are
+# merged HERE, so `--stats --only <name>` reproduces the committed file (8 worker processes: the per-process seeds
+# derive from the batch seed and the process index, ref_harness.stat_batch).
+MERGED_STATS = {"bench_texhou": ((83, 991), 1_000_000)}
+STATS_PROCS = 8
+
+
+def make_stats(name, matchup, use_noise, n_games, seed, out_dir=None):
+    seeds, per_batch = MERGED_STATS.get(name, ((seed,), n_games))
     t = time.time()
-    st = rh.stat_batch(matchup, n_games, seed, use_noise=use_noise)
+    st = None
+    for sd in seeds:
+        part = rh.stat_batch(matchup, per_batch, sd, use_noise=use_noise, procs=STATS_PROCS)
+        st = part if st is None else {k: st[k] + part[k] for k in st}
     dt = time.time() - t
+    extra = {"seeds": np.array(seeds, dtype=np.int64)} if len(seeds) > 1 else {}
     np.savez_compressed(
-        os.path.join(GOLDEN, f"stats_{name}.npz"),
-        matchup=jsonable(matchup), use_noise=use_noise, seed=seed, n=st["n"],
+        os.path.join(out_dir or GOLDEN, f"stats_{name}.npz"),
+        matchup=jsonable(matchup), use_noise=use_noise, seed=seeds[0], n=st["n"],
         joint=st["joint"].astype(np.int32), innings=st["innings"], pa=st["pa"],
         rel_games=st["rel_games"], rel_picks=st["rel_picks"],
-        ref_games_per_s=n_games / dt, ref_procs=os.cpu_count(),
+        ref_games_per_s=st["n"] / dt, ref_procs=STATS_PROCS, **extra,
     )
-    print(f"stats_{name}: {n_games} games in {dt:.1f}s ({n_games / dt:.0f} games/s on {os.cpu_count()} procs)")
+    print(f"stats_{name}: {st['n']} games in {dt:.1f}s ({st['n'] / dt:.0f} games/s on {STATS_PROCS} procs)")
 
 
 def main():
@@ -137,6 +149,7 @@ def main():
     ap.add_argument("--stats-games", type=int, default=200000)
     ap.add_argument("--only", default=None)
     ap.add_argument("--no-replay", action="store_true", help="leave the replay fixtures alone (with --stats)")
+    ap.add_argument("--out-dir", default=None, help="write the stats fixtures somewhere else (to compare with the committed ones)")
     args = ap.parse_args()
     os.makedirs(GOLDEN, exist_ok=True)
     sc = scenarios()
@@ -145,23 +158,24 @@ def main():
             continue
         make_replay(name, m, noise, n, seed=1000 + i)
     if args.stats:
-        # (stats_bench_texhou.npz holds 2 x 10^6 games: this batch plus an independent one with seed 991, merged by hand)
+        # (stats_bench_texhou.npz holds 2 x 10^6 games: two seeded batches merged in make_stats, see MERGED_STATS)
         for i, name in enumerate(["hetero_bullpen_noise", "hetero_nobullpen_noise", "neutral_calibration", "odd_onesided",
                                   "short_degenerate", "hetero_bullpen_nonoise", "bench_texhou"]):
             if args.only and args.only != name:
                 continue
             m, noise, _ = sc[name]
-            make_stats(name, m, noise, args.stats_games, seed=77 + i)
+            make_stats(name, m, noise, args.stats_games, seed=77 + i, out_dir=args.out_dir)
 
 
-if __name__ == "__main__" and "--distribution" not in sys.argv and "--assets" not in sys.argv:
+if __name__ == "__main__" and not any(a in sys.argv for a in ("--distribution", "--distribution2", "--assets")):
     main()
 
 
 # ---------------------------------------------------------------------------------------------
 # N1 fixture: the reference's own reduction / pricing chain on a fixed set of per-sim results
 # ---------------------------------------------------------------------------------------------
-def make_distribution_fixture(n_sims=10000, seed=20250404, game_id="2025-04-04-TEX@HOU"):
+def make_distribution_fixture(n_sims=10000, seed=20250404, game_id="2025-04-04-TEX@HOU", with_calibration=True,
+                              out_name="distribution_TEXHOU.json", matchup_seed=None):
     """Runs the UNMODIFIED `simulate_distribution` (cli/run_distribution_simulator.py:195) with its
     module-global `simulate_game` replaced by an iterator over per-sim results produced by the
     oracle's native twin (deterministic: the test regenerates them), and stores what it priced."""
@@ -190,7 +204,7 @@ def make_distribution_fixture(n_sims=10000, seed=20250404, game_id="2025-04-04-T
             stub(extra, By=object, WebDriverWait=object, load_dotenv=lambda *a, **k: None)
     import cli.run_distribution_simulator as rds
 
-    matchup = synth.make_matchup(game_id)
+    matchup = synth.make_matchup(game_id) if matchup_seed is None else synth.make_matchup(game_id, seed=matchup_seed)
     table = tables.build_table(matchup)
     games = orc.native_persim(table, 0, 0, n_sims, seed)
     names = [[p["name"] for p in matchup["home_bullpen"]], [p["name"] for p in matchup["away_bullpen"]]]
@@ -220,24 +234,32 @@ def make_distribution_fixture(n_sims=10000, seed=20250404, game_id="2025-04-04-T
     import tempfile
     os.chdir(tempfile.mkdtemp(prefix="mlbsim_golden_"))   # the reference reads and writes CWD-relative paths
     os.makedirs("logs", exist_ok=True)
-    shutil.copy(os.path.join(rh.REFERENCE_ROOT, "logs", "calibration_offset.json"), "logs/calibration_offset.json")
+    if with_calibration:
+        shutil.copy(os.path.join(rh.REFERENCE_ROOT, "logs", "calibration_offset.json"), "logs/calibration_offset.json")
+    # (without the file the reference prices with factors 1.0 and leaves the segments unscaled:
+    #  cli/run_distribution_simulator.py:351-354, 657-674)
     rds.simulate_distribution(game_id, 9.5, no_weather=True, export_json="./dist_out.json", n_simulations=n_sims)
     doc = json.load(open("./dist_out.json"))
+    snapshot = json.load(open(rds.SNAPSHOT_PATH))      # the side file of :853-859
     for block in ("raw_distributions", "scaled_distributions"):
         for v in doc[block].values():
             v.pop("values", None)
     fixture = {
-        "game_id": game_id, "n_sims": n_sims, "seed": seed,
-        "calibration": json.load(open("logs/calibration_offset.json")),
-        "doc": doc,
+        "game_id": game_id, "n_sims": n_sims, "seed": seed, "matchup_seed": matchup_seed,
+        "calibration": json.load(open("logs/calibration_offset.json")) if with_calibration else None,
+        "doc": doc, "table_snapshot": snapshot,
     }
-    with open(os.path.join(GOLDEN, "distribution_TEXHOU.json"), "w") as f:
+    with open(os.path.join(GOLDEN, out_name), "w") as f:
         json.dump(fixture, f, indent=1, sort_keys=True)
     print(f"distribution fixture: {len(doc['markets'])} market entries, home {doc['home_score']:.3f} away {doc['away_score']:.3f}")
 
 
 if __name__ == "__main__" and "--distribution" in sys.argv:
     make_distribution_fixture()
+if __name__ == "__main__" and "--distribution2" in sys.argv:
+    # second pin of N1: no calibration file in the working directory, a game id with a start-time suffix
+    make_distribution_fixture(seed=77, game_id="2025-06-17-ARI@TOR-T1907", with_calibration=False,
+                              out_name="distribution_ARITOR_nocal.json", matchup_seed=5150)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -7,9 +7,10 @@ TIMED and SAMPLED on the GPU box, where /root/reference does not exist.
 What it does: imports the reference read-only from /root/reference exactly as oracle/ref_harness.py does, lists the
 reference modules that import pulled in (core.game_simulator and everything it reaches: half_inning_simulator,
 pa_simulator, bip_resolution, fatigue_modeling, assets.bullpen_utils, ...), and compiles each of those files with
-`py_compile` to oracle/_ref/<package>/<module>.pyc.  No reference SOURCE is copied: oracle/_ref/ holds compiler output
-only, it is git-ignored (never enters history) and it is not gpurun-ignored (it travels to the GPU box like the
-other built artefacts).  oracle/ref_harness.py falls back to oracle/_ref/ when /root/reference is absent.
+`py_compile` to oracle/_ref/<package>/<module>.refbc (byte code in the .pyc format under another extension: snapshot
+tools drop *.pyc).  No reference SOURCE is copied: oracle/_ref/ holds compiler output only, it is git-ignored (never
+enters history) and it is not gpurun-ignored (it travels to the GPU box like the other built artefacts).
+oracle/ref_harness.py imports from oracle/_ref/ through a small finder when /root/reference is absent.
 """
 from __future__ import annotations
 
@@ -23,6 +24,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.environ.get("MLBSIM_REFERENCE_ROOT", "/root/reference")
 DST = os.path.join(HERE, "_ref")
+EXT = ".refbc"
 
 _LIST = r"""
 import json, os, sys
@@ -40,7 +42,7 @@ print(json.dumps(files))
 def build(verbose: bool = False) -> bool:
     """Returns True if oracle/_ref/ is usable afterwards (freshly built, or kept from an earlier build)."""
     if not os.path.isdir(os.path.join(SRC, "core")):
-        return os.path.isfile(os.path.join(DST, "core", "game_simulator.pyc"))
+        return os.path.isfile(os.path.join(DST, "core", "game_simulator" + EXT))
     env = dict(os.environ, PYTHONDONTWRITEBYTECODE="1")
     r = subprocess.run([sys.executable, "-c", _LIST % (HERE, SRC, SRC)], capture_output=True, text=True, env=env, cwd="/tmp")
     if r.returncode != 0:
@@ -51,7 +53,7 @@ def build(verbose: bool = False) -> bool:
     root = os.path.realpath(SRC)
     for f in files:
         rel = os.path.relpath(f, root)
-        out = os.path.join(tmp, rel + "c")                      # core/game_simulator.py -> core/game_simulator.pyc
+        out = os.path.join(tmp, os.path.splitext(rel)[0] + EXT)  # core/game_simulator.py -> core/game_simulator.refbc
         os.makedirs(os.path.dirname(out), exist_ok=True)
         py_compile.compile(f, cfile=out, dfile=os.path.join("<reference>", rel), doraise=True,
                            invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)

@@ -32,7 +32,37 @@ OUTCOMES = ["K", "BB", "1B", "2B", "3B", "HR", "OUT"]
 _mods = None
 
 
+_BYTECODE_EXT = ".refbc"
+
+
+class _BytecodeFinder:
+    """Imports the reference's modules from oracle/_ref/<package>/<module>.refbc (pyc-format byte code compiled from
+    the unmodified checkout by oracle/make_ref.py)."""
+
+    def __init__(self, root):
+        self.root = root
+
+    def find_spec(self, fullname, path=None, target=None):
+        import importlib.util
+
+        base = os.path.join(self.root, *fullname.split("."))
+        init = os.path.join(base, "__init__" + _BYTECODE_EXT)
+        if os.path.isfile(init):
+            loader = importlib.machinery.SourcelessFileLoader(fullname, init)
+            return importlib.util.spec_from_file_location(fullname, init, loader=loader, submodule_search_locations=[base])
+        if os.path.isfile(base + _BYTECODE_EXT):
+            loader = importlib.machinery.SourcelessFileLoader(fullname, base + _BYTECODE_EXT)
+            return importlib.util.spec_from_file_location(fullname, base + _BYTECODE_EXT, loader=loader)
+        if os.path.isdir(base) and any(f.endswith(_BYTECODE_EXT) for f in os.listdir(base)):   # namespace package (assets/)
+            spec = importlib.machinery.ModuleSpec(fullname, None, is_package=True)
+            spec.submodule_search_locations = [base]
+            return spec
+        return None
+
+
 def reference_available() -> bool:
+    if reference_kind() == "bytecode":
+        return os.path.isfile(os.path.join(REFERENCE_ROOT, "core", "game_simulator" + _BYTECODE_EXT))
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "core"))
 
 
@@ -55,7 +85,10 @@ def load_reference():
         m.__spec__ = importlib.machinery.ModuleSpec("pytz", None)
         sys.modules["pytz"] = m
     sys.dont_write_bytecode = True
-    if REFERENCE_ROOT not in sys.path:
+    if reference_kind() == "bytecode":
+        if not any(isinstance(f, _BytecodeFinder) for f in sys.meta_path):
+            sys.meta_path.insert(0, _BytecodeFinder(REFERENCE_ROOT))
+    elif REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)
     import core.game_simulator as gs
     import core.pa_simulator as pa

@@ -11,13 +11,16 @@ import oracle as orc
 from mlb_odds_engine_b200 import _abi, distribution, synth, tables
 from mlb_odds_engine_b200.simulator import RunHistogram, result_dicts
 
-GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "distribution_TEXHOU.json")
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+# two pins of the same chain: the calibration file present / a plain id; no calibration file (factors 1.0, segments
+# unscaled: cli/run_distribution_simulator.py:351-354, 657-674) / an id with a -T1907 start-time suffix
+FIXTURES = ["distribution_TEXHOU.json", "distribution_ARITOR_nocal.json"]
 
 
-@pytest.fixture(scope="module")
-def case():
-    fx = json.load(open(GOLDEN))
-    matchup = synth.make_matchup(fx["game_id"])
+@pytest.fixture(scope="module", params=FIXTURES)
+def case(request):
+    fx = json.load(open(os.path.join(GOLDEN_DIR, request.param)))
+    matchup = synth.make_matchup(fx["game_id"]) if fx.get("matchup_seed") is None else synth.make_matchup(fx["game_id"], seed=fx["matchup_seed"])
     table = tables.build_table(matchup)
     hist = orc.native(table, 0, 0, fx["n_sims"], fx["seed"])
     games = orc.native_persim(table, 0, 0, fx["n_sims"], fx["seed"])
@@ -103,6 +106,21 @@ def test_weighted_matches_numpy_on_expanded_lists():
     assert distribution.to_american_odds(0.5) == 100.0 and distribution.to_american_odds(0.6) == -150.0
     assert distribution.to_american_odds(0.25) == 300.0 and distribution.to_american_odds(1.0) == -float("inf")
     assert distribution.adjust_for_push(0.45, 0.45) == (0.5, 0.5)
+
+
+def test_start_time_and_table_snapshot_follow_the_reference(tmp_path, case):
+    """N2: `start_time_iso` derived from the game id when no odds-file entry exists (run_distribution_simulator.py:243-250,
+    core/utils.py:1009-1027) and the backtest/last_table_snapshot.json side file (:853-859), both byte-for-byte what the
+    unmodified reference wrote for the same games."""
+    fx, matchup, hist, _ = case
+    doc = distribution.price_from_histogram(hist, fx["game_id"], fx["calibration"])
+    assert doc["start_time_iso"] == fx["doc"]["start_time_iso"] and doc["start_time_iso"] is not None
+    if "-T1907" in fx["game_id"]:
+        assert doc["start_time_iso"].startswith("2025-06-17T19:07:00")
+    snap = tmp_path / "backtest" / "last_table_snapshot.json"
+    distribution.write_table_snapshot(doc, str(snap))
+    assert json.load(open(snap)) == fx["table_snapshot"]
+    assert distribution.start_time_iso_from_game_id("not-a-game-id") is None
 
 
 def test_sim_json_roundtrip(tmp_path, case):
