@@ -32,36 +32,32 @@ _W = (("barrel", 0.020), ("nev", 0.018), ("nla", 0.018), ("xSLG", 0.010), ("xwOB
       ("one_minus_bb", 0.005), ("norm_stuff", 0.004), ("location", 0.010), ("norm_fip", 0.005))
 
 
-def dynamic_shrink_n(tbf) -> float:
-    """core/project_hr_pa.py:7-15."""
-    try:
-        tbf = float(tbf)
-    except (TypeError, ValueError):
-        return DEFAULT_SHRINK_BASE
-    if tbf <= 0:
-        return DEFAULT_SHRINK_BASE * (REFERENCE_TBF / 1)
-    return DEFAULT_SHRINK_BASE * (REFERENCE_TBF / tbf)
+# League prior of HR/PA by role: (base, ((Stuff+ bound, is the bound a floor?, multiplier), ... first match wins)).
+# core/project_hr_pa.py:17-37.  One table drives both the scalar and the batched projection.
+_LEAGUE_PRIOR = {
+    "RP": (0.020, ((120, True, 0.85), (110, True, 0.90), (95, False, 1.10))),
+    "SP": (0.030, ((110, True, 0.90), (100, True, 0.95), (90, False, 1.10))),
+}
 
 
 def infer_league_avg_hr_pa(role: str = "SP", stuff_plus: float = 100.0) -> float:
-    """core/project_hr_pa.py:17-37: league prior by role, nudged by Stuff+ band."""
-    if role.upper() == "RP":
-        base = 0.020
-        if stuff_plus >= 120:
-            return base * 0.85
-        if stuff_plus >= 110:
-            return base * 0.90
-        if stuff_plus <= 95:
-            return base * 1.10
-        return base
-    base = 0.030
-    if stuff_plus >= 110:
-        return base * 0.90
-    if stuff_plus >= 100:
-        return base * 0.95
-    if stuff_plus <= 90:
-        return base * 1.10
+    """League-average HR/PA for the pitcher's role, nudged by his Stuff+ band (core/project_hr_pa.py:17-37)."""
+    base, bands = _LEAGUE_PRIOR["RP" if role.upper() == "RP" else "SP"]
+    for bound, is_floor, mult in bands:
+        if (stuff_plus >= bound) if is_floor else (stuff_plus <= bound):
+            return base * mult
     return base
+
+
+def dynamic_shrink_n(tbf) -> float:
+    """Pseudo-count of the shrinkage towards the league prior: 300 batters faced at the reference workload of 650,
+    inversely proportional to the pitcher's own TBF; a TBF that is not a number keeps the base, a non-positive one
+    counts as a single batter (core/project_hr_pa.py:7-15)."""
+    try:
+        faced = float(tbf)
+    except (TypeError, ValueError):
+        return DEFAULT_SHRINK_BASE
+    return DEFAULT_SHRINK_BASE * (REFERENCE_TBF / (faced if faced > 0 else 1))
 
 
 def _float_or(value, fallback: float) -> float:
@@ -164,10 +160,9 @@ def project_hr_pa_batch(role: str = "SP", **columns) -> np.ndarray:
 
     if "league_avg_hr_pa" in columns:
         league = np.broadcast_to(np.asarray(columns["league_avg_hr_pa"], dtype=np.float64), shape)
-    elif role.upper() == "RP":
-        league = np.select([stuff >= 120, stuff >= 110, stuff <= 95], [0.020 * 0.85, 0.020 * 0.90, 0.020 * 1.10], 0.020)
     else:
-        league = np.select([stuff >= 110, stuff >= 100, stuff <= 90], [0.030 * 0.90, 0.030 * 0.95, 0.030 * 1.10], 0.030)
+        base, bands = _LEAGUE_PRIOR["RP" if role.upper() == "RP" else "SP"]
+        league = np.select([(stuff >= b) if floor else (stuff <= b) for b, floor, _ in bands], [base * m for _, _, m in bands], base)
 
     terms = {
         "barrel": c["barrel_batted_rate"], "nev": (c["exit_velocity_avg"] - 85) / 1000,
@@ -199,6 +194,11 @@ def _safe_float(val, fallback=0.0) -> float:
         return fallback
 
 
+_RELIEVER_FIELDS = (("k_rate", 0.22), ("bb_rate", 0.08), ("hr_fb_rate", 0.10), ("stuff_plus", 100), ("command_plus", 100),
+                    ("location_plus", 100), ("barrel_batted_rate", 0.06), ("exit_velocity_avg", 88.0),
+                    ("launch_angle_avg", 13.0), ("HR", 0), ("TBF", 1))
+
+
 def reliever_from_stats(name: str, stats: dict) -> dict | None:
     """One bullpen entry from a pitcher-stats row (assets/bullpen_utils.py:62-98).  Returns None where the
     reference skips the pitcher (no row, missing / NaN Stuff+ or HR/FB)."""
@@ -212,22 +212,12 @@ def reliever_from_stats(name: str, stats: dict) -> dict | None:
         return None
     if hr_fb is None or (isinstance(hr_fb, float) and math.isnan(hr_fb)):
         return None
-    r = {
-        "name": name,
-        "throws": stats.get("throws", "R"),
-        "k_rate": _safe_float(stats.get("k_rate"), 0.22),
-        "bb_rate": _safe_float(stats.get("bb_rate"), 0.08),
-        "hr_fb_rate": _safe_float(hr_fb, 0.10),
-        "stuff_plus": _safe_float(stuff, 100),
-        "command_plus": _safe_float(stats.get("command_plus"), 100),
-        "location_plus": _safe_float(stats.get("location_plus"), 100),
-        "barrel_batted_rate": _safe_float(stats.get("barrel_batted_rate"), 0.06),
-        "exit_velocity_avg": _safe_float(stats.get("exit_velocity_avg"), 88.0),
-        "launch_angle_avg": _safe_float(stats.get("launch_angle_avg"), 13.0),
-        "HR": _safe_float(stats.get("HR"), 0),
-        "TBF": max(_safe_float(stats.get("TBF"), 1), 1),
-        "role": "RP",
-    }
+    # fields copied from the stats row with the reference's fallbacks, in its key order (assets/bullpen_utils.py:77-92)
+    r = {"name": name, "throws": stats.get("throws", "R")}
+    for key, fallback in _RELIEVER_FIELDS:
+        r[key] = _safe_float({"hr_fb_rate": hr_fb, "stuff_plus": stuff}.get(key, stats.get(key)), fallback)
+    r["TBF"] = max(r["TBF"], 1)
+    r["role"] = "RP"
     r["hr_pa"] = project_hr_pa(r)
     r["score"] = r["stuff_plus"] + r["k_rate"] * 100 - r["bb_rate"] * 100
     return r

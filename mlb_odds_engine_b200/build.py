@@ -3,7 +3,7 @@
     python -m mlb_odds_engine_b200.build [--force]
 
 The replay kernel is compiled with -fmad=false (bit-exact float64 compares, see
-csrc/replay_kernel.cu); everything carries -lineinfo so ncu's source page maps to the .cu files.
+csrc/replay_flat_kernel.cu); everything carries -lineinfo so ncu's source page maps to the .cu files.
 """
 from __future__ import annotations
 
@@ -23,7 +23,6 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", INCLUDE
 COMMON += os.environ.get("MLBSIM_NVCC_DEFS", "").split()   # e.g. "-DOPT_ANYSYNC=1" (tuning sweeps)
 UNITS = {
     "native_kernel.cu": [],
-    "replay_kernel.cu": ["-fmad=false"],
     "replay_flat_kernel.cu": ["-fmad=false"],
     "summary_kernel.cu": [],
     "mlbsim_api.cu": [],

@@ -42,7 +42,6 @@ struct mlbsim_ctx {
   uint64_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
-  bool replay_simple = false;  // MLBSIM_REPLAY_KERNEL=simple selects the nested-loop replay kernel
   std::string err;
 };
 
@@ -107,10 +106,6 @@ int mlbsim_init(int device, mlbsim_ctx** out) {
   }
   if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
   ctx->stream = ctx->own_stream;
-  {
-    const char* rk = std::getenv("MLBSIM_REPLAY_KERNEL");
-    ctx->replay_simple = rk && std::strcmp(rk, "simple") == 0;
-  }
   if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return bail("cudaEventCreate", e);
   if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail("cudaEventCreate", e);
   if ((e = cudaMalloc(&ctx->params_dev, sizeof(mlbsim_params))) != cudaSuccess) return bail("cudaMalloc", e);
@@ -422,14 +417,7 @@ int mlbsim_run_replay_dev(mlbsim_ctx* ctx, const mlbsim_params* params_host, con
   }
   CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
   CK(ctx, cudaMemsetAsync(out_dev, 0, sizeof(mlbsim_replay_game) * (size_t)n_games, ctx->stream));  // kernels write non-zero fields only
-  if (ctx->replay_simple) {
-    // nested-loop version (one thread walks one game start to finish); kept for A/B measurements
-    const int threads = 128;
-    long long blocks = (n_games + threads - 1) / threads;
-    const long long cap = (long long)ctx->prop.multiProcessorCount * 16;
-    if (blocks > cap) blocks = cap;
-    mlbsim_replay_kernel<<<(int)blocks, threads, 0, ctx->stream>>>(a);
-  } else {
+  {
     const int threads = MLBSIM_REPLAY_FLAT_THREADS;
     const int grid = ctx->prop.multiProcessorCount * MLBSIM_REPLAY_FLAT_BLOCKS;
     const long long warps = (long long)grid * (threads / 32);

@@ -272,7 +272,7 @@ __device__ __forceinline__ uint32_t wrap_fix(uint32_t cur, uint32_t hs) {
 }
 
 // WRAP_STEP: put the lineup slot back after every plate appearance instead of once per round (needed when a lineup is
-// shorter than four batters, and on the fatigue path, whose threshold rows are addressed by the true (tier, slot)).
+// too short for the repeated rows: more than one wrap could fall into one round).
 template <bool FATIGUE, bool COUNT_PA, bool WRAP_STEP>
 __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned long long* const H,
                                              unsigned long long* const counter, const uint32_t rng_matchup, const uint32_t L0,
@@ -393,18 +393,27 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
       const uint32_t e = lds32(A_ALIAS + row + (col << 2));
       uint32_t o = ((w0 << 3) < e) ? col : (e & 7u);   // draw variant 0..7 (7 = single, runner on first advances)
       if (FATIGUE) {
-        const uint32_t T = (cur >> CX_T_SHIFT) & 31u;  // pit*4 + tier
-        if (T < 4u && (cur & CX_PC_BITS) >= ((uint32_t)(FATIGUE_START + 1) << CX_PC_SHIFT)) {  // starter past 75 pitches
-          const uint32_t side = (cur >> CX_SIDE_SHIFT) & 1u;
-          const uint32_t slot = ((cur & CX_SLOT) >> CX_SLOT_SHIFT) - (cur >> CX_BIAS_SHIFT);
-          const uint32_t ex = ((cur & CX_PC_BITS) >> CX_PC_SHIFT) - FATIGUE_START;
-          const uint32_t srow = (((side * MLBSIM_N_TIERS + T) * MLBSIM_MAX_LINEUP + slot) * MLBSIM_ROW_WORDS) << 2;
-          const uint32_t u = w0 >> 1;
-          o = 0;
+        if ((cur & CX_PC_BITS) >= ((uint32_t)(FATIGUE_START + 1) << CX_PC_SHIFT)) {   // past 75 pitches (rare)
+          uint32_t T = (cur >> CX_T_SHIFT) & 31u;  // pit*4 + tier
+          const uint32_t slotp = (cur & CX_SLOT) >> CX_SLOT_SHIFT, bias = cur >> CX_BIAS_SHIFT;
+          uint32_t slot = slotp - bias;
+          if (!WRAP_STEP && slotp < bias) {
+            // after a lineup wrap inside this round (repeated rows): the batter is number slot', and a carry that left
+            // tier bits 0 came out of a saturated tier — it is still (pit - 1, tier 4+)
+            slot = slotp;
+            if ((T & 3u) == 0u) T -= 1u;
+          }
+          if (T < 4u) {  // the starter
+            const uint32_t side = (cur >> CX_SIDE_SHIFT) & 1u;
+            const uint32_t ex = ((cur & CX_PC_BITS) >> CX_PC_SHIFT) - FATIGUE_START;
+            const uint32_t srow = (((side * MLBSIM_N_TIERS + T) * MLBSIM_MAX_LINEUP + slot) * MLBSIM_ROW_WORDS) << 2;
+            const uint32_t u = w0 >> 1;
+            o = 0;
 #pragma unroll
-          for (int j = 0; j < 6; ++j) o += (u >= lds32(A_FTHR + srow + 4 * j) + ex * lds32(A_FSLOPE + srow + 4 * j)) ? 1u : 0u;
-          // thresholds know seven outcomes: the single's 0.8 draw comes from the low half of w1 here
-          if (o == (uint32_t)MLBSIM_1B && (w1 & 0xFFFFu) < T_080_16) o = MLBSIM_V_1B_ADV;
+            for (int j = 0; j < 6; ++j) o += (u >= lds32(A_FTHR + srow + 4 * j) + ex * lds32(A_FSLOPE + srow + 4 * j)) ? 1u : 0u;
+            // thresholds know seven outcomes: the single's 0.8 draw comes from the low half of w1 here
+            if (o == (uint32_t)MLBSIM_1B && (w1 & 0xFFFFu) < T_080_16) o = MLBSIM_V_1B_ADV;
+          }
         }
       }
 
@@ -635,12 +644,17 @@ mlbsim_native_kernel(const NativeArgs args) {
     unsigned long long* const counter = args.counters + m;
 
     const bool short_lineup = !OPT_WRAP_ROUND || (L0 < L1 ? L0 : L1) <= (uint32_t)WRAP_DUP_ROWS;   // more than one wrap per round possible
-    if (fatigue) {
-      if (count_pa) play_matchup<true, true, true>(args, H, counter, rng_matchup, L0, L1, nb0, nb1);
-      else play_matchup<true, false, true>(args, H, counter, rng_matchup, L0, L1, nb0, nb1);
-    } else if (short_lineup) {
-      if (count_pa) play_matchup<false, true, true>(args, H, counter, rng_matchup, L0, L1, nb0, nb1);
-      else play_matchup<false, false, true>(args, H, counter, rng_matchup, L0, L1, nb0, nb1);
+    if (short_lineup) {   // (rare: tests and the reference's 3-batter demo)
+      if (fatigue) {
+        if (count_pa) play_matchup<true, true, true>(args, H, counter, rng_matchup, L0, L1, nb0, nb1);
+        else play_matchup<true, false, true>(args, H, counter, rng_matchup, L0, L1, nb0, nb1);
+      } else {
+        if (count_pa) play_matchup<false, true, true>(args, H, counter, rng_matchup, L0, L1, nb0, nb1);
+        else play_matchup<false, false, true>(args, H, counter, rng_matchup, L0, L1, nb0, nb1);
+      }
+    } else if (fatigue) {
+      if (count_pa) play_matchup<true, true, false>(args, H, counter, rng_matchup, L0, L1, nb0, nb1);
+      else play_matchup<true, false, false>(args, H, counter, rng_matchup, L0, L1, nb0, nb1);
     } else {
       if (count_pa) play_matchup<false, true, false>(args, H, counter, rng_matchup, L0, L1, nb0, nb1);
       else play_matchup<false, false, false>(args, H, counter, rng_matchup, L0, L1, nb0, nb1);

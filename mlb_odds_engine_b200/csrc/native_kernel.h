@@ -55,7 +55,6 @@ struct PersimArgs {
 extern "C" __global__ void mlbsim_persim_kernel(const PersimArgs args);
 extern "C" __global__ void mlbsim_native_kernel(const NativeArgs args);
 extern "C" __global__ void mlbsim_stage_tables_kernel(const mlbsim_table* tables, mlbsim_staged_table* staged, int n);
-extern "C" __global__ void mlbsim_replay_kernel(const ReplayArgs args);
 extern "C" __global__ void mlbsim_replay_flat_kernel(const ReplayArgs args, unsigned long long* counter, uint32_t chunk);
 extern "C" __global__ void mlbsim_summary_kernel(const mlbsim_hist* hist, mlbsim_summary* out);
 #endif

@@ -1,7 +1,7 @@
 // replay_flat_kernel.cu — tape-replay mode, flat-loop version (the default replay kernel).
 //
-// Same contract as replay_kernel.cu (bit-exact integers on the reference's recorded draws,
-// float64 compares, no FMA contraction) but organised like the native kernel: the warp runs in
+// Contract: bit-exact integers on the reference's recorded draws (the fields of core/game_simulator.py:134-144),
+// float64 compares, no FMA contraction.  Organised like the native kernel: the warp runs in
 // rounds of REPLAY_UNROLL plate-appearance steps followed by one boundary pass, lanes refill by
 // ballot prefix, and inside a PA step every tape read is a PREDICATED load at the lane's own
 // position (`if the reference would draw here: v = tape[pos++]`) instead of a branch — the

@@ -59,31 +59,30 @@ def contact_cdfs():
     return cdf_bip, cdf_hit, cdf_fb
 
 
+# resolve_bip's modifiers as data: (below, factor if below, above, factor if above); inside the band the factor is 1.0
+_SPEED_BAND = (40, 0.97, 65, 1.025)        # core/bip_resolution.py:23-26  batter speed
+_RANGE_BAND = (40, 1.03, 60, 0.97)         # :29-32  fielder rating (50 = neutral)
+_EV_BAND = (85, 0.97, 95, 1.03)            # :40-43  exit velocity, default 88
+_LA_BAND = (6.0, 0.96, 10.0, 1.03)         # :45-48  launch angle, default 12
+_CONTACT_CAP = 1.06                        # :51
+_BABIP_LIMITS = (0.05, 0.55)               # :57
+
+
+def _band_factor(x, band):
+    """1.0 inside [below, above], else the band's factor.  Comparing a non-number raises TypeError exactly where the
+    reference does (the "N/A" strings of un-enriched starters, core/bip_resolution.py:40)."""
+    below, f_below, above, f_above = band
+    return f_above if x > above else f_below if x < below else 1.0
+
+
 def bip_hit_probability(bip_type, ev, la, batter_speed, fielder_rating):
-    """P(hit | ball in play of `bip_type`) — core/bip_resolution.py:20-57, same multiply order."""
-    prob = BASE_BABIP[bip_type]
-    if batter_speed > 65:
-        prob *= 1.025
-    elif batter_speed < 40:
-        prob *= 0.97
-    if fielder_rating > 60:
-        prob *= 0.97
-    elif fielder_rating < 40:
-        prob *= 1.03
-    hard_hit = ev if ev is not None else 88
-    barrels = la if la is not None else 12
-    mult = 1.0
-    if hard_hit < 85:
-        mult *= 0.97
-    elif hard_hit > 95:
-        mult *= 1.03
-    if barrels < 6.0:
-        mult *= 0.96
-    elif barrels > 10.0:
-        mult *= 1.03
-    mult = min(mult, 1.06)
-    prob *= mult
-    return max(min(prob, 0.55), 0.05)
+    """P(hit | ball in play of `bip_type`), core/bip_resolution.py:20-57.  Floating-point products are taken in the
+    reference's order — ((base x speed) x range) x min(ev x la, 1.06) — so replay mode compares the same doubles;
+    a factor of 1.0 is exact, which is what lets the bands be data."""
+    prob = BASE_BABIP[bip_type] * _band_factor(batter_speed, _SPEED_BAND) * _band_factor(fielder_rating, _RANGE_BAND)
+    contact = _band_factor(88 if ev is None else ev, _EV_BAND) * _band_factor(12 if la is None else la, _LA_BAND)
+    prob *= min(contact, _CONTACT_CAP)
+    return max(min(prob, _BABIP_LIMITS[1]), _BABIP_LIMITS[0])
 
 
 class Matchup:
@@ -472,9 +471,9 @@ def _table_rows(m: Matchup):
 
 
 def _fatigue_rows(m: Matchup, S, P):
-    """Rows that need pitch-count slopes: a starter without a bullpen is never replaced, so his pitch count passes
-    75 (core/fatigue_modeling.py:38)."""
-    return np.nonzero((P == 0) & (np.asarray(m.bullpen_len)[S] == 0))[0]
+    """Rows that need pitch-count slopes: both starters of a matchup in which some staff has no bullpen (see
+    `tables_from_arrays`)."""
+    return np.nonzero((P == 0) & (min(m.bullpen_len) == 0))[0]
 
 
 def _warm_clip_cache(ms) -> None:
@@ -589,8 +588,13 @@ def tables_from_arrays(A: dict, validate: bool = True) -> np.ndarray:
             raise MatchupCannotScore(f"matchup(s) {np.nonzero(~can_reach)[0][:8].tolist()}: no plate appearance of either side "
                                      "can put a runner on base, the game would never end")
     alias[where] = alias_rows(outcome_variants(probs))
-    # a starter without a bullpen is never replaced: his pitch count passes 75 (core/fatigue_modeling.py:38)
-    fat = valid & (pit == 0) & (A["bullpen_len"][:, :, None, None, None] == 0)
+    # A starter without a bullpen is never replaced: his pitch count passes 75 (core/fatigue_modeling.py:38).  Such a
+    # matchup is flagged and BOTH of its starters get pitch-count rows: one who has a bullpen normally leaves at his third
+    # time through the order, long before 75 pitches, but lineup wraps that coincide with the end of a half do not
+    # count (half_inning_simulator.py:177-178), so once in ~10^4 games he gets there too.  (With bullpens on both sides
+    # the flag stays off and that rare starter keeps his 75-pitch law for the few PAs until the hook at 90.)
+    flagged = (A["bullpen_len"] == 0).any(axis=1)
+    fat = valid & (pit == 0) & flagged[:, None, None, None, None]
     if fat.any():
         c1, (M, S, P, T, B) = _cdf_tensor(A, fat, max(0.0, SLOPE_SPAN / 25))
         c0f, _ = _cdf_tensor(A, fat, 0.0)
