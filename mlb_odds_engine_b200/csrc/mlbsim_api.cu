@@ -426,7 +426,8 @@ int mlbsim_run_replay_dev(mlbsim_ctx* ctx, const mlbsim_params* params_host, con
     if (chunk < 32) chunk = 32;
     if (chunk > 256) chunk = 256;
     CK(ctx, cudaMemsetAsync(ctx->counters_dev, 0, sizeof(unsigned long long), ctx->stream));
-    mlbsim_replay_flat_kernel<<<grid, threads, 0, ctx->stream>>>(a, ctx->counters_dev, (uint32_t)chunk);
+    if (params_host->use_noise) mlbsim_replay_flat_kernel<<<grid, threads, 0, ctx->stream>>>(a, ctx->counters_dev, (uint32_t)chunk);
+    else mlbsim_replay_flat_nonoise_kernel<<<grid, threads, 0, ctx->stream>>>(a, ctx->counters_dev, (uint32_t)chunk);
   }
   CK(ctx, cudaGetLastError());
   CK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));

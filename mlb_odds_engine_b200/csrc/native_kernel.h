@@ -56,6 +56,7 @@ extern "C" __global__ void mlbsim_persim_kernel(const PersimArgs args);
 extern "C" __global__ void mlbsim_native_kernel(const NativeArgs args);
 extern "C" __global__ void mlbsim_stage_tables_kernel(const mlbsim_table* tables, mlbsim_staged_table* staged, int n);
 extern "C" __global__ void mlbsim_replay_flat_kernel(const ReplayArgs args, unsigned long long* counter, uint32_t chunk);
+extern "C" __global__ void mlbsim_replay_flat_nonoise_kernel(const ReplayArgs args, unsigned long long* counter, uint32_t chunk);
 extern "C" __global__ void mlbsim_summary_kernel(const mlbsim_hist* hist, mlbsim_summary* out);
 #endif
 size_t mlbsim_native_smem_bytes(int threads_per_block);

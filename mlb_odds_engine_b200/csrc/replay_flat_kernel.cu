@@ -1,14 +1,20 @@
-// replay_flat_kernel.cu — tape-replay mode, flat-loop version (the default replay kernel).
+// replay_flat_kernel.cu — tape-replay mode (bit-exact verification against the reference's recorded draws).
 //
 // Contract: bit-exact integers on the reference's recorded draws (the fields of core/game_simulator.py:134-144),
-// float64 compares, no FMA contraction.  Organised like the native kernel: the warp runs in
-// rounds of REPLAY_UNROLL plate-appearance steps followed by one boundary pass, lanes refill by
-// ballot prefix, and inside a PA step every tape read is a PREDICATED load at the lane's own
-// position (`if the reference would draw here: v = tape[pos++]`) instead of a branch — the
-// draw grammar of SURVEY.md §8(c) becomes straight-line code:
+// float64 compares, no FMA contraction.  Organised like the native kernel: the warp runs in rounds of REPLAY_UNROLL
+// plate-appearance steps followed by one boundary pass, lanes refill by ballot prefix.
+//
+// The tape is the only HBM traffic (~535 float64 per game).  The reference's draw grammar
 //     [beta_k] [beta_bb] u u_hr [u_bip u_hit (u_hit3 | u_fb [u_fb2])] [h1] [h2] [h3]
-// so lanes that take different paths through core/pa_simulator.py:91-143 and the handlers of
-// core/half_inning_simulator.py:73-136 still execute together.
+// makes WHICH value a draw is depend on the values before it, but not WHERE the next few values are: a plate
+// appearance consumes at most eleven consecutive tape entries.  So every step first issues eleven INDEPENDENT 8-byte
+// loads of the window tape[pos .. pos+10] (one memory round trip per plate appearance, not one per draw), and the
+// grammar then only selects among registers: with both Beta draws present (every realistic rate) u, u_hr, u_bip ...
+// sit at fixed window slots, and the three base-running draws at one of three.  Degenerate rates (k or bb outside
+// (0, 1): no Beta draw, core/pa_simulator.py:23-32) fall back to draw-by-draw predicated loads.  The per-PA K / BB
+// rates of every (side, pitcher, TTO tier, batter) up to 75 pitches are tabulated in shared memory at block start with
+// the reference's operation order (core/fatigue_modeling.py:25-43, core/pa_simulator.py:108-114), so the hot step does
+// two 16-byte shared loads instead of ten float64 operations and two divisions.
 #include <cuda_runtime.h>
 #include <stddef.h>
 #include <stdint.h>
@@ -43,15 +49,42 @@ constexpr uint32_t HS_OVER = (1u << 30) | (1u << 14);
 constexpr uint32_t HS_REACHED = 0x3Fu << 24;
 constexpr uint32_t HS_DEAD = 1u << 15;
 
+constexpr int KB_ENTRIES = 2 * MLBSIM_MAX_PITCHERS * MLBSIM_N_TIERS * MLBSIM_MAX_LINEUP;   // 504
+
 struct FlatSmem {
   mlbsim_params P;
   uint32_t lut[LUT_WORDS];
+  double2 kb[KB_ENTRIES];   // {k, bb} before noise at pitch_count <= 75: [side][pit][tier][slot]
 };
+
+// effective K / BB rates of one plate appearance before noise: fatigue-adjusted pitcher rate averaged with the batter's,
+// times the umpire modifiers — core/fatigue_modeling.py:25-43 (two separate multiplies per rate, in this order), then
+// core/pa_simulator.py:108-114
+__device__ __forceinline__ double2 effective_rates(const mlbsim_params& P, uint32_t side, uint32_t pit, uint32_t tier, uint32_t slot, int pc) {
+  const double pen = tier == 0 ? 0.0 : tier == 1 ? 0.015 : tier == 2 ? 0.035 : 0.060;
+  double ak = __dmul_rn(P.pit_k[side][pit], __dsub_rn(1.0, pen));
+  double ab = __dmul_rn(P.pit_bb[side][pit], __dadd_rn(1.0, pen));
+  double fl = __ddiv_rn((double)(pc - 75), 25.0);
+  if (!(fl > 0.0)) fl = 0.0;
+  ak = __dmul_rn(ak, __dsub_rn(1.0, __dmul_rn(0.02, fl)));
+  ab = __dmul_rn(ab, __dadd_rn(1.0, __dmul_rn(0.03, fl)));
+  double2 r;
+  r.x = __dmul_rn(__ddiv_rn(__dadd_rn(P.bat_k[side][slot], ak), 2.0), P.k_mod);
+  r.y = __dmul_rn(__ddiv_rn(__dadd_rn(P.bat_bb[side][slot], ab), 2.0), P.bb_mod);
+  return r;
+}
 
 __device__ __forceinline__ uint32_t lanemask_lt() {
   uint32_t m;
   asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
   return m;
+}
+
+// window read: entry pos + i of the lane's tape, 0.5 past the end (flagged later through pos > len)
+__device__ __forceinline__ double peek(const double* p, uint32_t at, uint32_t len) {
+  double v = 0.5;
+  if (at < len) asm volatile("ld.global.nc.L2::256B.f64 %0, [%1];" : "=d"(v) : "l"(p + at));
+  return v;
 }
 
 // predicated tape read: past-the-end reads yield 0.5 (flagged later through pos > len)
@@ -64,10 +97,8 @@ __device__ __forceinline__ double take(const double* p, uint32_t& pos, uint32_t 
   return v;
 }
 
-}  // namespace
-
-extern "C" __global__ void __launch_bounds__(REPLAY_FLAT_THREADS, REPLAY_FLAT_BLOCKS)
-mlbsim_replay_flat_kernel(const ReplayArgs args, unsigned long long* counter, uint32_t chunk) {
+template <bool NOISE>
+__device__ __forceinline__ void replay_body(const ReplayArgs& args, unsigned long long* counter, uint32_t chunk) {
   __shared__ FlatSmem S;
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(args.params);
@@ -79,10 +110,15 @@ mlbsim_replay_flat_kernel(const ReplayArgs args, unsigned long long* counter, ui
     }
   }
   __syncthreads();
+  for (int i = threadIdx.x; i < KB_ENTRIES; i += blockDim.x) {
+    const uint32_t slot = (uint32_t)i % MLBSIM_MAX_LINEUP, g = (uint32_t)i / MLBSIM_MAX_LINEUP;
+    S.kb[i] = effective_rates(S.P, g / (MLBSIM_MAX_PITCHERS * MLBSIM_N_TIERS), (g / MLBSIM_N_TIERS) % MLBSIM_MAX_PITCHERS, g % MLBSIM_N_TIERS, slot, 0);
+  }
+  __syncthreads();
   const mlbsim_params& P = S.P;
   const int lane = threadIdx.x & 31;
   const uint32_t n_games = (uint32_t)args.n_games;
-  const bool noise = P.use_noise != 0;
+  constexpr bool noise = NOISE;
   const uint32_t L0 = (uint32_t)P.lineup_len[0], L1 = (uint32_t)P.lineup_len[1];
   const uint32_t nb0 = (uint32_t)P.bullpen_len[0], nb1 = (uint32_t)P.bullpen_len[1];
 
@@ -135,59 +171,94 @@ mlbsim_replay_flat_kernel(const ReplayArgs args, unsigned long long* counter, ui
       const uint32_t tier = (cur >> 4) & 3u;
       const uint32_t pit = (cur >> CX_PIT_SHIFT) & 7u;
       const int pc = (int)(cur >> CX_PC_SHIFT);
-      // core/fatigue_modeling.py:25-43 — two separate multiplies per rate, in this order
-      const double pen = tier == 0 ? 0.0 : tier == 1 ? 0.015 : tier == 2 ? 0.035 : 0.060;
-      double ak = __dmul_rn(P.pit_k[side][pit], __dsub_rn(1.0, pen));
-      double ab = __dmul_rn(P.pit_bb[side][pit], __dadd_rn(1.0, pen));
-      double fl = __ddiv_rn((double)(pc - 75), 25.0);
-      if (!(fl > 0.0)) fl = 0.0;
-      ak = __dmul_rn(ak, __dsub_rn(1.0, __dmul_rn(0.02, fl)));
-      ab = __dmul_rn(ab, __dadd_rn(1.0, __dmul_rn(0.03, fl)));
-      double k = __dmul_rn(__ddiv_rn(__dadd_rn(P.bat_k[side][slot], ak), 2.0), P.k_mod);
-      double bb = __dmul_rn(__ddiv_rn(__dadd_rn(P.bat_bb[side][slot], ab), 2.0), P.bb_mod);
-      // beta_noise (:23-32): a draw only when 0 < p < 1
-      const double vk = take(tp, pos, len, noise && k > 0.0 && k < 1.0);
-      const double vb = take(tp, pos, len, noise && bb > 0.0 && bb < 1.0);
-      const double kp = noise ? (k <= 0.0 ? 0.0 : k >= 1.0 ? 1.0 : vk) : k;
-      double bp = noise ? (bb <= 0.0 ? 0.0 : bb >= 1.0 ? 1.0 : vb) : bb;
-      bp = __dmul_rn(bp, 1.01);
-      const double u = take(tp, pos, len, true);
-      const double uhr = take(tp, pos, len, true);                     // always consumed (:126)
-      const bool is_k = u < kp;
-      const bool is_bb = !is_k && (u < __dadd_rn(kp, bp));
-      const bool contact = !is_k && !is_bb;
-      const bool is_hr = contact && (uhr < P.pit_hr[side][pit]);
-      const bool bip = contact && !is_hr;
-      // resolve_contact (:51-88)
-      const double ubip = take(tp, pos, len, bip);
-      uint32_t type = (uint32_t)(P.cdf_bip[0] <= ubip) + (uint32_t)(P.cdf_bip[1] <= ubip) + (uint32_t)(P.cdf_bip[2] <= ubip) +
-                      (uint32_t)(P.cdf_bip[3] <= ubip);
-      if (type > 3u) type = 3u;
-      const double uhit = take(tp, pos, len, bip);                     // stdlib stream (core/bip_resolution.py:62)
-      const bool hit = bip && (uhit < P.hit_prob[side][pit][slot][type]);
-      const double u7 = take(tp, pos, len, bip);                       // hit: 1B/2B/3B split; else the 10 % fallback draw
-      const bool fb = bip && !hit && (u7 < 0.10);
-      const double u8 = take(tp, pos, len, fb);
-      uint32_t o = MLBSIM_OUT;
-      if (hit) o = MLBSIM_1B + (uint32_t)(P.cdf_hit[0] <= u7) + (uint32_t)(P.cdf_hit[1] <= u7) + (uint32_t)(P.cdf_hit[2] <= u7);
-      if (fb) o = MLBSIM_1B + (uint32_t)(P.cdf_fb[0] <= u8) + (uint32_t)(P.cdf_fb[1] <= u8);
-      if (is_hr) o = MLBSIM_HR;
-      if (is_bb) o = MLBSIM_BB;
-      if (is_k) o = MLBSIM_K;
-
-      // ---------------- handler draws (core/half_inning_simulator.py:73-136, :28-39) ----------------
+      const double2 rates = pc <= 75 ? S.kb[((side * MLBSIM_MAX_PITCHERS + pit) * MLBSIM_N_TIERS + tier) * MLBSIM_MAX_LINEUP + slot]
+                                     : effective_rates(P, side, pit, tier, slot, pc);
+      const double k = rates.x, bb = rates.y;
+      // beta_noise (core/pa_simulator.py:23-32): a draw only when 0 < p < 1
+      const bool has_k = noise && k > 0.0 && k < 1.0, has_b = noise && bb > 0.0 && bb < 1.0;
       const uint32_t ob = hs & HS_OB;
       const uint32_t outs = ob >> 3;
       const bool on1 = (ob & 1u) != 0, on2 = (ob & 2u) != 0;
-      const bool is_out = (o == MLBSIM_K) || (o == MLBSIM_OUT);
-      const bool is_1b = o == MLBSIM_1B, is_2b = o == MLBSIM_2B;
-      // h1: double-play draw | runner on 2B on a single | runner on 1B on a double
-      const double h1 = take(tp, pos, len, (is_out && on1 && outs < 2u) || (is_1b && on2) || (is_2b && on1));
-      // h2: runner on 1B on a single
-      const double h2 = take(tp, pos, len, is_1b && on1);
-      // h3: two outs, runner from 2B held at 3B on a single
-      const bool held = is_1b && on2 && !(h1 < 0.4);
-      const double h3 = take(tp, pos, len, held && outs == 2u);
+      uint32_t o;
+      double h1, h2, h3;
+      bool is_out, is_1b, held;
+      if (!noise || (has_k && has_b)) {
+        // ---- window path: every draw of this plate appearance sits at a known slot of tape[pos .. pos + B + 8] ----
+        constexpr int B = NOISE ? 2 : 0;
+        double w[B + 9];
+#pragma unroll
+        for (int i = 0; i < B + 9; ++i) w[i] = peek(tp, pos + (uint32_t)i, len);
+        const double kp = NOISE ? w[0] : k;
+        const double bp = __dmul_rn(NOISE ? w[1] : bb, 1.01);
+        const double u = w[B], uhr = w[B + 1];                          // u_hr is always consumed (:126)
+        const bool is_k = u < kp;
+        const bool is_bb = !is_k && (u < __dadd_rn(kp, bp));
+        const bool contact = !is_k && !is_bb;
+        const bool is_hr = contact && (uhr < P.pit_hr[side][pit]);
+        const bool bip = contact && !is_hr;
+        // resolve_contact (:51-88)
+        const double ubip = w[B + 2], uhit = w[B + 3], u7 = w[B + 4], u8 = w[B + 5];
+        uint32_t type = (uint32_t)(P.cdf_bip[0] <= ubip) + (uint32_t)(P.cdf_bip[1] <= ubip) + (uint32_t)(P.cdf_bip[2] <= ubip) +
+                        (uint32_t)(P.cdf_bip[3] <= ubip);
+        if (type > 3u) type = 3u;
+        const bool hit = bip && (uhit < P.hit_prob[side][pit][slot][type]);   // stdlib stream (core/bip_resolution.py:62)
+        const bool fb = bip && !hit && (u7 < 0.10);                           // u7: 1B/2B/3B split of a hit, else the 10 % fallback draw
+        o = MLBSIM_OUT;
+        if (hit) o = MLBSIM_1B + (uint32_t)(P.cdf_hit[0] <= u7) + (uint32_t)(P.cdf_hit[1] <= u7) + (uint32_t)(P.cdf_hit[2] <= u7);
+        if (fb) o = MLBSIM_1B + (uint32_t)(P.cdf_fb[0] <= u8) + (uint32_t)(P.cdf_fb[1] <= u8);
+        if (is_hr) o = MLBSIM_HR;
+        if (is_bb) o = MLBSIM_BB;
+        if (is_k) o = MLBSIM_K;
+        // ---- handler draws (core/half_inning_simulator.py:73-136, :28-39): they follow the B + 2 (+3 if in play, +1 if
+        //      the fallback drew) entries above ----
+        is_out = (o == MLBSIM_K) || (o == MLBSIM_OUT);
+        is_1b = o == MLBSIM_1B;
+        const bool is_2b = o == MLBSIM_2B;
+        const bool need1 = (is_out && on1 && outs < 2u) || (is_1b && on2) || (is_2b && on1);   // double play | runner on 2B on a single | runner on 1B on a double
+        const bool need2 = is_1b && on1;                                                         // runner on 1B on a single
+        h1 = bip ? (fb ? w[B + 6] : w[B + 5]) : w[B + 2];
+        h2 = fb ? (need1 ? w[B + 7] : w[B + 6]) : (need1 ? w[B + 6] : w[B + 5]);                 // (a single is always a ball in play)
+        held = is_1b && on2 && !(h1 < 0.4);
+        const bool need3 = held && outs == 2u;                                                   // two outs, runner from 2B held at 3B
+        h3 = need2 ? (fb ? w[B + 8] : w[B + 7]) : (fb ? w[B + 7] : w[B + 6]);                    // (held => need1)
+        pos += (uint32_t)B + 2u + (bip ? 3u + (uint32_t)fb : 0u) + (uint32_t)need1 + (uint32_t)need2 + (uint32_t)need3;
+      } else {
+        // ---- degenerate rate (k or bb outside (0, 1)): draw by draw ----
+        const double vk = take(tp, pos, len, has_k);
+        const double vb = take(tp, pos, len, has_b);
+        const double kp = k <= 0.0 ? 0.0 : k >= 1.0 ? 1.0 : vk;
+        double bp = bb <= 0.0 ? 0.0 : bb >= 1.0 ? 1.0 : vb;
+        bp = __dmul_rn(bp, 1.01);
+        const double u = take(tp, pos, len, true);
+        const double uhr = take(tp, pos, len, true);
+        const bool is_k = u < kp;
+        const bool is_bb = !is_k && (u < __dadd_rn(kp, bp));
+        const bool contact = !is_k && !is_bb;
+        const bool is_hr = contact && (uhr < P.pit_hr[side][pit]);
+        const bool bip = contact && !is_hr;
+        const double ubip = take(tp, pos, len, bip);
+        uint32_t type = (uint32_t)(P.cdf_bip[0] <= ubip) + (uint32_t)(P.cdf_bip[1] <= ubip) + (uint32_t)(P.cdf_bip[2] <= ubip) +
+                        (uint32_t)(P.cdf_bip[3] <= ubip);
+        if (type > 3u) type = 3u;
+        const double uhit = take(tp, pos, len, bip);
+        const bool hit = bip && (uhit < P.hit_prob[side][pit][slot][type]);
+        const double u7 = take(tp, pos, len, bip);
+        const bool fb = bip && !hit && (u7 < 0.10);
+        const double u8 = take(tp, pos, len, fb);
+        o = MLBSIM_OUT;
+        if (hit) o = MLBSIM_1B + (uint32_t)(P.cdf_hit[0] <= u7) + (uint32_t)(P.cdf_hit[1] <= u7) + (uint32_t)(P.cdf_hit[2] <= u7);
+        if (fb) o = MLBSIM_1B + (uint32_t)(P.cdf_fb[0] <= u8) + (uint32_t)(P.cdf_fb[1] <= u8);
+        if (is_hr) o = MLBSIM_HR;
+        if (is_bb) o = MLBSIM_BB;
+        if (is_k) o = MLBSIM_K;
+        is_out = (o == MLBSIM_K) || (o == MLBSIM_OUT);
+        is_1b = o == MLBSIM_1B;
+        const bool is_2b = o == MLBSIM_2B;
+        h1 = take(tp, pos, len, (is_out && on1 && outs < 2u) || (is_1b && on2) || (is_2b && on1));
+        h2 = take(tp, pos, len, is_1b && on1);
+        held = is_1b && on2 && !(h1 < 0.4);
+        h3 = take(tp, pos, len, held && outs == 2u);
+      }
       bool dA;
       if (is_out) dA = h1 < 0.14;
       else if (is_1b) dA = (h1 < 0.4) || (held && outs == 2u && h3 < 0.10);
@@ -211,9 +282,13 @@ mlbsim_replay_flat_kernel(const ReplayArgs args, unsigned long long* counter, ui
       const uint32_t side = hidx & 1u;
       uint32_t runs = (hs >> 16) & 63u;
       const bool reached = (hs & HS_REACHED) != 0u;
-      const double um = take(tp, pos, len, reached && runs == 0u);
-      if (reached && runs == 0u && um < 0.011) runs += 1u;
-      const double ug = take(tp, pos, len, reached);
+      // misc run, ghost run, reliever pick: at most three consecutive entries, loaded together
+      const double b0 = peek(tp, pos, len), b1 = peek(tp, pos + 1u, len), b2 = peek(tp, pos + 2u, len);
+      const bool need_m = reached && runs == 0u;
+      const double um = b0, ug = need_m ? b1 : b0;
+      const double upick = reached ? (need_m ? b2 : b1) : b0;
+      pos += (uint32_t)need_m + (uint32_t)reached;
+      if (need_m && um < 0.011) runs += 1u;
       if (reached && ug < 0.01) runs += 1u;
       sc += runs << (side * 16u);
       const uint32_t inning = (hidx >> 1) + 1u;
@@ -236,7 +311,8 @@ mlbsim_replay_flat_kernel(const ReplayArgs args, unsigned long long* counter, ui
         { const unsigned long long t = pa_cur; pa_cur = pa_oth; pa_oth = t; }
         const uint32_t nb = side ? nb0 : nb1;     // staff that now takes the mound
         if (nb != 0u && ((cur & CX_TIER_GE2) != 0u || cur >= ((uint32_t)91 << CX_PC_SHIFT))) {   // game_simulator.py:8-12
-          int idx = (int)take(tp, pos, len, true);
+          int idx = (int)upick;
+          ++pos;
           idx = idx < 0 ? 0 : (idx >= (int)nb ? (int)nb - 1 : idx);
           cur = (cur & CX_SLOT) | ((uint32_t)(idx + 1) << CX_PIT_SHIFT);
           const uint32_t sh = side ? 0u : 8u;     // new side 0 -> home staff
@@ -262,4 +338,16 @@ mlbsim_replay_flat_kernel(const ReplayArgs args, unsigned long long* counter, ui
     }
     __syncwarp();
   }
+}
+
+}  // namespace
+
+extern "C" __global__ void __launch_bounds__(REPLAY_FLAT_THREADS, REPLAY_FLAT_BLOCKS)
+mlbsim_replay_flat_kernel(const ReplayArgs args, unsigned long long* counter, uint32_t chunk) {
+  replay_body<true>(args, counter, chunk);     // simulate_game(use_noise=True)
+}
+
+extern "C" __global__ void __launch_bounds__(REPLAY_FLAT_THREADS, REPLAY_FLAT_BLOCKS)
+mlbsim_replay_flat_nonoise_kernel(const ReplayArgs args, unsigned long long* counter, uint32_t chunk) {
+  replay_body<false>(args, counter, chunk);
 }
