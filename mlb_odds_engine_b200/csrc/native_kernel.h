@@ -65,5 +65,5 @@ size_t mlbsim_native_smem_bytes(int threads_per_block);
 #define MLBSIM_REPLAY_FLAT_THREADS 256
 #endif
 #ifndef MLBSIM_REPLAY_FLAT_BLOCKS
-#define MLBSIM_REPLAY_FLAT_BLOCKS 6   /* 1536 threads per SM at 40 registers: measured best (profiles/r01_replay_variants.log) */
+#define MLBSIM_REPLAY_FLAT_BLOCKS 3   /* 768 threads per SM at 80 registers (the 11-entry tape window lives in registers): measured best (profiles/r02_rp1.log) */
 #endif
