@@ -314,7 +314,7 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
   // ---- lane state ----
   uint32_t c0 = 0, c1 = 0;   // Philox counter: c0 = sim_lo, c1 = PA number | matchup | sim_hi
   uint32_t cur = 0, oth = 0; // side contexts: cur = side at bat
-  uint32_t sc = 0;           // away | home << 16
+  uint32_t sc = 0;           // score: side at bat | other side << 16
   uint32_t hidx = 0;         // half-inning index: side = hidx & 1, inning = (hidx >> 1) + 1
   uint32_t hs = HS_DEAD;     // half-inning state; HS_DEAD = this lane has no game
   uint32_t used = 0;         // reliever bitmasks: home staff bits 0-7, away staff 8-15
@@ -351,7 +351,7 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
         c0 = (uint32_t)sim;
         c1 = ((uint32_t)(sim >> 32) << RNG_SIMHI_SHIFT) | rng_matchup;
         cur = init0; oth = init1;
-        sc = 0; hidx = 0; hs = hs_new_half; used = 0; pa_addr = pa_mine;
+        sc = 0; hidx = 0; hs = hs_new_half; used = 0;   // (pa_addr already points at the away side's counters)
       }
       const uint32_t want = __popc(need);
       chunk_next += want < avail ? want : avail;
@@ -435,6 +435,8 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
     if ((hs & HS_OVER) != 0u) {   // (a dead lane has only HS_DEAD set)
       {
         // ---------------- end of half inning ----------------
+        // `sc` keeps the score of the side AT BAT in its low half and the other side's in its high half (the halves
+        // trade places when the sides do), so adding this half's runs needs no shift by the side.
         const uint32_t side = hidx & 1u;
         uint32_t runs = (hs >> HS_RUNS_SHIFT) & 31u;
         // misc / ghost run (half_inning_simulator.py:12-25): rare (2 %), only if a runner reached.
@@ -442,18 +444,24 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
         if (w1_first < T_END_ANY && (hs & HS_REACHED) != 0u) {
           runs += (runs == 0u) ? 1u + (uint32_t)(w1_first < T_END_BOTH) : (uint32_t)(w1_first < T_END_GHOST);
         }
-        sc += runs << (side * 16u);
-        // first 1/3/5/7 innings: committed when the bottom half of that inning ends (hidx = 1, 5, 9, 13)
-        if ((hidx & 3u) == 1u && hidx < 16u) commit_joint(A_JOINT, H, hidx >> 2, sc & 0xFFFFu, sc >> 16);
+        sc += runs;
+        // first 1/3/5/7 innings: committed when the bottom half of that inning ends (hidx = 1, 5, 9, 13): the home team
+        // just batted (low half), joint bin [away][home].  Both below 32 (all but never false): shared u32 bin at
+        // away * 32 + home = (sc >> 11) + (sc & 31); else the global u64 bin directly.
+        if ((hidx & 0xFFFFFFF3u) == 1u) {
+          if ((sc & 0xFFE0FFE0u) == 0u) red_inc_shared(A_JOINT + ((hidx & 0xCu) << 10) + (((sc >> 11) + (sc & 31u)) << 2));
+          else commit_joint(A_JOINT, H, hidx >> 2, sc >> 16, sc & 0xFFFFu);
+        }
         // game_simulator.py:72 (bottom of the 9th skipped when the home team leads) and :110-111; termination guard:
-        // the bottom of inning MLBSIM_MAX_INNINGS ends the game whatever the score
-        const uint32_t a_ = sc & 0xFFFFu, h_ = sc >> 16;
-        const bool over = ((side != 0u) & (hidx >= 17u) & ((a_ != h_) | (hidx >= LAST_HIDX))) | ((hidx == 16u) & (h_ > a_));
+        // the bottom of inning MLBSIM_MAX_INNINGS ends the game whatever the score.
+        const uint32_t bat = sc & 0xFFFFu, fld = sc >> 16;   // score of the side that just batted / of the side in the field
+        const bool over = ((side != 0u) & (hidx >= 17u) & ((bat != fld) | (hidx >= LAST_HIDX))) | ((hidx == 16u) & (fld > bat));
         if (!over) {
           hs = hs_new_half;
           ++hidx;
+          sc = __funnelshift_l(sc, sc, 16);   // the other side bats next
           const uint32_t t = cur; cur = oth; oth = t;
-          if (COUNT_PA) pa_addr = side ? pa_mine : pa_mine + pa_side;
+          if (COUNT_PA) pa_addr += side ? 0u - pa_side : pa_side;   // counters of the side that bats next
           // should_replace_pitcher (game_simulator.py:8-12) for the staff that now takes the mound
           const uint32_t nb = side ? nb0 : nb1;  // `side` is the half that just ended
           if (nb != 0u && ((cur & CX_TIER_GE2) != 0u || (cur & CX_PC_BITS) >= ((uint32_t)(PITCH_LIMIT + 1) << CX_PC_SHIFT))) {
@@ -470,6 +478,8 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
           }
         } else {
           // ---------------- game over: commit ----------------
+          const uint32_t a_ = side ? fld : bat, h_ = side ? bat : fld;
+          if (COUNT_PA && side) pa_addr -= pa_side;   // back to the away side's counters: where the lane's next game starts
           commit_joint(A_JOINT, H, 4u, a_, h_);
           const uint32_t inn = (hidx >> 1) + 1u;
           red_inc_shared(A_INN + ((inn < MLBSIM_INN_BINS - 1 ? inn : MLBSIM_INN_BINS - 1) << 2));
