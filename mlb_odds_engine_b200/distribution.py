@@ -13,6 +13,8 @@ use only `markets` and `start_time_iso`).
 """
 from __future__ import annotations
 
+import bisect
+import functools
 import json
 import math
 import os
@@ -89,12 +91,23 @@ class Weighted:
         return float(self.w[mask].sum() / self.n)
 
     def pmf_rounded(self):
-        """summarize_pmf(np.round(values).astype(int)) — core/stats_tools.py:40-51 (np.round = half to even)."""
-        keys = np.round(self.x).astype(np.int64)
-        out = {}
-        for k in np.unique(keys):
-            out[float(k)] = float(self.w[keys == k].sum() / self.n)
-        return out
+        """summarize_pmf(np.round(values).astype(int)) — core/stats_tools.py:40-51 (np.round = half to even).  One
+        bincount over the cells instead of one masked sum per key (the weights are integer counts: the sums are exact
+        in any order)."""
+        keys, inverse = np.unique(np.round(self.x).astype(np.int64), return_inverse=True)
+        mass = np.bincount(inverse.reshape(-1), weights=self.w, minlength=len(keys)) / self.n
+        return Pmf(zip(keys.astype(np.float64).tolist(), mass.tolist()))
+
+
+class Pmf(dict):
+    """{value: probability} in ascending value order (what `json.dump` writes), with the sorted columns cached so that
+    a tail probability is a bisection and one C-level sum over a slice instead of a Python loop over the items."""
+
+    def columns(self):
+        c = self.__dict__.get("_cols")
+        if c is None or len(c[0]) != len(self):
+            c = self.__dict__["_cols"] = (list(self.keys()), list(self.values()))
+        return c
 
 
 def scale_distribution(v: Weighted, target_mean=None, target_sd=None) -> Weighted:
@@ -110,6 +123,13 @@ def scale_distribution(v: Weighted, target_mean=None, target_sd=None) -> Weighte
 
 def tail(pmf, threshold, direction):
     """core/stats_tools.py:13-28."""
+    if isinstance(pmf, Pmf):      # ascending keys: the same left-to-right sums as the loops below, without the loop
+        keys, probs = pmf.columns()
+        if direction == "over":
+            return sum(probs[bisect.bisect_right(keys, threshold):])
+        if direction == "under":
+            return sum(probs[:bisect.bisect_left(keys, threshold)])
+        return pmf.get(float(int(threshold)), 0.0)
     if direction == "over":
         return sum(p for x, p in pmf.items() if x > threshold)
     if direction == "under":
@@ -149,6 +169,7 @@ def parse_game_id(game_id: str) -> dict:
         return {"date": game_id, "away": "", "home": "", "time": ""}
 
 
+@functools.lru_cache(maxsize=1)
 def _eastern():
     from zoneinfo import ZoneInfo, ZoneInfoNotFoundError
 

@@ -53,13 +53,15 @@ class RunHistogram:
         return {team: {o: int(self.rec["pa"][s][i]) for i, o in enumerate(_abi.OUTCOMES)}
                 for s, team in ((1, "HOME"), (0, "AWAY"))}
 
-    def reliever_usage(self) -> dict:
+    def reliever_usage(self, bullpen_names=None) -> dict:
         """{"home": {name: sims in which he appeared}, "away": {...}} —
-        cli/run_distribution_simulator.py:391-397."""
+        cli/run_distribution_simulator.py:391-397.  `bullpen_names`: [home names, away names] when the histogram
+        travels without its Matchup."""
         out = {"home": {}, "away": {}}
         for s, side in ((0, "home"), (1, "away")):
             n = 8
-            names = self.matchup.bullpen_names[s] if self.matchup is not None else [f"#{i}" for i in range(n)]
+            names = (bullpen_names[s] if bullpen_names is not None else
+                     self.matchup.bullpen_names[s] if self.matchup is not None else [f"#{i}" for i in range(n)])
             for i, name in enumerate(names):
                 c = int(self.rec["rel_games"][s][i])
                 if c:

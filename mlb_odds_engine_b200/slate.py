@@ -12,8 +12,52 @@ from __future__ import annotations
 
 import os
 
-from . import distribution, tables
-from .simulator import GpuSimulator
+import numpy as np
+
+from . import _abi, distribution, tables
+from .simulator import GpuSimulator, RunHistogram
+
+_POOL = None
+
+
+def pricing_pool(workers: int):
+    """A persistent pool of worker PROCESSES for the per-game host work (pricing a histogram and writing its JSON is
+    ~5 ms of pure Python per game: after a one-launch slate it, not the GPU, is the critical path).  Spawned, not forked
+    — the parent holds a CUDA context — and created once per process: the ~0.5 s of interpreter start-up is paid on the
+    first slate only."""
+    global _POOL
+    if _POOL is None or _POOL[0] != workers:
+        import multiprocessing as mp
+        from concurrent.futures import ProcessPoolExecutor
+
+        if _POOL is not None:
+            _POOL[1].shutdown(wait=False)
+        ex = ProcessPoolExecutor(workers, mp_context=mp.get_context("spawn"))
+        list(ex.map(_warm, range(workers)))          # import numpy / the package in every worker now
+        _POOL = (workers, ex)
+    return _POOL[1]
+
+
+def _warm(i):
+    return i
+
+
+def _price_one(job):
+    """Worker side: histogram bytes -> priced document (+ files).  Returns (game_id, doc | None, error | None)."""
+    gid, rec_bytes, bullpen_names, calibration, start_time, json_path, snapshot_path = job
+    try:
+        rec = np.frombuffer(rec_bytes, dtype=_abi.HIST_DTYPE)[0]
+        h = RunHistogram(rec, None)
+        doc = distribution.price_from_histogram(h, gid, calibration, start_time)
+        doc["reliever_usage"] = h.reliever_usage(bullpen_names)
+        doc["pa_recap"] = h.pa_recap()
+        if json_path:
+            distribution.write_sim_json(doc, json_path)
+        if snapshot_path:
+            distribution.write_table_snapshot(doc, snapshot_path)
+        return gid, doc, None
+    except Exception as e:
+        return gid, None, f"{type(e).__name__}: {e}"
 
 
 def matchup_from_assets(game_id: str, assets: dict, env: dict | None = None, use_noise: bool = True) -> dict:
@@ -31,13 +75,14 @@ def matchup_from_assets(game_id: str, assets: dict, env: dict | None = None, use
 
 def run_slate(matchups: list[dict], n_sims: int = 10_000, seed: int = 0, calibration: dict | None = None,
               out_dir: str | None = None, safe: bool = False, sim: GpuSimulator | None = None,
-              start_times: dict | None = None, snapshot_path: str | None = None) -> dict:
+              start_times: dict | None = None, snapshot_path: str | None = None, workers: int = 0) -> dict:
     """Simulate every game of the slate in one launch and price it.  `matchups`: simulate_game keyword
     dicts carrying `game_id` ('YYYY-MM-DD-AWAY@HOME[-Thhmm]').  Returns {game_id: document}; with `out_dir` also writes
     `<out_dir>/<date>/<game_id>.json`, and with `snapshot_path` the `last_table_snapshot.json` side file the reference
     rewrites after every game (cli/run_distribution_simulator.py:853-859; the last game of the slate wins, as in the
     serial loop).  A game that fails — malformed assets, an id without AWAY@HOME, an unwritable path — raises, or with
-    `safe=True` is reported under "failed" and skipped: the semantics of `--safe` (cli/full_slate_runner.py:157-162)."""
+    `safe=True` is reported under "failed" and skipped: the semantics of `--safe` (cli/full_slate_runner.py:157-162).
+    `workers` > 0 prices and writes the games in that many worker processes (`pricing_pool`)."""
     own = sim is None
     sim = sim or GpuSimulator(0)
     built, failed = [], {}
@@ -56,20 +101,21 @@ def run_slate(matchups: list[dict], n_sims: int = 10_000, seed: int = 0, calibra
         if built:
             sim.load_matchups([m for _, m in built])
             hists = sim.simulate(n_sims, seed=seed)
-            for (gid, _), h in zip(built, hists):
-                try:
-                    doc = distribution.price_from_histogram(h, gid, calibration, (start_times or {}).get(gid))
-                    doc["reliever_usage"] = h.reliever_usage()
-                    doc["pa_recap"] = h.pa_recap()
-                    if out_dir:
-                        distribution.write_sim_json(doc, os.path.join(out_dir, distribution.parse_game_id(gid)["date"], f"{gid}.json"))
-                    if snapshot_path:
-                        distribution.write_table_snapshot(doc, snapshot_path)
-                    docs[gid] = doc
-                except Exception as e:
+            jobs = []
+            for (gid, m), h in zip(built, hists):
+                path = os.path.join(out_dir, distribution.parse_game_id(gid)["date"], f"{gid}.json") if out_dir else None
+                jobs.append((gid, h.rec.tobytes(), m.bullpen_names, calibration, (start_times or {}).get(gid), path, None))
+            results = list(pricing_pool(workers).map(_price_one, jobs)) if workers > 0 and len(jobs) > 1 else [_price_one(j) for j in jobs]
+            for gid, doc, err in results:
+                if err is not None:
                     if not safe:
-                        raise
-                    failed[gid] = f"{type(e).__name__}: {e}"
+                        raise RuntimeError(f"{gid}: {err}")
+                    failed[gid] = err
+                else:
+                    docs[gid] = doc
+            if snapshot_path and docs:      # the serial reference loop leaves the LAST game's snapshot behind
+                last = [gid for gid, _ in built if gid in docs][-1]
+                distribution.write_table_snapshot(docs[last], snapshot_path)
     finally:
         if own:
             sim.close()
