@@ -539,7 +539,6 @@ mlbsim_stage_tables_kernel(const mlbsim_table* __restrict__ tables, mlbsim_stage
 extern "C" __global__ void __launch_bounds__(NATIVE_LB_THREADS, NATIVE_LB_BLOCKS)
 mlbsim_native_kernel(const NativeArgs args) {
   const int tid = threadIdx.x;
-  const int lane = tid & 31;
   const uint32_t n_sims = args.n_sims;
   const bool count_pa = (args.flags & 1u) == 0;
 

@@ -1,0 +1,459 @@
+// replay_ring_kernel.cu — tape-replay mode (bit-exact verification against the reference's recorded draws), fed by
+// the bulk-copy engine.
+//
+// Contract: bit-exact integers on the reference's recorded draws (the fields of core/game_simulator.py:134-144),
+// float64 compares, no FMA contraction.  Organised like the native kernel: the warp runs in rounds of REPLAY_UNROLL
+// plate-appearance steps followed by one boundary pass, lanes refill by ballot prefix.
+//
+// The tape is the only HBM traffic (~535 float64 per game) and every lane reads ITS OWN game's tape at its own
+// position: 32 unrelated 8-byte streams per warp.  Read with LDG that costs one L1 wavefront per lane per draw (the
+// flat kernel this replaces ran the L1 data pipe at 78 % of its peak moving 8 useful bytes per 32-byte sector).  Here
+// every lane owns a RING of four 128-byte chunks of its tape in shared memory.  Chunks are aligned to the tape array,
+// so a refill is one `cp.async.bulk` of 128 contiguous bytes (a full sector group, no LSU involvement) per consumed
+// chunk, completion counted on one mbarrier per warp; copies are asked for one round ahead of their use, so nobody
+// waits on them.  The reference's draw grammar
+//     [beta_k] [beta_bb] u u_hr [u_bip u_hit (u_hit3 | u_fb [u_fb2])] [h1] [h2] [h3]
+// makes WHICH value a draw is depend on the values before it, but not WHERE the next values are: a plate appearance
+// consumes at most eleven consecutive entries, so a step loads the window tape[pos .. pos+10] with eleven independent
+// LDS.64 at immediate offsets (the ring's first chunk is mirrored behind its last, so a window never wraps) and the
+// grammar only selects among registers.  Degenerate rates (k or bb outside (0, 1): no Beta draw,
+// core/pa_simulator.py:23-32) read draw by draw from the same ring.  The per-PA K / BB rates of every (side, pitcher,
+// TTO tier, batter) up to 75 pitches are tabulated in shared memory at block start with the reference's operation
+// order (core/fatigue_modeling.py:25-43, core/pa_simulator.py:108-114).
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/mlbsim.h"
+#include "game_rules.cuh"
+#include "native_kernel.h"
+
+#ifndef REPLAY_UNROLL
+#define REPLAY_UNROLL 4
+#endif
+
+namespace {
+
+constexpr int LUT_WORDS = 24 * 8 * 4;  // [outs*8+bases][outcome][dA][dB], same semantics as the native kernel's LUT
+
+// ring geometry
+constexpr uint32_t CHUNK = 16;                               // tape entries per chunk: 128 bytes
+constexpr uint32_t RING_CHUNKS = 4;
+constexpr uint32_t RING = CHUNK * RING_CHUNKS;               // 64 entries
+constexpr uint32_t CHUNK_BYTES = CHUNK * 8;
+constexpr uint32_t LANE_BYTES = MLBSIM_REPLAY_RING_LANE_BYTES;   // 4 chunks + the mirror of chunk slot 0 = 640
+constexpr int WINDOW = 11;                                   // most entries one plate appearance can consume
+static_assert(LANE_BYTES == (RING + CHUNK) * 8, "ring layout");
+static_assert(WINDOW <= (int)CHUNK, "a window must fit the mirrored head");
+
+// context word: slot[3:0] | tier[5:4] (min(tto,4)-1) | pit[8:6] | pitch_count[31:9]
+constexpr uint32_t CX_SLOT = 0xFu;
+constexpr uint32_t CX_TIER_ONE = 1u << 4;
+constexpr uint32_t CX_TIER_MASK = 3u << 4;
+constexpr uint32_t CX_TIER_GE2 = 2u << 4;
+constexpr int CX_PIT_SHIFT = 6;
+constexpr int CX_PC_SHIFT = 9;
+constexpr uint32_t CX_NEXT_PA = (1u << CX_PC_SHIFT) + 1u;
+// half state: ob[4:0] | n_pa + 34 [14:8] | runs[21:16] | reached[29:24] | three outs [30]
+constexpr uint32_t HS_OB = 31u;
+constexpr uint32_t HS_NEW_HALF = (64u - 30u) << 8;
+constexpr uint32_t HS_PA_ONE = 1u << 8;
+constexpr uint32_t HS_OVER = (1u << 30) | (1u << 14);
+constexpr uint32_t HS_REACHED = 0x3Fu << 24;
+constexpr uint32_t HS_DEAD = 1u << 15;
+
+constexpr int KB_ENTRIES = 2 * MLBSIM_MAX_PITCHERS * MLBSIM_N_TIERS * MLBSIM_MAX_LINEUP;   // 504
+
+struct RingSmem {
+  mlbsim_params P;
+  uint32_t lut[LUT_WORDS];
+  double2 kb[KB_ENTRIES];   // {k, bb} before noise at pitch_count <= 75: [side][pit][tier][slot]
+  unsigned long long mbar[MLBSIM_REPLAY_RING_THREADS / 32];   // one completion barrier per warp
+};
+
+// effective K / BB rates of one plate appearance before noise: fatigue-adjusted pitcher rate averaged with the batter's,
+// times the umpire modifiers — core/fatigue_modeling.py:25-43 (two separate multiplies per rate, in this order), then
+// core/pa_simulator.py:108-114
+__device__ __forceinline__ double2 effective_rates(const mlbsim_params& P, uint32_t side, uint32_t pit, uint32_t tier, uint32_t slot, int pc) {
+  const double pen = tier == 0 ? 0.0 : tier == 1 ? 0.015 : tier == 2 ? 0.035 : 0.060;
+  double ak = __dmul_rn(P.pit_k[side][pit], __dsub_rn(1.0, pen));
+  double ab = __dmul_rn(P.pit_bb[side][pit], __dadd_rn(1.0, pen));
+  double fl = __ddiv_rn((double)(pc - 75), 25.0);
+  if (!(fl > 0.0)) fl = 0.0;
+  ak = __dmul_rn(ak, __dsub_rn(1.0, __dmul_rn(0.02, fl)));
+  ab = __dmul_rn(ab, __dadd_rn(1.0, __dmul_rn(0.03, fl)));
+  double2 r;
+  r.x = __dmul_rn(__ddiv_rn(__dadd_rn(P.bat_k[side][slot], ak), 2.0), P.k_mod);
+  r.y = __dmul_rn(__ddiv_rn(__dadd_rn(P.bat_bb[side][slot], ab), 2.0), P.bb_mod);
+  return r;
+}
+
+__device__ __forceinline__ uint32_t lanemask_lt() {
+  uint32_t m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+
+// ---- bulk-copy engine (TMA, 1-D form) + mbarrier ------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t arrivals) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(arrivals) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t mbar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+               "r"(mbar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(mbar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+
+// N consecutive tape entries starting at ring position `ridx` (= absolute tape index & 63) of the lane's ring: independent
+// LDS.64 at immediate offsets (the mirrored head makes [ridx, ridx + N) contiguous).  Entries at or past the game's end
+// read as 0.5, exactly like the draw-by-draw path (the underrun is flagged later through pos > len) — only a lane within
+// N entries of its game's end pays for that.
+template <int N>
+__device__ __forceinline__ void ring_window(uint32_t ring, uint32_t ridx, uint32_t pos, uint32_t len, double (&w)[N]) {
+  const uint32_t a = ring + (ridx << 3);
+#pragma unroll
+  for (int i = 0; i < N; ++i) w[i] = lds_f64(a + 8u * (uint32_t)i);
+  if (pos + (uint32_t)N > len) {
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+      if (pos + (uint32_t)i >= len) w[i] = 0.5;
+  }
+}
+
+// one draw at the lane's position (degenerate-rate path): past-the-end reads yield 0.5
+__device__ __forceinline__ double ring_take(uint32_t ring, uint32_t gbase, uint32_t& pos, uint32_t len, bool want) {
+  double v = 0.5;
+  if (want) {
+    if (pos < len) v = lds_f64(ring + (((gbase + pos) & (RING - 1u)) << 3));
+    ++pos;
+  }
+  return v;
+}
+
+template <bool NOISE>
+__device__ __forceinline__ void replay_ring_body(const ReplayArgs& args, unsigned long long* counter, uint32_t chunk) {
+  __shared__ RingSmem S;
+  extern __shared__ __align__(128) unsigned char ring_smem[];
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(args.params);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&S.P);
+    for (int i = threadIdx.x; i < (int)(sizeof(mlbsim_params) / 4); i += blockDim.x) dst[i] = src[i];
+    for (int i = threadIdx.x; i < LUT_WORDS; i += blockDim.x) {
+      const int ob = i >> 5, o = (i >> 2) & 7, dA = (i >> 1) & 1, dB = i & 1;
+      S.lut[i] = transition_entry(o < 7 ? o : MLBSIM_OUT, dA, dB, ob >> 3, ob & 7);
+    }
+    if ((threadIdx.x & 31) == 0) mbar_init(smem_u32(&S.mbar[threadIdx.x >> 5]), 1);
+  }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+  for (int i = threadIdx.x; i < KB_ENTRIES; i += blockDim.x) {
+    const uint32_t slot = (uint32_t)i % MLBSIM_MAX_LINEUP, g = (uint32_t)i / MLBSIM_MAX_LINEUP;
+    S.kb[i] = effective_rates(S.P, g / (MLBSIM_MAX_PITCHERS * MLBSIM_N_TIERS), (g / MLBSIM_N_TIERS) % MLBSIM_MAX_PITCHERS, g % MLBSIM_N_TIERS, slot, 0);
+  }
+  __syncthreads();
+  const mlbsim_params& P = S.P;
+  const int lane = threadIdx.x & 31;
+  const uint32_t n_games = (uint32_t)args.n_games;
+  constexpr bool noise = NOISE;
+  const uint32_t L0 = (uint32_t)P.lineup_len[0], L1 = (uint32_t)P.lineup_len[1];
+  const uint32_t nb0 = (uint32_t)P.bullpen_len[0], nb1 = (uint32_t)P.bullpen_len[1];
+  const uint32_t ring = smem_u32(ring_smem) + threadIdx.x * LANE_BYTES;
+  const uint32_t mbar = smem_u32(&S.mbar[threadIdx.x >> 5]);
+  // chunks of the whole tape array that may be copied (the buffer is readable up to the end of its last chunk)
+  const uint32_t total_chunks = (uint32_t)((args.offsets[n_games] + (CHUNK - 1u)) / CHUNK);
+
+  uint32_t chunk_next = 0, chunk_end = 0;
+  bool exhausted = false;
+  // ring bookkeeping, in chunk indices of the whole tape array (absolute entry index >> 4)
+  uint32_t asked_c = 0;      // per lane: chunks [.., asked_c) have been asked for
+  uint32_t ready_c = 0;      // per lane: chunks [.., ready_c) have landed
+  uint32_t phase = 0;        // per warp: parity of the barrier phase in flight
+  bool pending = false;      // per warp: copies asked for in the previous round
+
+  // lane state
+  uint32_t gbase = 0;        // low 32 bits of the game's first absolute tape index (ring positions only need them)
+  uint32_t gchunk0 = 0;      // absolute chunk index of the game's first entry ...
+  uint32_t gfirst = 0;       // ... and that entry's position inside it: chunk of draw p = gchunk0 + ((gfirst + p) >> 4)
+  uint32_t pos = 0, len = 0, game = 0;
+  uint32_t cur = 0, oth = 0, sc = 0, hidx = 0, hs = HS_DEAD;
+  uint32_t nused = 0;                          // picks so far: home staff [7:0], away staff [15:8]
+  uint32_t status = 0;
+  unsigned long long pa_cur = 0, pa_oth = 0;   // 9-bit outcome counters of the side at bat / the other side
+
+  for (;;) {
+    // ---------------- refill / termination ----------------
+    if (__any_sync(0xffffffffu, hs == HS_DEAD)) {
+      const uint32_t need = __ballot_sync(0xffffffffu, hs == HS_DEAD);
+      if (chunk_next >= chunk_end && !exhausted) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(counter, (unsigned long long)chunk);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= (unsigned long long)n_games) {
+          exhausted = true;
+        } else {
+          chunk_next = (uint32_t)base;
+          const unsigned long long e = base + chunk;
+          chunk_end = e < (unsigned long long)n_games ? (uint32_t)e : n_games;
+        }
+      }
+      const uint32_t avail = chunk_end - chunk_next;
+      const uint32_t rank = __popc(need & lanemask_lt());
+      if (hs == HS_DEAD && rank < avail) {
+        game = chunk_next + rank;
+        const uint64_t lo = args.offsets[game], hi = args.offsets[game + 1];
+        gbase = (uint32_t)lo; gchunk0 = (uint32_t)(lo / CHUNK); gfirst = (uint32_t)(lo % CHUNK);
+        len = (uint32_t)(hi - lo); pos = 0;
+        asked_c = gchunk0; ready_c = gchunk0;   // nothing of this game is in the ring yet
+        cur = 0; oth = 0; sc = 0; hidx = 0; hs = HS_NEW_HALF; nused = 0; status = 0; pa_cur = 0; pa_oth = 0;
+      }
+      const uint32_t want = __popc(need);
+      chunk_next += want < avail ? want : avail;
+      if (exhausted && !__any_sync(0xffffffffu, hs != HS_DEAD)) break;
+    }
+
+    // ---------------- ring: last round's copies have landed; ask for the chunks consumed since ----------------
+    if (pending) {            // (warp-uniform)
+      mbar_wait(mbar, phase);
+      phase ^= 1u;
+      pending = false;
+    }
+    ready_c = asked_c;
+    {
+      const uint32_t cur_c = gchunk0 + ((gfirst + pos) >> 4);
+      const uint32_t upto = hs != HS_DEAD ? cur_c + RING_CHUNKS : asked_c;   // the chunk being read and the three after it
+      uint32_t bytes = 0;
+      for (uint32_t c = asked_c; c < upto; ++c)
+        if (c < total_chunks) bytes += CHUNK_BYTES + ((c & (RING_CHUNKS - 1u)) == 0u ? CHUNK_BYTES : 0u);
+      const uint32_t total = __reduce_add_sync(0xffffffffu, bytes);
+      if (total != 0u) {      // (warp-uniform)
+        fence_proxy_async();  // this lane's reads of the slots being replaced are ordered before the async writes
+        if (lane == 0) mbar_arrive_expect_tx(mbar, total);
+        __syncwarp();
+        for (uint32_t c = asked_c; c < upto; ++c) {
+          if (c < total_chunks) {
+            const double* src = args.tape + (size_t)c * CHUNK;
+            const uint32_t slot = c & (RING_CHUNKS - 1u);
+            bulk_copy_g2s(ring + slot * CHUNK_BYTES, src, CHUNK_BYTES, mbar);
+            if (slot == 0u) bulk_copy_g2s(ring + RING * 8u, src, CHUNK_BYTES, mbar);   // mirror behind the last slot
+          }
+        }
+        pending = true;
+      }
+      if (upto > asked_c) asked_c = upto;
+    }
+
+#pragma unroll
+    for (int rep = 0; rep < REPLAY_UNROLL; ++rep)
+    // a live lane plays when its whole window has landed (else it waits one round for the copies it asked for)
+    if ((hs & (HS_OVER | HS_DEAD)) == 0u && gchunk0 + ((gfirst + pos + (uint32_t)(WINDOW - 1)) >> 4) < ready_c) {
+      // ---------------- one plate appearance (core/pa_simulator.py:91-143) ----------------
+      const uint32_t side = hidx & 1u;
+      const uint32_t slot = cur & CX_SLOT;
+      const uint32_t tier = (cur >> 4) & 3u;
+      const uint32_t pit = (cur >> CX_PIT_SHIFT) & 7u;
+      const int pc = (int)(cur >> CX_PC_SHIFT);
+      const double2 rates = pc <= 75 ? S.kb[((side * MLBSIM_MAX_PITCHERS + pit) * MLBSIM_N_TIERS + tier) * MLBSIM_MAX_LINEUP + slot]
+                                     : effective_rates(P, side, pit, tier, slot, pc);
+      const double k = rates.x, bb = rates.y;
+      // beta_noise (core/pa_simulator.py:23-32): a draw only when 0 < p < 1
+      const bool has_k = noise && k > 0.0 && k < 1.0, has_b = noise && bb > 0.0 && bb < 1.0;
+      const uint32_t ob = hs & HS_OB;
+      const uint32_t outs = ob >> 3;
+      const bool on1 = (ob & 1u) != 0, on2 = (ob & 2u) != 0;
+      uint32_t o;
+      double h1, h2, h3;
+      bool is_out, is_1b, held;
+      if (!noise || (has_k && has_b)) {
+        // ---- window path: every draw of this plate appearance sits at a known slot of tape[pos .. pos + B + 8] ----
+        constexpr int B = NOISE ? 2 : 0;
+        double w[B + 9];
+        ring_window<B + 9>(ring, (gbase + pos) & (RING - 1u), pos, len, w);
+        const double kp = NOISE ? w[0] : k;
+        const double bp = __dmul_rn(NOISE ? w[1] : bb, 1.01);
+        const double u = w[B], uhr = w[B + 1];                          // u_hr is always consumed (:126)
+        const bool is_k = u < kp;
+        const bool is_bb = !is_k && (u < __dadd_rn(kp, bp));
+        const bool contact = !is_k && !is_bb;
+        const bool is_hr = contact && (uhr < P.pit_hr[side][pit]);
+        const bool bip = contact && !is_hr;
+        // resolve_contact (:51-88)
+        const double ubip = w[B + 2], uhit = w[B + 3], u7 = w[B + 4], u8 = w[B + 5];
+        uint32_t type = (uint32_t)(P.cdf_bip[0] <= ubip) + (uint32_t)(P.cdf_bip[1] <= ubip) + (uint32_t)(P.cdf_bip[2] <= ubip) +
+                        (uint32_t)(P.cdf_bip[3] <= ubip);
+        if (type > 3u) type = 3u;
+        const bool hit = bip && (uhit < P.hit_prob[side][pit][slot][type]);   // stdlib stream (core/bip_resolution.py:62)
+        const bool fb = bip && !hit && (u7 < 0.10);                           // u7: 1B/2B/3B split of a hit, else the 10 % fallback draw
+        o = MLBSIM_OUT;
+        if (hit) o = MLBSIM_1B + (uint32_t)(P.cdf_hit[0] <= u7) + (uint32_t)(P.cdf_hit[1] <= u7) + (uint32_t)(P.cdf_hit[2] <= u7);
+        if (fb) o = MLBSIM_1B + (uint32_t)(P.cdf_fb[0] <= u8) + (uint32_t)(P.cdf_fb[1] <= u8);
+        if (is_hr) o = MLBSIM_HR;
+        if (is_bb) o = MLBSIM_BB;
+        if (is_k) o = MLBSIM_K;
+        // ---- handler draws (core/half_inning_simulator.py:73-136, :28-39): they follow the B + 2 (+3 if in play, +1 if
+        //      the fallback drew) entries above ----
+        is_out = (o == MLBSIM_K) || (o == MLBSIM_OUT);
+        is_1b = o == MLBSIM_1B;
+        const bool is_2b = o == MLBSIM_2B;
+        const bool need1 = (is_out && on1 && outs < 2u) || (is_1b && on2) || (is_2b && on1);   // double play | runner on 2B on a single | runner on 1B on a double
+        const bool need2 = is_1b && on1;                                                         // runner on 1B on a single
+        h1 = bip ? (fb ? w[B + 6] : w[B + 5]) : w[B + 2];
+        h2 = fb ? (need1 ? w[B + 7] : w[B + 6]) : (need1 ? w[B + 6] : w[B + 5]);                 // (a single is always a ball in play)
+        held = is_1b && on2 && !(h1 < 0.4);
+        const bool need3 = held && outs == 2u;                                                   // two outs, runner from 2B held at 3B
+        h3 = need2 ? (fb ? w[B + 8] : w[B + 7]) : (fb ? w[B + 7] : w[B + 6]);                    // (held => need1)
+        pos += (uint32_t)B + 2u + (bip ? 3u + (uint32_t)fb : 0u) + (uint32_t)need1 + (uint32_t)need2 + (uint32_t)need3;
+      } else {
+        // ---- degenerate rate (k or bb outside (0, 1)): draw by draw ----
+        const double vk = ring_take(ring, gbase, pos, len, has_k);
+        const double vb = ring_take(ring, gbase, pos, len, has_b);
+        const double kp = k <= 0.0 ? 0.0 : k >= 1.0 ? 1.0 : vk;
+        double bp = bb <= 0.0 ? 0.0 : bb >= 1.0 ? 1.0 : vb;
+        bp = __dmul_rn(bp, 1.01);
+        const double u = ring_take(ring, gbase, pos, len, true);
+        const double uhr = ring_take(ring, gbase, pos, len, true);
+        const bool is_k = u < kp;
+        const bool is_bb = !is_k && (u < __dadd_rn(kp, bp));
+        const bool contact = !is_k && !is_bb;
+        const bool is_hr = contact && (uhr < P.pit_hr[side][pit]);
+        const bool bip = contact && !is_hr;
+        const double ubip = ring_take(ring, gbase, pos, len, bip);
+        uint32_t type = (uint32_t)(P.cdf_bip[0] <= ubip) + (uint32_t)(P.cdf_bip[1] <= ubip) + (uint32_t)(P.cdf_bip[2] <= ubip) +
+                        (uint32_t)(P.cdf_bip[3] <= ubip);
+        if (type > 3u) type = 3u;
+        const double uhit = ring_take(ring, gbase, pos, len, bip);
+        const bool hit = bip && (uhit < P.hit_prob[side][pit][slot][type]);
+        const double u7 = ring_take(ring, gbase, pos, len, bip);
+        const bool fb = bip && !hit && (u7 < 0.10);
+        const double u8 = ring_take(ring, gbase, pos, len, fb);
+        o = MLBSIM_OUT;
+        if (hit) o = MLBSIM_1B + (uint32_t)(P.cdf_hit[0] <= u7) + (uint32_t)(P.cdf_hit[1] <= u7) + (uint32_t)(P.cdf_hit[2] <= u7);
+        if (fb) o = MLBSIM_1B + (uint32_t)(P.cdf_fb[0] <= u8) + (uint32_t)(P.cdf_fb[1] <= u8);
+        if (is_hr) o = MLBSIM_HR;
+        if (is_bb) o = MLBSIM_BB;
+        if (is_k) o = MLBSIM_K;
+        is_out = (o == MLBSIM_K) || (o == MLBSIM_OUT);
+        is_1b = o == MLBSIM_1B;
+        const bool is_2b = o == MLBSIM_2B;
+        h1 = ring_take(ring, gbase, pos, len, (is_out && on1 && outs < 2u) || (is_1b && on2) || (is_2b && on1));
+        h2 = ring_take(ring, gbase, pos, len, is_1b && on1);
+        held = is_1b && on2 && !(h1 < 0.4);
+        h3 = ring_take(ring, gbase, pos, len, held && outs == 2u);
+      }
+      bool dA;
+      if (is_out) dA = h1 < 0.14;
+      else if (is_1b) dA = (h1 < 0.4) || (held && outs == 2u && h3 < 0.10);
+      else dA = h1 < 0.4;
+      const bool dB = h2 < 0.8;
+      const uint32_t ent = S.lut[(ob << 5) + (o << 2) + (dA ? 2u : 0u) + (dB ? 1u : 0u)];
+      hs = (hs & ~HS_OB) + HS_PA_ONE + ent;
+      pa_cur += 1ull << (9u * o);
+
+      cur += CX_NEXT_PA;
+      const uint32_t L = side ? L1 : L0;
+      const bool wrapped = (cur & CX_SLOT) == L;
+      if (wrapped) cur -= L;
+      if ((hs & HS_OVER) == 0u) {
+        if (wrapped && (cur & CX_TIER_MASK) != CX_TIER_MASK) cur += CX_TIER_ONE;   // :177-178
+      }
+    }
+
+    // (a lane whose half is over but whose next three entries have not landed yet keeps HS_OVER and comes back next round)
+    if ((hs & HS_OVER) != 0u && gchunk0 + ((gfirst + pos + 2u) >> 4) < ready_c) {
+      // ---------------- end of half inning (:242-250) ----------------
+      const uint32_t side = hidx & 1u;
+      uint32_t runs = (hs >> 16) & 63u;
+      const bool reached = (hs & HS_REACHED) != 0u;
+      // misc run, ghost run, reliever pick: at most three consecutive entries, loaded together
+      double bw[3];
+      ring_window<3>(ring, (gbase + pos) & (RING - 1u), pos, len, bw);
+      const bool need_m = reached && runs == 0u;
+      const double um = bw[0], ug = need_m ? bw[1] : bw[0];
+      const double upick = reached ? (need_m ? bw[2] : bw[1]) : bw[0];
+      pos += (uint32_t)need_m + (uint32_t)reached;
+      if (need_m && um < 0.011) runs += 1u;
+      if (reached && ug < 0.01) runs += 1u;
+      sc += runs << (side * 16u);
+      const uint32_t inning = (hidx >> 1) + 1u;
+      mlbsim_replay_game* const R = args.out + game;
+      if (runs) {
+        if (inning <= MLBSIM_REPLAY_MAX_INNINGS) {
+          uint8_t* dst = side ? R->home_runs : R->away_runs;
+          dst[inning - 1] = (uint8_t)(runs > 255u ? 255u : runs);
+        }
+      }
+      if (inning > MLBSIM_REPLAY_MAX_INNINGS) status |= MLBSIM_ST_INNINGS_OVERFLOW;
+      const uint32_t a = sc & 0xFFFFu, h = sc >> 16;
+      bool over = (side != 0u && hidx >= 17u && a != h) || (hidx == 16u && h > a);
+      // a tape that ran dry cannot end the game by itself (0.5 draws): stop after a bound (as the oracle does)
+      if (side != 0u && pos > len && inning >= 200u) over = true;
+      if (!over) {
+        hs = HS_NEW_HALF;
+        ++hidx;
+        { const uint32_t t = cur; cur = oth; oth = t; }
+        { const unsigned long long t = pa_cur; pa_cur = pa_oth; pa_oth = t; }
+        const uint32_t nb = side ? nb0 : nb1;     // staff that now takes the mound
+        if (nb != 0u && ((cur & CX_TIER_GE2) != 0u || cur >= ((uint32_t)91 << CX_PC_SHIFT))) {   // game_simulator.py:8-12
+          int idx = (int)upick;
+          ++pos;
+          idx = idx < 0 ? 0 : (idx >= (int)nb ? (int)nb - 1 : idx);
+          cur = (cur & CX_SLOT) | ((uint32_t)(idx + 1) << CX_PIT_SHIFT);
+          const uint32_t sh = side ? 0u : 8u;     // new side 0 -> home staff
+          const uint32_t cnt = (nused >> sh) & 255u;
+          if (cnt < MLBSIM_REPLAY_MAX_USED) (side ? R->used_home : R->used_away)[cnt] = (uint8_t)idx;
+          else status |= MLBSIM_ST_USED_OVERFLOW;
+          nused += 1u << sh;
+        }
+      } else {
+        if (pos > len) status |= MLBSIM_ST_TAPE_UNDERRUN;
+        // side at bat when the game ended: pa_cur belongs to it
+        const unsigned long long pa0 = side ? pa_oth : pa_cur, pa1 = side ? pa_cur : pa_oth;
+        reinterpret_cast<int4*>(R)[0] = make_int4((int)h, (int)a, (int)inning, (int)pos);
+        reinterpret_cast<int4*>(R)[1] = make_int4((int)(nused & 255u), (int)((nused >> 8) & 255u), (int)status, 0);
+#pragma unroll
+        for (int o = 0; o < MLBSIM_N_OUTCOMES; ++o) {
+          const uint16_t c0 = (uint16_t)((pa0 >> (9 * o)) & 511ull), c1 = (uint16_t)((pa1 >> (9 * o)) & 511ull);
+          if (c0) R->pa[0][o] = c0;
+          if (c1) R->pa[1][o] = c1;
+        }
+        hs = HS_DEAD;
+      }
+    }
+    __syncwarp();
+  }
+  if (pending) mbar_wait(mbar, phase);   // no copy may still be writing this block's shared memory when it exits
+}
+
+}  // namespace
+
+extern "C" __global__ void __launch_bounds__(MLBSIM_REPLAY_RING_THREADS, 1)
+mlbsim_replay_ring_kernel(const ReplayArgs args, unsigned long long* counter, uint32_t chunk) {
+  replay_ring_body<true>(args, counter, chunk);     // simulate_game(use_noise=True)
+}
+
+extern "C" __global__ void __launch_bounds__(MLBSIM_REPLAY_RING_THREADS, 1)
+mlbsim_replay_ring_nonoise_kernel(const ReplayArgs args, unsigned long long* counter, uint32_t chunk) {
+  replay_ring_body<false>(args, counter, chunk);
+}
