@@ -24,7 +24,6 @@ COMMON += os.environ.get("MLBSIM_NVCC_DEFS", "").split()   # e.g. "-DOPT_ANYSYNC
 UNITS = {
     "native_kernel.cu": [],
     "replay_flat_kernel.cu": ["-fmad=false"],
-    "replay_ring_kernel.cu": ["-fmad=false"],
     "summary_kernel.cu": [],
     "mlbsim_api.cu": [],
 }

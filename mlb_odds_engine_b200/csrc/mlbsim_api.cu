@@ -39,7 +39,6 @@ struct mlbsim_ctx {
   int threads_per_block = 0;
   int blocks_per_sm = 0;
   int occ_threads = -1, occ_blocks = 0;   // cached occupancy query of the native kernel
-  bool replay_flat = false;               // MLBSIM_REPLAY_KERNEL=flat: the LDG-window replay kernel (A/B measurements)
   uint64_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
@@ -113,14 +112,6 @@ int mlbsim_init(int device, mlbsim_ctx** out) {
   if ((e = cudaFuncSetAttribute(mlbsim_native_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)mlbsim_native_smem_bytes(MLBSIM_NATIVE_MAX_THREADS))) != cudaSuccess)
     return bail("cudaFuncSetAttribute", e);
-  {
-    const int ring_bytes = MLBSIM_REPLAY_RING_THREADS * MLBSIM_REPLAY_RING_LANE_BYTES;
-    if ((e = cudaFuncSetAttribute(mlbsim_replay_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_bytes)) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(mlbsim_replay_ring_nonoise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_bytes)) != cudaSuccess)
-      return bail("cudaFuncSetAttribute(replay)", e);
-    const char* rk = std::getenv("MLBSIM_REPLAY_KERNEL");
-    ctx->replay_flat = rk && std::strcmp(rk, "flat") == 0;
-  }
   *out = ctx;
   return MLBSIM_OK;
 }
@@ -426,20 +417,7 @@ int mlbsim_run_replay_dev(mlbsim_ctx* ctx, const mlbsim_params* params_host, con
   }
   CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
   CK(ctx, cudaMemsetAsync(out_dev, 0, sizeof(mlbsim_replay_game) * (size_t)n_games, ctx->stream));  // kernels write non-zero fields only
-  if (!ctx->replay_flat) {
-    // ring kernel: one block per SM (its tape rings fill the SM's shared memory)
-    const int threads = MLBSIM_REPLAY_RING_THREADS;
-    const int grid = ctx->prop.multiProcessorCount;
-    const size_t smem = (size_t)threads * MLBSIM_REPLAY_RING_LANE_BYTES;
-    const long long warps = (long long)grid * (threads / 32);
-    long long chunk = n_games / (warps * 4 + 1);
-    chunk = (chunk / 32) * 32;
-    if (chunk < 32) chunk = 32;
-    if (chunk > 256) chunk = 256;
-    CK(ctx, cudaMemsetAsync(ctx->counters_dev, 0, sizeof(unsigned long long), ctx->stream));
-    if (params_host->use_noise) mlbsim_replay_ring_kernel<<<grid, threads, smem, ctx->stream>>>(a, ctx->counters_dev, (uint32_t)chunk);
-    else mlbsim_replay_ring_nonoise_kernel<<<grid, threads, smem, ctx->stream>>>(a, ctx->counters_dev, (uint32_t)chunk);
-  } else {
+  {
     const int threads = MLBSIM_REPLAY_FLAT_THREADS;
     const int grid = ctx->prop.multiProcessorCount * MLBSIM_REPLAY_FLAT_BLOCKS;
     const long long warps = (long long)grid * (threads / 32);
@@ -471,7 +449,7 @@ int mlbsim_run_replay(mlbsim_ctx* ctx, const mlbsim_params* params, const double
   mlbsim_replay_game* out_dev = nullptr;
   int rc = MLBSIM_OK;
   cudaError_t e;
-  // (rounded up to whole 128-byte chunks: the ring kernel copies the tape chunk by chunk)
+  // (rounded up to whole 128-byte chunks + one: the kernel loads aligned 16-byte units of whole windows)
   if ((e = cudaMalloc(&tape_dev, sizeof(double) * (size_t)(((n_draws + 15) / 16) * 16 + 16))) != cudaSuccess ||
       (e = cudaMalloc(&off_dev, sizeof(uint64_t) * (size_t)(n_games + 1))) != cudaSuccess ||
       (e = cudaMalloc(&out_dev, sizeof(mlbsim_replay_game) * (size_t)n_games)) != cudaSuccess) {

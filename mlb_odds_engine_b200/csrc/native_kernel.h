@@ -57,20 +57,14 @@ extern "C" __global__ void mlbsim_native_kernel(const NativeArgs args);
 extern "C" __global__ void mlbsim_stage_tables_kernel(const mlbsim_table* tables, mlbsim_staged_table* staged, int n);
 extern "C" __global__ void mlbsim_replay_flat_kernel(const ReplayArgs args, unsigned long long* counter, uint32_t chunk);
 extern "C" __global__ void mlbsim_replay_flat_nonoise_kernel(const ReplayArgs args, unsigned long long* counter, uint32_t chunk);
-extern "C" __global__ void mlbsim_replay_ring_kernel(const ReplayArgs args, unsigned long long* counter, uint32_t chunk);
-extern "C" __global__ void mlbsim_replay_ring_nonoise_kernel(const ReplayArgs args, unsigned long long* counter, uint32_t chunk);
 extern "C" __global__ void mlbsim_summary_kernel(const mlbsim_hist* hist, mlbsim_summary* out);
 #endif
-// replay kernel fed by the bulk-copy engine: one block per SM, 640 bytes of tape ring per lane in dynamic shared memory
-#ifndef MLBSIM_REPLAY_RING_THREADS
-#define MLBSIM_REPLAY_RING_THREADS 320
-#endif
-#define MLBSIM_REPLAY_RING_LANE_BYTES 640
+
 size_t mlbsim_native_smem_bytes(int threads_per_block);
 #define MLBSIM_SUMMARY_THREADS 256
 #ifndef MLBSIM_REPLAY_FLAT_THREADS
 #define MLBSIM_REPLAY_FLAT_THREADS 256
 #endif
 #ifndef MLBSIM_REPLAY_FLAT_BLOCKS
-#define MLBSIM_REPLAY_FLAT_BLOCKS 3   /* 768 threads per SM at 80 registers (the 11-entry tape window lives in registers): measured best (profiles/r02_rp1.log) */
+#define MLBSIM_REPLAY_FLAT_BLOCKS 3   /* 768 threads per SM at 80 registers (the 11-entry tape window lives in registers): measured best (profiles/r02_rp1.log, r02_rp4.log) */
 #endif

@@ -8,7 +8,8 @@
 //     [beta_k] [beta_bb] u u_hr [u_bip u_hit (u_hit3 | u_fb [u_fb2])] [h1] [h2] [h3]
 // makes WHICH value a draw is depend on the values before it, but not WHERE the next few values are: a plate
 // appearance consumes at most eleven consecutive tape entries.  So every step first issues eleven INDEPENDENT 8-byte
-// loads of the window tape[pos .. pos+10] (one memory round trip per plate appearance, not one per draw), and the
+// loads of the window tape[pos .. pos+10] — as aligned 16-byte units, because a lane's load costs one L1 wavefront
+// whatever its width (one memory round trip per plate appearance, not one per draw, and half the wavefronts) — and the
 // grammar then only selects among registers: with both Beta draws present (every realistic rate) u, u_hr, u_bip ...
 // sit at fixed window slots, and the three base-running draws at one of three.  Degenerate rates (k or bb outside
 // (0, 1): no Beta draw, core/pa_simulator.py:23-32) fall back to draw-by-draw predicated loads.  The per-PA K / BB
@@ -81,10 +82,51 @@ __device__ __forceinline__ uint32_t lanemask_lt() {
 }
 
 // window read: entry pos + i of the lane's tape, 0.5 past the end (flagged later through pos > len)
-__device__ __forceinline__ double peek(const double* p, uint32_t at, uint32_t len) {
-  double v = 0.5;
-  if (at < len) asm volatile("ld.global.nc.L2::256B.f64 %0, [%1];" : "=d"(v) : "l"(p + at));
-  return v;
+#ifndef REPLAY_VEC
+#define REPLAY_VEC 2   /* tape entries per window load: 1 = LDG.64, 2 = LDG.128, 4 = LDG.256 (aligned units) */
+#endif
+
+// N consecutive entries from `pos` as ALIGNED vector loads: every lane's load costs one L1 wavefront whatever its width,
+// so 16- or 32-byte units cut the wavefronts of a window by that factor; the lane then shifts the window into place by
+// its misalignment (selects in registers).  Unguarded: the tape buffer is readable to the end of the 128-byte chunk
+// holding its last draw (mlbsim_run_replay pads its copy; mlbsim_run_replay_dev asks the caller to); entries at or
+// past the game's end read as 0.5 exactly like `take` — only a lane within N entries of its game's end pays for that.
+template <int N>
+__device__ __forceinline__ void peek_window(const double* p, uint32_t pos, uint32_t len, double (&w)[N]) {
+  const double* q = p + pos;
+#if REPLAY_VEC == 1
+#pragma unroll
+  for (int i = 0; i < N; ++i) asm volatile("ld.global.nc.L2::256B.f64 %0, [%1];" : "=d"(w[i]) : "l"(q + i));
+#elif REPLAY_VEC == 2
+  const uint32_t off = (uint32_t)(((uintptr_t)q >> 3) & 1u);      // 0 or 1 entries past a 16-byte boundary
+  const double* a = q - off;
+  constexpr int U = (N + 2) / 2;                                   // units covering [q - 1, q + N)
+  double buf[2 * U];
+#pragma unroll
+  for (int u = 0; u < U; ++u)
+    asm volatile("ld.global.nc.L2::256B.v2.f64 {%0, %1}, [%2];" : "=d"(buf[2 * u]), "=d"(buf[2 * u + 1]) : "l"(a + 2 * u));
+#pragma unroll
+  for (int i = 0; i < N; ++i) w[i] = off ? buf[i + 1] : buf[i];
+#else
+  const uint32_t off = (uint32_t)(((uintptr_t)q >> 3) & 3u);      // 0..3 entries past a 32-byte boundary
+  const double* a = q - off;
+  constexpr int U = (N + 3 + 3) / 4;                               // units covering [q - 3, q + N)
+  double buf[4 * U];
+#pragma unroll
+  for (int u = 0; u < U; ++u)
+    asm volatile("ld.global.nc.L2::256B.v4.f64 {%0, %1, %2, %3}, [%4];"
+                 : "=d"(buf[4 * u]), "=d"(buf[4 * u + 1]), "=d"(buf[4 * u + 2]), "=d"(buf[4 * u + 3]) : "l"(a + 4 * u));
+  double t[N + 1];
+#pragma unroll
+  for (int i = 0; i < N + 1; ++i) t[i] = (off & 2u) ? buf[i + 2] : buf[i];
+#pragma unroll
+  for (int i = 0; i < N; ++i) w[i] = (off & 1u) ? t[i + 1] : t[i];
+#endif
+  if (pos + (uint32_t)N > len) {
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+      if (pos + (uint32_t)i >= len) w[i] = 0.5;
+  }
 }
 
 // predicated tape read: past-the-end reads yield 0.5 (flagged later through pos > len)
@@ -186,8 +228,7 @@ __device__ __forceinline__ void replay_body(const ReplayArgs& args, unsigned lon
         // ---- window path: every draw of this plate appearance sits at a known slot of tape[pos .. pos + B + 8] ----
         constexpr int B = NOISE ? 2 : 0;
         double w[B + 9];
-#pragma unroll
-        for (int i = 0; i < B + 9; ++i) w[i] = peek(tp, pos + (uint32_t)i, len);
+        peek_window<B + 9>(tp, pos, len, w);
         const double kp = NOISE ? w[0] : k;
         const double bp = __dmul_rn(NOISE ? w[1] : bb, 1.01);
         const double u = w[B], uhr = w[B + 1];                          // u_hr is always consumed (:126)
@@ -283,7 +324,9 @@ __device__ __forceinline__ void replay_body(const ReplayArgs& args, unsigned lon
       uint32_t runs = (hs >> 16) & 63u;
       const bool reached = (hs & HS_REACHED) != 0u;
       // misc run, ghost run, reliever pick: at most three consecutive entries, loaded together
-      const double b0 = peek(tp, pos, len), b1 = peek(tp, pos + 1u, len), b2 = peek(tp, pos + 2u, len);
+      double bw[3];
+      peek_window<3>(tp, pos, len, bw);
+      const double b0 = bw[0], b1 = bw[1], b2 = bw[2];
       const bool need_m = reached && runs == 0u;
       const double um = b0, ug = need_m ? b1 : b0;
       const double upick = reached ? (need_m ? b2 : b1) : b0;
