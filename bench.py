@@ -263,9 +263,14 @@ def run_reference(args):
         per_worker = max(len(ms), int(rate1 * step_seconds * 0.8))
         per_worker -= per_worker % len(ms)
         per_worker = max(per_worker, len(ms))
+        # a step = 4 tasks per worker process handed out dynamically, so that one slow core does not hold the step up
+        slices = 4
+        per_task = max(len(ms), (per_worker // slices) - (per_worker // slices) % len(ms))
+        per_worker = per_task * slices
         with mp.get_context("fork").Pool(procs) as pool:
             def step(i):
-                return sum(pool.map(rh._fixed_worker, [(ms, per_worker, args.seed * 100_003 + i * procs + w, True) for w in range(procs)]))
+                jobs = [(ms, per_task, args.seed * 100_003 + (i * procs + w) * slices + t, True) for w in range(procs) for t in range(slices)]
+                return sum(pool.imap_unordered(rh._fixed_worker, jobs))
             for i in range(args.warmup):
                 step(i)
             t0 = time.perf_counter()
