@@ -50,14 +50,15 @@ def matchups(name: str):
     return sweep.grid_matchups(base, "home", **axes)[0]
 
 
-def build_tables(name: str) -> np.ndarray:
-    """TABLE_DTYPE array of a workload, built the way a user would (the sweep through sweep.grid_tables)."""
+def build_tables(name: str, alias_fn=None) -> np.ndarray:
+    """TABLE_DTYPE array of a workload, built the way a user would (the sweep through sweep.grid_tables).  `alias_fn`:
+    the device builder of the alias rows (`Context.alias_rows`) where a GPU is at hand — same bytes either way."""
     from mlb_odds_engine_b200 import sweep, tables
 
     if name == "sweep":
         base, axes = sweep_grid()
-        return sweep.grid_tables(base, "home", **axes)[0]
-    return tables.build_tables(matchups(name))
+        return sweep.grid_tables(base, "home", alias_fn=alias_fn, **axes)[0]
+    return tables.build_tables(matchups(name), alias_fn=alias_fn)
 
 
 def digest(records: np.ndarray) -> str:

@@ -185,6 +185,13 @@ int mlbsim_upload_tables(mlbsim_ctx* ctx, const mlbsim_table* tables, int n_matc
  * must stay <= 4096. */
 int mlbsim_set_matchup_base(mlbsim_ctx* ctx, int base);
 
+/* Table construction helper: Walker alias rows for `n_rows` probability rows of `n_own` (7 or 8) float64 entries each
+ * (host pointers; out receives n_rows * 8 words, entry = cut29 << 3 | alias as in mlbsim_table.alias).  Bit-identical
+ * to the host builder (mlb_odds_engine_b200/tables.py::alias_rows): one thread per row runs the same float64
+ * operations in the same order.  Replaces nothing in the reference (it samples with np.random.choice per PA,
+ * core/pa_simulator.py:54-79); it takes the per-row Python/numpy work out of building 10^3-point sweeps. */
+int mlbsim_alias_rows(mlbsim_ctx* ctx, const double* probs_host, int n_rows, int n_own, uint32_t* out_host);
+
 /* Native-RNG mode: for every uploaded matchup m in [matchup_lo, matchup_hi) simulate the sims
  * [sim_lo, sim_hi) — the loop of cli/run_distribution_simulator.py:368-382 — and ADD the results
  * into hist_dev[m - matchup_lo] (device memory, caller-allocated, caller-zeroed).  Sim i of

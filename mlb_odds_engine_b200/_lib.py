@@ -20,6 +20,7 @@ SYMBOLS = [
     "mlbsim_run_persim", "mlbsim_malloc", "mlbsim_free", "mlbsim_memset", "mlbsim_memcpy_h2d", "mlbsim_memcpy_d2h",
     "mlbsim_launch_count", "mlbsim_set_launch_config", "mlbsim_last_kernel_ms",
     "mlbsim_summarize", "mlbsim_run_native_summary_host", "mlbsim_allreduce", "mlbsim_set_matchup_base",
+    "mlbsim_alias_rows",
 ]
 
 ERR_NAMES = {1: "CUDA", 2: "ARG", 3: "TABLE", 4: "NO_DEVICE", 5: "STATE"}
@@ -88,6 +89,7 @@ def load() -> ctypes.CDLL:
         "mlbsim_run_native_summary_host": (i32, [vp, i32, i32, u64, u64, u64, vp, u32]),
         "mlbsim_allreduce": (i32, [vp, vp, vp, i32]),
         "mlbsim_set_matchup_base": (i32, [vp, i32]),
+        "mlbsim_alias_rows": (i32, [vp, vp, i32, i32, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(L, name)  # AttributeError if the library lacks a declared symbol
@@ -185,6 +187,14 @@ class Context:
         self._ck(self.L.mlbsim_memcpy_d2h(self.h, _ptr(host), ctypes.c_void_p(dev_ptr), host.nbytes))
 
     # ---- compute ----
+    def alias_rows(self, probs: np.ndarray) -> np.ndarray:
+        """Device form of `tables.alias_rows` ([N, 7 or 8] float64 -> [N, 8] uint32), bit-identical to it."""
+        probs = np.ascontiguousarray(probs, dtype=np.float64)
+        n, n_own = probs.shape
+        out = np.zeros((n, _abi.ROW_WORDS), dtype=np.uint32)
+        self._ck(self.L.mlbsim_alias_rows(self.h, _ptr(probs), n, n_own, _ptr(out)))
+        return out
+
     def upload_tables(self, tables: np.ndarray):
         tables = np.ascontiguousarray(np.atleast_1d(tables))
         assert tables.dtype == _abi.TABLE_DTYPE

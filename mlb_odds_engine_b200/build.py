@@ -25,6 +25,7 @@ UNITS = {
     "native_kernel.cu": [],
     "replay_flat_kernel.cu": ["-fmad=false"],
     "summary_kernel.cu": [],
+    "alias_kernel.cu": ["-fmad=false"],
     "mlbsim_api.cu": [],
 }
 DEPS = ["native_kernel.h", "philox.cuh", "game_rules.cuh", os.path.join(INCLUDE, "mlbsim.h")]

@@ -385,6 +385,36 @@ int mlbsim_allreduce(mlbsim_ctx* ctx, void* nccl_comm, mlbsim_hist* hist_dev, in
   return MLBSIM_OK;
 }
 
+int mlbsim_alias_rows(mlbsim_ctx* ctx, const double* probs_host, int n_rows, int n_own, uint32_t* out_host) {
+  if (!ctx) return MLBSIM_ERR_ARG;
+  if (!probs_host || !out_host || n_rows < 0 || (n_own != 7 && n_own != 8)) return fail(ctx, MLBSIM_ERR_ARG, "mlbsim_alias_rows: bad argument");
+  if (n_rows == 0) return MLBSIM_OK;
+  CK(ctx, cudaSetDevice(ctx->device));
+  double* p_dev = nullptr;
+  uint32_t* o_dev = nullptr;
+  cudaError_t e;
+  if ((e = cudaMalloc(&p_dev, sizeof(double) * (size_t)n_rows * n_own)) != cudaSuccess ||
+      (e = cudaMalloc(&o_dev, sizeof(uint32_t) * (size_t)n_rows * MLBSIM_ROW_WORDS)) != cudaSuccess) {
+    cudaFree(p_dev);
+    ctx->err = std::string("cudaMalloc: ") + cudaGetErrorString(e);
+    return MLBSIM_ERR_CUDA;
+  }
+  if ((e = cudaMemcpyAsync(p_dev, probs_host, sizeof(double) * (size_t)n_rows * n_own, cudaMemcpyHostToDevice, ctx->stream)) == cudaSuccess) {
+    mlbsim_alias_rows_kernel<<<(n_rows + 127) / 128, 128, 0, ctx->stream>>>(p_dev, n_rows, n_own, o_dev);
+    ctx->launches++;
+    if ((e = cudaGetLastError()) == cudaSuccess &&
+        (e = cudaMemcpyAsync(out_host, o_dev, sizeof(uint32_t) * (size_t)n_rows * MLBSIM_ROW_WORDS, cudaMemcpyDeviceToHost, ctx->stream)) == cudaSuccess)
+      e = cudaStreamSynchronize(ctx->stream);
+  }
+  cudaFree(p_dev);
+  cudaFree(o_dev);
+  if (e != cudaSuccess) {
+    ctx->err = std::string("mlbsim_alias_rows: ") + cudaGetErrorString(e);
+    return MLBSIM_ERR_CUDA;
+  }
+  return MLBSIM_OK;
+}
+
 int mlbsim_last_kernel_ms(mlbsim_ctx* ctx, float* ms) {
   if (!ctx || !ms) return MLBSIM_ERR_ARG;
   if (!ctx->timed) return fail(ctx, MLBSIM_ERR_STATE, "no timed launch yet");

@@ -58,6 +58,7 @@ extern "C" __global__ void mlbsim_stage_tables_kernel(const mlbsim_table* tables
 extern "C" __global__ void mlbsim_replay_flat_kernel(const ReplayArgs args, unsigned long long* counter, uint32_t chunk);
 extern "C" __global__ void mlbsim_replay_flat_nonoise_kernel(const ReplayArgs args, unsigned long long* counter, uint32_t chunk);
 extern "C" __global__ void mlbsim_summary_kernel(const mlbsim_hist* hist, mlbsim_summary* out);
+extern "C" __global__ void mlbsim_alias_rows_kernel(const double* probs, int n_rows, int n_own, uint32_t* out);
 #endif
 
 size_t mlbsim_native_smem_bytes(int threads_per_block);

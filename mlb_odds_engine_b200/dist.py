@@ -119,7 +119,7 @@ class ShardedSimulator:
         from . import tables
 
         ms = [tables.as_matchup(m, use_noise) for m in matchups]
-        return self.load_tables(tables.build_tables(ms), ms)
+        return self.load_tables(tables.build_tables(ms, alias_fn=self.ctx.alias_rows), ms)
 
     def load_tables(self, tbl, matchups=None):
         """`tbl`: TABLE_DTYPE array of the WHOLE job (may live in pinned memory); one H2D copy of what this rank needs."""

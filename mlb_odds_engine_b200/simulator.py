@@ -100,7 +100,7 @@ class GpuSimulator:
     def load_matchups(self, matchups, use_noise: bool = True):
         """`matchups`: iterable of `simulate_game` keyword dicts (or tables.Matchup)."""
         self.matchups = [tables.as_matchup(m, use_noise) for m in matchups]
-        self._tables = tables.build_tables(self.matchups)
+        self._tables = tables.build_tables(self.matchups, alias_fn=self.ctx.alias_rows)   # alias rows on the device (bit-identical)
         self.ctx.upload_tables(self._tables)
         return self
 

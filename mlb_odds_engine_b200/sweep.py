@@ -49,11 +49,12 @@ def grid_matchups(base: dict, side: str = "home", project: bool = False, **axes)
     return out, points
 
 
-def grid_tables(base: dict, side: str = "home", project: bool = False, use_noise: bool = True, **axes):
+def grid_tables(base: dict, side: str = "home", project: bool = False, use_noise: bool = True, alias_fn=None, **axes):
     """The device tables of `grid_matchups(base, side, project, **axes)` without materialising one dict per grid
     point: the base matchup is parsed once, the swept pitcher's numbers are written into stacked arrays and
     `tables.tables_from_arrays` builds every table in one pass (1 024 points: ~0.35 s instead of ~1.2 s).
-    Byte-identical to `tables.build_tables(grid_matchups(...)[0])`.  Returns (TABLE_DTYPE[n], points)."""
+    Byte-identical to `tables.build_tables(grid_matchups(...)[0])`.  `alias_fn`: e.g. `Context.alias_rows`, the device
+    builder of the alias rows (same bytes).  Returns (TABLE_DTYPE[n], points)."""
     names = list(axes)
     if project and "hr_pa_projected" in names:
         raise ValueError("hr_pa_projected cannot be a grid axis when project=True (it is recomputed)")
@@ -98,7 +99,7 @@ def grid_tables(base: dict, side: str = "home", project: bool = False, use_noise
             A["hit_prob"][g, s, 0, :L] = cache[key]
     # (axes the hot path never reads — Stuff+, ISO, HR/FB without project=True — leave every table equal to the base
     # table, as in the reference)
-    return tables.tables_from_arrays(A), points
+    return tables.tables_from_arrays(A, alias_fn=alias_fn), points
 
 
 def sensitivity_matchups(field: str, values, project: bool = False) -> list[dict]:

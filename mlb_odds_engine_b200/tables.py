@@ -395,7 +395,7 @@ def alias_row(p) -> np.ndarray:
 def alias_rows(P) -> np.ndarray:
     """`alias_row` for N rows at once ([N, 7 or 8] probabilities -> [N, 8] uint32): the same stack discipline
     (highest column first) run in lock step over all rows, so the result is identical entry for entry."""
-    P = np.asarray(P, dtype=np.float64)
+    P = np.ascontiguousarray(P, dtype=np.float64)   # (C order: the row sums below then round like the device builder's)
     N, n_own = P.shape
     q = np.zeros((N, ALIAS_COLS))
     q[:, :n_own] = P * ALIAS_COLS / P.sum(axis=1)[:, None]
@@ -526,16 +526,32 @@ def stack_matchups(ms) -> dict:
 def _cdf_tensor(A, valid, fl):
     """Cumulative outcome law of every valid (matchup, side, pitcher, tier, slot) row at fatigue level `fl`
     (0 = at most 75 pitches): the arithmetic of `outcome_cdf_batch`, same operations in the same order, evaluated
-    on the gathered rows.  Returns float64 [n_valid, 6]."""
+    once per DISTINCT row of inputs.  Returns float64 [n_valid, 6] and the row coordinates."""
     M, S, P, T, B = np.nonzero(valid)
-    pen = np.asarray(TTO_PENALTY)[T]
-    ak = A["pit_k"][M, S, P] * (1 - pen) * (1.0 - 0.02 * fl)
-    ab = A["pit_bb"][M, S, P] * (1 + pen) * (1.0 + 0.03 * fl)
-    k = (A["bat_k"][M, S, B] + ak) / 2 * A["k_mod"][M]
-    bb = (A["bat_bb"][M, S, B] + ab) / 2 * A["bb_mod"][M]
-    noise = A["use_noise"][M]
-    pk = np.empty(len(M))
-    pkbb = np.empty(len(M))
+    X = np.empty((len(M), 13))
+    X[:, 0], X[:, 1], X[:, 2] = A["pit_k"][M, S, P], A["pit_bb"][M, S, P], A["pit_hr"][M, S, P]
+    X[:, 3], X[:, 4] = A["bat_k"][M, S, B], A["bat_bb"][M, S, B]
+    X[:, 5], X[:, 6], X[:, 7] = A["k_mod"][M], A["bb_mod"][M], A["use_noise"][M]
+    X[:, 8] = T
+    X[:, 9:13] = A["hit_prob"][M, S, P, B]
+    u = _unique_rows(X) if len(M) >= 4096 else None
+    if u is None:
+        return _cdf_rows(X, fl), (M, S, P, T, B)
+    index, inverse = u
+    return _cdf_rows(X[index], fl)[inverse], (M, S, P, T, B)
+
+
+def _cdf_rows(X, fl):
+    """Rows of [pit_k, pit_bb, pit_hr, bat_k, bat_bb, k_mod, bb_mod, use_noise, tier, hit_prob x 4] -> cumulative
+    outcome law [n, 6] (K, K+BB, +1B, +2B, +3B, +HR)."""
+    pen = np.asarray(TTO_PENALTY)[X[:, 8].astype(np.int64)]
+    ak = X[:, 0] * (1 - pen) * (1.0 - 0.02 * fl)
+    ab = X[:, 1] * (1 + pen) * (1.0 + 0.03 * fl)
+    k = (X[:, 3] + ak) / 2 * X[:, 5]
+    bb = (X[:, 4] + ab) / 2 * X[:, 6]
+    noise = X[:, 7] != 0.0
+    pk = np.empty(len(X))
+    pkbb = np.empty(len(X))
     for flag in (True, False):
         sel = noise == flag
         if sel.any():
@@ -545,15 +561,37 @@ def _cdf_tensor(A, valid, fl):
     w_bip = np.diff(np.concatenate([[0.0], cdf_bip]))
     h = np.diff(np.concatenate([[0.0], cdf_hit]))
     f = np.diff(np.concatenate([[0.0], cdf_fb]))
-    hr = np.clip(A["pit_hr"][M, S, P], 0.0, 1.0)
-    hp = A["hit_prob"][M, S, P, B]
+    hr = np.clip(X[:, 2], 0.0, 1.0)
+    hp = X[:, 9:13]
     ph = hp[..., 0] * w_bip[0] + hp[..., 1] * w_bip[1] + hp[..., 2] * w_bip[2] + hp[..., 3] * w_bip[3]   # fixed order
     s1 = (1 - hr) * (ph * h[0] + (1 - ph) * INFIELD_FALLBACK * f[0])
     s2 = (1 - hr) * (ph * h[1] + (1 - ph) * INFIELD_FALLBACK * f[1])
     s3 = (1 - hr) * ph * h[2]
     c = np.stack([pk, pkbb, pkbb + contact * s1, pkbb + contact * (s1 + s2), pkbb + contact * (s1 + s2 + s3),
                   pkbb + contact * (s1 + s2 + s3 + hr)], axis=1)
-    return np.minimum(np.maximum.accumulate(c, axis=1), 1.0), (M, S, P, T, B)
+    return np.minimum(np.maximum.accumulate(c, axis=1), 1.0)
+
+
+_HASH_MULT = None
+
+
+def _unique_rows(X: np.ndarray):
+    """(index, inverse) such that X[index][inverse] == X, found through a 64-bit multiplicative hash of the rows' bit
+    patterns (one pass over the data instead of a lexicographic sort of 100-byte rows) and verified exactly; None when
+    nothing repeats or — never observed — two different rows collide."""
+    global _HASH_MULT
+    n, k = X.shape
+    if _HASH_MULT is None or len(_HASH_MULT) < k:
+        _HASH_MULT = np.random.default_rng(0x6D6C62).integers(1, 2**63, size=max(k, 32), dtype=np.uint64) | np.uint64(1)
+    bits = np.ascontiguousarray(X, dtype=np.float64).view(np.uint64)
+    with np.errstate(over="ignore"):
+        h = (bits * _HASH_MULT[None, :k]).sum(axis=1, dtype=np.uint64)
+    _, index, inverse = np.unique(h, return_index=True, return_inverse=True)
+    if len(index) > 0.8 * n:
+        return None
+    if not np.array_equal(bits[index][inverse], bits):
+        return None
+    return index, inverse.reshape(-1)
 
 
 class MatchupCannotScore(ValueError):
@@ -561,11 +599,14 @@ class MatchupCannotScore(ValueError):
     reference loops forever on such input (core/game_simulator.py:110-111); tables are refused instead."""
 
 
-def tables_from_arrays(A: dict, validate: bool = True) -> np.ndarray:
+def tables_from_arrays(A: dict, validate: bool = True, alias_fn=None) -> np.ndarray:
     """`mlbsim_table` records (include/mlbsim.h) for a batch of matchups given as stacked arrays (`stack_matchups`):
     alias rows for every reachable (side, pitcher, TTO tier, lineup slot) and, for starters that are never replaced,
     31-bit thresholds with pitch-count slopes.  One pass of the noise integral and one of the alias construction
-    over the rows of the whole batch; no per-matchup Python."""
+    over the DISTINCT rows of the whole batch (a sweep over one pitcher repeats the other side's rows in every grid
+    point); no per-matchup Python.  `alias_fn`: a drop-in for `alias_rows`, e.g. `Context.alias_rows` (the device builder,
+    bit-identical)."""
+    alias_fn = alias_fn or alias_rows
     n = len(A["use_noise"])
     out = np.zeros(n, dtype=_abi.TABLE_DTYPE)
     if n == 0:
@@ -587,7 +628,11 @@ def tables_from_arrays(A: dict, validate: bool = True) -> np.ndarray:
         if not can_reach.all():
             raise MatchupCannotScore(f"matchup(s) {np.nonzero(~can_reach)[0][:8].tolist()}: no plate appearance of either side "
                                      "can put a runner on base, the game would never end")
-    alias[where] = alias_rows(outcome_variants(probs))
+    u = _unique_rows(probs) if len(probs) >= 4096 else None
+    if u is None:
+        alias[where] = alias_fn(outcome_variants(probs))
+    else:
+        alias[where] = alias_fn(outcome_variants(probs[u[0]]))[u[1]]
     # A starter without a bullpen is never replaced: his pitch count passes 75 (core/fatigue_modeling.py:38).  Such a
     # matchup is flagged and BOTH of its starters get pitch-count rows: one who has a bullpen normally leaves at his third
     # time through the order, long before 75 pitches, but lineup wraps that coincide with the end of a half do not
@@ -597,7 +642,7 @@ def tables_from_arrays(A: dict, validate: bool = True) -> np.ndarray:
     fat = valid & (pit == 0) & flagged[:, None, None, None, None]
     if fat.any():
         c1, (M, S, P, T, B) = _cdf_tensor(A, fat, max(0.0, SLOPE_SPAN / 25))
-        c0f, _ = _cdf_tensor(A, fat, 0.0)
+        c0f = c0[fat[where]]            # the 75-pitch law of the same rows, already computed above (same row order)
         q0, q1 = _quantise(c0f), _quantise(c1)
         fthr[M, S, T, B, :6] = q0
         fslope[M, S, T, B, :6] = np.round((q1.astype(np.int64) - q0.astype(np.int64)) / SLOPE_SPAN)
@@ -608,10 +653,11 @@ def tables_from_arrays(A: dict, validate: bool = True) -> np.ndarray:
     return out
 
 
-def build_tables(matchups, use_noise=True, validate: bool = True) -> np.ndarray:
+def build_tables(matchups, use_noise=True, validate: bool = True, alias_fn=None) -> np.ndarray:
     """Tables for a batch of matchups (dicts take `use_noise` as the default for a missing key).  `validate=False`
-    skips the can-anybody-score check (tests of the kernel's own termination guard)."""
+    skips the can-anybody-score check (tests of the kernel's own termination guard); `alias_fn`: see
+    `tables_from_arrays`."""
     ms = [m if isinstance(m, Matchup) else as_matchup(m, use_noise) for m in matchups]
     if not ms:
         return np.zeros(0, dtype=_abi.TABLE_DTYPE)
-    return tables_from_arrays(stack_matchups(ms), validate=validate)
+    return tables_from_arrays(stack_matchups(ms), validate=validate, alias_fn=alias_fn)
