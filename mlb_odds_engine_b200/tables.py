@@ -526,7 +526,8 @@ def stack_matchups(ms) -> dict:
 def _cdf_tensor(A, valid, fl):
     """Cumulative outcome law of every valid (matchup, side, pitcher, tier, slot) row at fatigue level `fl`
     (0 = at most 75 pitches): the arithmetic of `outcome_cdf_batch`, same operations in the same order, evaluated
-    once per DISTINCT row of inputs.  Returns float64 [n_valid, 6] and the row coordinates."""
+    once per DISTINCT row of inputs.  Returns (float64 [n_distinct, 6], inverse | None, row coordinates): row i of the
+    valid rows has the law `c[inverse[i]]` (`c[i]` when nothing repeats)."""
     M, S, P, T, B = np.nonzero(valid)
     X = np.empty((len(M), 13))
     X[:, 0], X[:, 1], X[:, 2] = A["pit_k"][M, S, P], A["pit_bb"][M, S, P], A["pit_hr"][M, S, P]
@@ -536,9 +537,9 @@ def _cdf_tensor(A, valid, fl):
     X[:, 9:13] = A["hit_prob"][M, S, P, B]
     u = _unique_rows(X) if len(M) >= 4096 else None
     if u is None:
-        return _cdf_rows(X, fl), (M, S, P, T, B)
+        return _cdf_rows(X, fl), None, (M, S, P, T, B)
     index, inverse = u
-    return _cdf_rows(X[index], fl)[inverse], (M, S, P, T, B)
+    return _cdf_rows(X[index], fl), inverse, (M, S, P, T, B)
 
 
 def _cdf_rows(X, fl):
@@ -619,20 +620,17 @@ def tables_from_arrays(A: dict, validate: bool = True, alias_fn=None) -> np.ndar
     alias = np.zeros((n,) + _abi.TABLE_DTYPE["alias"].shape, dtype=np.uint32)   # unused rows: always K (never reached)
     fthr = np.full((n,) + _abi.TABLE_DTYPE["fthr"].shape, 2147483648, dtype=np.uint32)
     fslope = np.zeros((n,) + _abi.TABLE_DTYPE["fslope"].shape, dtype=np.int32)
-    c0, where = _cdf_tensor(A, valid, 0.0)
-    probs = np.diff(np.concatenate([np.zeros((len(c0), 1)), c0, np.ones((len(c0), 1))], axis=1), axis=1)
+    c0, inv0, where = _cdf_tensor(A, valid, 0.0)
+    probs = np.diff(np.concatenate([np.zeros((len(c0), 1)), c0, np.ones((len(c0), 1))], axis=1), axis=1)   # distinct rows
+    expand = (lambda x: x) if inv0 is None else (lambda x: x[inv0])
     if validate:
         # a matchup terminates with probability 1 iff somebody can reach base (K = column 0, OUT = column 6)
         can_reach = np.zeros(n, dtype=bool)
-        np.logical_or.at(can_reach, where[0], (probs[:, 0] + probs[:, 6]) < 1.0)
+        np.logical_or.at(can_reach, where[0], expand((probs[:, 0] + probs[:, 6]) < 1.0))
         if not can_reach.all():
             raise MatchupCannotScore(f"matchup(s) {np.nonzero(~can_reach)[0][:8].tolist()}: no plate appearance of either side "
                                      "can put a runner on base, the game would never end")
-    u = _unique_rows(probs) if len(probs) >= 4096 else None
-    if u is None:
-        alias[where] = alias_fn(outcome_variants(probs))
-    else:
-        alias[where] = alias_fn(outcome_variants(probs[u[0]]))[u[1]]
+    alias[where] = expand(alias_fn(outcome_variants(probs)))
     # A starter without a bullpen is never replaced: his pitch count passes 75 (core/fatigue_modeling.py:38).  Such a
     # matchup is flagged and BOTH of its starters get pitch-count rows: one who has a bullpen normally leaves at his third
     # time through the order, long before 75 pitches, but lineup wraps that coincide with the end of a half do not
@@ -641,8 +639,10 @@ def tables_from_arrays(A: dict, validate: bool = True, alias_fn=None) -> np.ndar
     flagged = (A["bullpen_len"] == 0).any(axis=1)
     fat = valid & (pit == 0) & flagged[:, None, None, None, None]
     if fat.any():
-        c1, (M, S, P, T, B) = _cdf_tensor(A, fat, max(0.0, SLOPE_SPAN / 25))
-        c0f = c0[fat[where]]            # the 75-pitch law of the same rows, already computed above (same row order)
+        c1, inv1, (M, S, P, T, B) = _cdf_tensor(A, fat, max(0.0, SLOPE_SPAN / 25))
+        if inv1 is not None:
+            c1 = c1[inv1]
+        c0f = expand(c0)[fat[where]]    # the 75-pitch law of the same rows, already computed above (same row order)
         q0, q1 = _quantise(c0f), _quantise(c1)
         fthr[M, S, T, B, :6] = q0
         fslope[M, S, T, B, :6] = np.round((q1.astype(np.int64) - q0.astype(np.int64)) / SLOPE_SPAN)
