@@ -32,8 +32,11 @@ def pricing_pool(workers: int):
 
         if _POOL is not None:
             _POOL[1].shutdown(wait=False)
+        import atexit
+
         ex = ProcessPoolExecutor(workers, mp_context=mp.get_context("spawn"))
         list(ex.map(_warm, range(workers)))          # import numpy / the package in every worker now
+        atexit.register(ex.shutdown, wait=True, cancel_futures=True)   # before the interpreter tears modules down
         _POOL = (workers, ex)
     return _POOL[1]
 
