@@ -32,7 +32,7 @@
 #include "native_kernel.h"
 #include "philox.cuh"
 
-// tuning switches (scripts/variant_sweep.sh builds one library per set of -D switches; results under profiles/)
+// tuning switches (scripts/build_variants.py builds one library per set of -D switches, scripts/variant_bench.sh benches them; results under profiles/)
 #ifndef OPT_UNROLL
 #define OPT_UNROLL 5   /* plate appearances per round: one refill check and one boundary pass per round (3/4/5/6 measured: profiles/r02_v15_variants.log) */
 #endif
@@ -379,7 +379,7 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
       // (w0 << 3) < entry — the low 29 bits of w0 against the cut, the entry's alias bits breaking the (2^-29) tie.
       const uint32_t col = w0 >> 29;
       const uint32_t row = cur & CX_ROW_BYTES;
-#ifdef MLBSIM_DEBUG_BOUNDS   // (compute-sanitizer stand-in: scripts/debug_bounds.sh runs the GPU suite with these traps)
+#ifdef MLBSIM_DEBUG_BOUNDS   // (compute-sanitizer stand-in: scripts/r02_cycle.sh runs the GPU suite on a build with these traps)
       {
         const uint32_t sd = hidx & 1u, Lc = sd ? L1 : L0, nbp = sd ? nb1 : nb0, bias = 16u - Lc;
         const uint32_t slotp = (cur & CX_SLOT) >> CX_SLOT_SHIFT, pit = (cur >> CX_PIT_SHIFT) & 7u;
