@@ -444,12 +444,11 @@ def main():
     sampler.start()          # already running through the warm-up, so the timed region is covered from its first ms
     # The W warm-up steps of the contract, preceded by up to 0.3 s of the same steps when W of them would be shorter than
     # that: an idle GPU needs tens of milliseconds to reach its boost clock, and W = 3 steps of this kernel are 10 ms.
-    prewarm_steps, t_pre = 0, time.perf_counter()
-    while time.perf_counter() - t_pre < 0.3:
+    # (a step COUNT, the same on every rank — the steps hold a collective — sized to ~0.3 s at 3 x 10^9 games/s)
+    prewarm_steps = min(400, max(3, int(1e9 / max(1, n_m * sims_per_gpu))))
+    for _ in range(prewarm_steps):
         device_step()
         flush.fill_(1)
-        torch.cuda.synchronize()
-        prewarm_steps += 1
     for _ in range(args.warmup):
         device_step()
         flush.fill_(1)
@@ -579,7 +578,7 @@ def main():
                    "parallelism": f"sim-index shards x{world}, uint64 histogram all-reduce" if world > 1 else "1 GPU",
                    "l2": "256 MB device buffer rewritten between timed iterations (L2 flush); every step simulates a fresh sim-index range",
                    "threads_per_block": args.threads_per_block or 640, "table_build_ms_once": 1e3 * t_build,
-                   "prewarm": f"{prewarm_steps} untimed steps (0.3 s) before the {args.warmup} warm-up steps: clock ramp"},
+                   "prewarm": f"{prewarm_steps} untimed steps (~0.3 s) before the {args.warmup} warm-up steps: clock ramp"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(tbl.nbytes),
                 "d2h_bytes_per_step": int(n_m * e2e_out_bytes)},
         "parity": parity,
