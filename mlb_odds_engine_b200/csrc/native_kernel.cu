@@ -17,11 +17,14 @@
 //     from a global counter.  Sim i draws Philox2x32-10 blocks with counter (i, draw number,
 //     kind, matchup) and a key derived from the seed (philox.cuh), so which lane / block / GPU
 //     runs it is irrelevant to its result;
-//   * the per-matchup alias table (28 KB as staged: rows padded to 16 lineup slots, one word read
-//     per PA), the transition LUT (5 KB) and the five joint (away, home) histograms (20 KB of u32
-//     bins) live in shared memory; histograms are flushed to the uint64 device totals once per
-//     (block, matchup).  The state words are laid out so that table addresses are bit fields of the
-//     state (see the "side context" and "half-inning state" comments below);
+//   * the per-matchup alias table (32 KB, rows at [side][pitcher 8][tier][16 slots], one word read per PA; it
+//     arrives as ONE cp.async.bulk copy of the image mlbsim_stage_tables_kernel laid out at upload time, completion on
+//     an mbarrier), the transition LUT (4.6 KB), the lineup-wrap table (2.5 KB) and the five joint (away, home)
+//     histograms (20 KB of u32 bins) live in shared memory; PA outcomes are counted per warp (ATOMS.POPC.INC merges
+//     the lanes that hit the same counter); everything is flushed to the uint64 device totals once per (block,
+//     matchup).  The state words are laid out so that table addresses are bit fields of the state and a plate
+//     appearance is a handful of adds (see the "side context" and "half-inning state" comments below); a lineup wrap
+//     costs nothing inside a round (repeated table rows) and one table lookup at its end;
 //   * no tensor cores: there is no dense contraction in this path.
 #include <cuda_runtime.h>
 #include <stddef.h>
