@@ -379,7 +379,7 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
     if ((hs & (HS_OVER | HS_DEAD)) == 0u) {   // live lane whose half inning is still running
       // ---------------- one plate appearance ----------------
       uint32_t w0;
-      philox2x32_10(c0, c1, args.keys, w0, w1);
+      philox2x32_native(c0, c1, args.keys, w0, w1);
       ++c1;
 
       // The first PA of a half has empty bases, so its w1 never reaches the transition: keep it
@@ -783,7 +783,7 @@ mlbsim_persim_kernel(const PersimArgs args) {
         int outs = 0, bases = 0, runs = 0, n = 0, sl = slot[side];
         bool reached = false;
         while (outs < 3 && n < MAX_PA_PER_HALF) {
-          philox2x32_10(c0, c1base + seq, args.keys, w0, w1);
+          philox2x32_native(c0, c1base + seq, args.keys, w0, w1);
           if (n == 0) w1_first = w1;
           if (sl == 0 && n > 0) tto[side] += 1;
           const int tier = (tto[side] >= 4 ? 4 : tto[side]) - 1;

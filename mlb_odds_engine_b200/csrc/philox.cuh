@@ -22,6 +22,12 @@
 #define PHILOX_W0 0x9E3779B9u
 #define PHILOX_W1 0xBB67AE85u
 #define PHILOX2_M 0xD256D193u
+// Rounds of the generator behind the native law.  10 = Philox2x32-10 as published (the product).  Fewer rounds are an
+// EXPERIMENT switch only (what the generator costs, measured): the oracle twin must be built with the same
+// value (oracle/Makefile: NATIVE_PHILOX_ROUNDS), and nothing but 10 is backed by the Random123 known-answer vectors.
+#ifndef NATIVE_PHILOX_ROUNDS
+#define NATIVE_PHILOX_ROUNDS 10
+#endif
 
 #define RNG_KIND_HALF_END (1u << 13)
 #define RNG_MATCHUP_SHIFT 14
@@ -61,9 +67,9 @@ static inline Philox2Keys philox2_keys_from_seed(uint64_t seed) {
 }
 
 #ifdef __CUDACC__
-__device__ __forceinline__ void philox2x32_10(uint32_t c0, uint32_t c1, const Philox2Keys& K, uint32_t& o0, uint32_t& o1) {
+__device__ __forceinline__ void philox2x32_native(uint32_t c0, uint32_t c1, const Philox2Keys& K, uint32_t& o0, uint32_t& o1) {
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < NATIVE_PHILOX_ROUNDS; ++r) {
     const uint64_t p = (uint64_t)PHILOX2_M * c0;
     c0 = (uint32_t)(p >> 32) ^ K.k[r] ^ c1;
     c1 = (uint32_t)p;

@@ -98,6 +98,21 @@ void oracle_philox2x32_10(const uint32_t ctr[2], uint32_t key, uint32_t out[2]) 
   }
   out[0] = c0; out[1] = c1;
 }
+/* the generator of the native law: Philox2x32 with NATIVE_PHILOX_ROUNDS rounds — 10 unless an experiment build of the
+ * CUDA library says otherwise (csrc/philox.cuh) */
+#ifndef NATIVE_PHILOX_ROUNDS
+#define NATIVE_PHILOX_ROUNDS 10
+#endif
+static void philox2x32_native(const uint32_t ctr[2], uint32_t key, uint32_t out[2]) {
+  uint32_t c0 = ctr[0], c1 = ctr[1], k = key;
+  for (int r = 0; r < NATIVE_PHILOX_ROUNDS; ++r) {
+    uint64_t p = (uint64_t)PHILOX2_M * c0;
+    c0 = (uint32_t)(p >> 32) ^ k ^ c1;
+    c1 = (uint32_t)p;
+    k += PHILOX_W0;
+  }
+  out[0] = c0; out[1] = c1;
+}
 /* 64-bit seed -> 32-bit Philox2x32 key: word 0 of Philox4x32-10 over a fixed domain-separation counter */
 uint32_t oracle_native_key(uint64_t seed) {
   const uint32_t ctr[4] = {0x6d6c6273u, 0x696d3278u, 0u, 0u};
@@ -531,7 +546,7 @@ static void native_game(const mlbsim_table* T, uint32_t matchup, uint32_t key, u
       int outs = 0, runs = 0, n = 0, bases = 0, reached = 0, sl = slot[side];
       while (outs < 3 && n < 30) {
         const uint32_t ctr[2] = {c0, c1base + seq};
-        oracle_philox2x32_10(ctr, key, w);
+        philox2x32_native(ctr, key, w);
         if (n == 0) w1_first = w[1]; /* bases empty: this w1 never reaches the transition -> end-of-half draw */
         if (sl == 0 && n > 0) st[side].tto += 1;
         int tier = (st[side].tto >= 4 ? 4 : st[side].tto) - 1;

@@ -12,7 +12,8 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "_build", "libmlbsim_oracle.so")
+# MLBSIM_ORACLE_LIB: an experiment build of the twin (e.g. another NATIVE_PHILOX_ROUNDS), paired with MLBSIM_LIB
+LIB_PATH = os.environ.get("MLBSIM_ORACLE_LIB") or os.path.join(HERE, "_build", "libmlbsim_oracle.so")
 
 _lib = None
 
@@ -23,6 +24,8 @@ def build(force: bool = False) -> str:
     stale = (not os.path.exists(LIB_PATH)) or any(
         os.path.exists(p) and os.path.getmtime(p) > os.path.getmtime(LIB_PATH) for p in (src, hdr)
     )
+    if os.environ.get("MLBSIM_ORACLE_LIB"):
+        return LIB_PATH          # experiment builds are made by hand (make -C oracle OUT=... EXTRA=...)
     if force or stale:
         subprocess.run(["make", "-C", HERE, "-B"], check=True, capture_output=True)
     return LIB_PATH
