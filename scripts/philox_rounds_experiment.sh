@@ -4,6 +4,8 @@
 # statistical GPU parity tests run on that pair, then the bench.  The product (R = 10) is not touched.
 mkdir -p gpurun_out; LOG=gpurun_out/r02_philox_rounds.log; : > $LOG
 for R in 7 8; do
+  [ -f variants/libmlbsim_r$R.so ] || python scripts/build_variants.py r$R="-DNATIVE_PHILOX_ROUNDS=$R" > /dev/null
+  [ -f oracle/_build/libmlbsim_oracle_r$R.so ] || make -s -C oracle -B OUT=_build/libmlbsim_oracle_r$R.so EXTRA=-DNATIVE_PHILOX_ROUNDS=$R
   export MLBSIM_LIB=$PWD/variants/libmlbsim_r$R.so MLBSIM_ORACLE_LIB=$PWD/oracle/_build/libmlbsim_oracle_r$R.so
   echo "== NATIVE_PHILOX_ROUNDS=$R" >> $LOG
   timeout 900 python -m pytest tests/test_gpu_parity.py -q -k "native or statistics or calibration_outcome or fresh_reference or slate_multi" 2>&1 | tail -3 >> $LOG
