@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define MLBSIM_ABI_VERSION 4
+#define MLBSIM_ABI_VERSION 5
 
 /* ---- model dimensions ------------------------------------------------------------------- */
 #define MLBSIM_MAX_LINEUP 9   /* len(lineup); 9 in every caller (half_inning_simulator.py:175) */
@@ -152,6 +152,7 @@ typedef struct mlbsim_summary {
 #define MLBSIM_ERR_TABLE 3      /* table failed validation (magic, lengths) */
 #define MLBSIM_ERR_NO_DEVICE 4  /* no CUDA device / not an sm_100 part */
 #define MLBSIM_ERR_STATE 5      /* call order (e.g. run before upload) */
+#define MLBSIM_ERR_CANNOT_SCORE 6 /* mlbsim_build_tables: a matchup in which nobody can reach base (the game never ends) */
 
 typedef struct mlbsim_ctx mlbsim_ctx;
 
@@ -191,6 +192,22 @@ int mlbsim_set_matchup_base(mlbsim_ctx* ctx, int base);
  * operations in the same order.  Replaces nothing in the reference (it samples with np.random.choice per PA,
  * core/pa_simulator.py:54-79); it takes the per-row Python/numpy work out of building 10^3-point sweeps. */
 int mlbsim_alias_rows(mlbsim_ctx* ctx, const double* probs_host, int n_rows, int n_own, uint32_t* out_host);
+
+/* Table construction on the device: the sampling tables of `n_matchups` matchups from their raw float64 numbers (the
+ * mlbsim_params of replay mode: what core/pa_simulator.py:91-143, core/bip_resolution.py and core/fatigue_modeling.py read
+ * per plate appearance), installed like mlbsim_upload_tables — one block per matchup, one warp per (side, pitcher, tier,
+ * slot) row: effective rates, the Beta-noise expectation E[min(1, kp + 1.01 bp)] by 48-node Gauss-Legendre quadrature
+ * (lanes = nodes), the contact split, the Walker alias row, and for never-replaced starters the pitch-count thresholds.
+ * Everything but the quadrature is the host builder's float64 arithmetic in the same order (bit-identical); the
+ * quadrature agrees with the host's (scipy) to ~1e-16, so a 29/31-bit table entry can differ from the host-built one by
+ * one unit, rarely.  A 1 024-point sweep builds in about a millisecond and its 20 MB of tables never exist on the host.
+ * MLBSIM_ERR_CANNOT_SCORE (nothing installed; indices in mlbsim_last_error) when some matchup could never leave 0-0 —
+ * the reference would loop forever there (core/game_simulator.py:110-111) — unless MLBSIM_BUILD_NO_VALIDATE is passed. */
+#define MLBSIM_BUILD_NO_VALIDATE 1u
+int mlbsim_build_tables(mlbsim_ctx* ctx, const mlbsim_params* params_host, int n_matchups, uint32_t flags);
+
+/* Copy installed tables [matchup_lo, matchup_hi) back to the host (e.g. to hand the oracle the very bytes the device uses). */
+int mlbsim_download_tables(mlbsim_ctx* ctx, int matchup_lo, int matchup_hi, mlbsim_table* out_host);
 
 /* Native-RNG mode: for every uploaded matchup m in [matchup_lo, matchup_hi) simulate the sims
  * [sim_lo, sim_hi) — the loop of cli/run_distribution_simulator.py:368-382 — and ADD the results

@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import numpy as np
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 MAX_LINEUP = 9
 MAX_BULLPEN = 6
@@ -118,6 +118,15 @@ SUMMARY_DTYPE = np.dtype(
     ],
     align=True,
 )
+
+ERR_CANNOT_SCORE = 6
+BUILD_NO_VALIDATE = 1
+
+
+class MatchupCannotScore(ValueError):
+    """Every reachable plate appearance of BOTH sides is a strikeout or an out: the game can never leave 0-0.  The
+    reference loops forever on such input (core/game_simulator.py:110-111); tables are refused instead."""
+
 
 STRUCTS = {0: PARAMS_DTYPE, 1: TABLE_DTYPE, 2: HIST_DTYPE, 3: REPLAY_GAME_DTYPE, 4: SUMMARY_DTYPE}
 

@@ -20,10 +20,10 @@ SYMBOLS = [
     "mlbsim_run_persim", "mlbsim_malloc", "mlbsim_free", "mlbsim_memset", "mlbsim_memcpy_h2d", "mlbsim_memcpy_d2h",
     "mlbsim_launch_count", "mlbsim_set_launch_config", "mlbsim_last_kernel_ms",
     "mlbsim_summarize", "mlbsim_run_native_summary_host", "mlbsim_allreduce", "mlbsim_set_matchup_base",
-    "mlbsim_alias_rows",
+    "mlbsim_alias_rows", "mlbsim_build_tables", "mlbsim_download_tables",
 ]
 
-ERR_NAMES = {1: "CUDA", 2: "ARG", 3: "TABLE", 4: "NO_DEVICE", 5: "STATE"}
+ERR_NAMES = {1: "CUDA", 2: "ARG", 3: "TABLE", 4: "NO_DEVICE", 5: "STATE", 6: "CANNOT_SCORE"}
 
 
 class MlbsimError(RuntimeError):
@@ -90,6 +90,8 @@ def load() -> ctypes.CDLL:
         "mlbsim_allreduce": (i32, [vp, vp, vp, i32]),
         "mlbsim_set_matchup_base": (i32, [vp, i32]),
         "mlbsim_alias_rows": (i32, [vp, vp, i32, i32, vp]),
+        "mlbsim_build_tables": (i32, [vp, vp, i32, u32]),
+        "mlbsim_download_tables": (i32, [vp, i32, i32, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(L, name)  # AttributeError if the library lacks a declared symbol
@@ -200,6 +202,25 @@ class Context:
         assert tables.dtype == _abi.TABLE_DTYPE
         self._ck(self.L.mlbsim_upload_tables(self.h, _ptr(tables), len(tables)))
         self.n_tables = len(tables)
+
+    def build_tables(self, params: np.ndarray, validate: bool = True):
+        """Build and install the tables of a batch of matchups ON THE DEVICE from their raw numbers (PARAMS_DTYPE records:
+        `tables.build_params` / `tables.params_from_arrays`).  Raises `MatchupCannotScore` like the host builder."""
+        params = np.ascontiguousarray(np.atleast_1d(params))
+        assert params.dtype == _abi.PARAMS_DTYPE
+        rc = self.L.mlbsim_build_tables(self.h, _ptr(params), len(params), 0 if validate else _abi.BUILD_NO_VALIDATE)
+        if rc == _abi.ERR_CANNOT_SCORE:
+            self.n_tables = 0
+            raise _abi.MatchupCannotScore((self.L.mlbsim_last_error(self.h) or b"").decode())
+        self._ck(rc)
+        self.n_tables = len(params)
+
+    def download_tables(self, lo: int = 0, hi: int | None = None) -> np.ndarray:
+        """The installed tables [lo, hi) as TABLE_DTYPE records (the very bytes the kernels read)."""
+        hi = self.n_tables if hi is None else hi
+        out = np.zeros(hi - lo, dtype=_abi.TABLE_DTYPE)
+        self._ck(self.L.mlbsim_download_tables(self.h, int(lo), int(hi), _ptr(out)))
+        return out
 
     def run_native_host(self, matchup_lo, matchup_hi, sim_lo, sim_hi, seed, flags=0, out=None) -> np.ndarray:
         n = matchup_hi - matchup_lo

@@ -26,9 +26,10 @@ UNITS = {
     "replay_flat_kernel.cu": ["-fmad=false"],
     "summary_kernel.cu": [],
     "alias_kernel.cu": ["-fmad=false"],
+    "table_kernel.cu": ["-fmad=false"],
     "mlbsim_api.cu": [],
 }
-DEPS = ["native_kernel.h", "philox.cuh", "game_rules.cuh", os.path.join(INCLUDE, "mlbsim.h")]
+DEPS = ["native_kernel.h", "philox.cuh", "game_rules.cuh", "alias_row.cuh", os.path.join(INCLUDE, "mlbsim.h")]
 
 
 def _nvcc() -> str:

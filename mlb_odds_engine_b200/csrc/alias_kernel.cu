@@ -1,65 +1,17 @@
-// alias_kernel.cu — Walker/Vose alias rows on the device: one thread builds one row.
+// alias_kernel.cu — Walker/Vose alias rows on the device: one thread builds one row (alias_row.cuh).
 //
-// Host statement: mlb_odds_engine_b200/tables.py::alias_row (and its lock-step batch form alias_rows).  This kernel
-// performs the SAME float64 operations in the SAME order, so its output is bit-identical to the host's (tested on
-// the GPU box against random rows and against every row of real tables): tables built through it hash to the same
-// digests as tables built on the CPU.  A 1 024-point sweep has 73 728 rows; numpy needs ~60 ms for them, this ~20 us.
-//
-// Row law: probabilities p[0..n_own) (n_own = 7 or 8) on 8 columns; q = p * 8 / sum(p); columns with q < 1 are topped up
-// from columns with q >= 1, highest column index first (two stacks).  Entry = cut29 << 3 | alias; a full column is
-// encoded as "cut 0, alias = own outcome".  (What the alias row is for: include/mlbsim.h, native mode.)
+// Bit-identical to mlb_odds_engine_b200/tables.py::alias_rows (tested on the GPU box against random rows and against every
+// row of real tables): tables built through it hash to the same digests as tables built on the CPU.  A 1 024-point sweep
+// has 73 728 rows; numpy needs ~60 ms for them, this ~20 us.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#include "../../include/mlbsim.h"
+#include "alias_row.cuh"
 #include "native_kernel.h"
 
 extern "C" __global__ void __launch_bounds__(128)
 mlbsim_alias_rows_kernel(const double* __restrict__ probs, int n_rows, int n_own, uint32_t* __restrict__ out) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n_rows) return;
-  constexpr int C = MLBSIM_ROW_WORDS;   // 8 columns
-  double p[C], q[C], cut[C];
-  int alias[C], small[C], large[C];
-#pragma unroll
-  for (int i = 0; i < C; ++i) p[i] = i < n_own ? probs[(size_t)r * n_own + i] : 0.0;
-  // numpy's sum over a contiguous axis: fewer than 8 elements left to right, exactly 8 as ((0+1)+(2+3))+((4+5)+(6+7))
-  double s;
-  if (n_own == C) {
-    s = __dadd_rn(__dadd_rn(__dadd_rn(p[0], p[1]), __dadd_rn(p[2], p[3])), __dadd_rn(__dadd_rn(p[4], p[5]), __dadd_rn(p[6], p[7])));
-  } else {
-    s = p[0];
-    for (int i = 1; i < n_own; ++i) s = __dadd_rn(s, p[i]);
-  }
-  int ns = 0, nl = 0;
-#pragma unroll
-  for (int i = 0; i < C; ++i) {
-    q[i] = i < n_own ? __ddiv_rn(__dmul_rn(p[i], (double)C), s) : 0.0;
-    cut[i] = 1.0;
-    alias[i] = i;
-  }
-  for (int i = 0; i < C; ++i) {
-    if (q[i] < 1.0) small[ns++] = i; else large[nl++] = i;
-  }
-  while (ns > 0 && nl > 0) {
-    const int sm = small[--ns], lg = large[--nl];
-    cut[sm] = q[sm];
-    alias[sm] = lg;
-    q[lg] = __dsub_rn(q[lg], __dsub_rn(1.0, q[sm]));
-    if (q[lg] < 1.0) small[ns++] = lg; else large[nl++] = lg;
-  }
-  int top = 0;                                  // np.argmax(p): first index of the maximum
-  for (int i = 1; i < n_own; ++i) if (p[i] > p[top]) top = i;
-  for (int j = 0; j < ns; ++j) { const int c = small[j]; cut[c] = 1.0; alias[c] = c < n_own ? c : top; }
-  for (int j = 0; j < nl; ++j) { const int c = large[j]; cut[c] = 1.0; alias[c] = c < n_own ? c : top; }
-  const long long one = 1ll << 29;
-  for (int i = 0; i < C; ++i) {
-    long long c = (long long)floor(__dadd_rn(__dmul_rn(cut[i], (double)one), 0.5));
-    int a = alias[i];
-    const bool full = c >= one;
-    if (full && i < n_own) a = i;
-    if (full || i >= n_own) c = 0;
-    if (c < 0) c = 0;
-    out[(size_t)r * C + i] = (uint32_t)((c << 3) | (long long)a);
-  }
+  mlbsim_alias_row(probs + (size_t)r * n_own, n_own, out + (size_t)r * MLBSIM_ROW_WORDS);
 }

@@ -4,12 +4,14 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "../../include/mlbsim.h"
 #include "native_kernel.h"
@@ -39,6 +41,7 @@ struct mlbsim_ctx {
   int threads_per_block = 0;
   int blocks_per_sm = 0;
   int occ_threads = -1, occ_blocks = 0;   // cached occupancy query of the native kernel
+  bool nodes_set = false;                 // quadrature nodes of the table builder are in this device's constant memory
   uint64_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
@@ -175,18 +178,8 @@ int mlbsim_set_matchup_base(mlbsim_ctx* ctx, int base) {
   return MLBSIM_OK;
 }
 
-int mlbsim_upload_tables(mlbsim_ctx* ctx, const mlbsim_table* tables, int n_matchups) {
-  if (!ctx) return MLBSIM_ERR_ARG;
-  if (!tables || n_matchups <= 0) return fail(ctx, MLBSIM_ERR_ARG, "mlbsim_upload_tables: no tables");
-  for (int i = 0; i < n_matchups; ++i) {
-    const mlbsim_table& t = tables[i];
-    if (t.magic != MLBSIM_TABLE_MAGIC) return fail(ctx, MLBSIM_ERR_TABLE, "table magic mismatch");
-    for (int s = 0; s < 2; ++s) {
-      if (t.lineup_len[s] < 1 || t.lineup_len[s] > MLBSIM_MAX_LINEUP) return fail(ctx, MLBSIM_ERR_TABLE, "lineup_len out of range");
-      if (t.bullpen_len[s] > MLBSIM_MAX_BULLPEN) return fail(ctx, MLBSIM_ERR_TABLE, "bullpen_len out of range");
-    }
-  }
-  CK(ctx, cudaSetDevice(ctx->device));
+// device buffers for n_matchups tables (raw + staged image) and their work counters
+static int ensure_table_capacity(mlbsim_ctx* ctx, int n_matchups) {
   if (n_matchups > ctx->tables_cap) {
     CK(ctx, cudaStreamSynchronize(ctx->stream));
     cudaFree(ctx->tables_dev);
@@ -205,6 +198,22 @@ int mlbsim_upload_tables(mlbsim_ctx* ctx, const mlbsim_table* tables, int n_matc
     CK(ctx, cudaMalloc(&ctx->counters_dev, sizeof(unsigned long long) * (size_t)n_matchups));
     ctx->counters_cap = n_matchups;
   }
+  return MLBSIM_OK;
+}
+
+int mlbsim_upload_tables(mlbsim_ctx* ctx, const mlbsim_table* tables, int n_matchups) {
+  if (!ctx) return MLBSIM_ERR_ARG;
+  if (!tables || n_matchups <= 0) return fail(ctx, MLBSIM_ERR_ARG, "mlbsim_upload_tables: no tables");
+  for (int i = 0; i < n_matchups; ++i) {
+    const mlbsim_table& t = tables[i];
+    if (t.magic != MLBSIM_TABLE_MAGIC) return fail(ctx, MLBSIM_ERR_TABLE, "table magic mismatch");
+    for (int s = 0; s < 2; ++s) {
+      if (t.lineup_len[s] < 1 || t.lineup_len[s] > MLBSIM_MAX_LINEUP) return fail(ctx, MLBSIM_ERR_TABLE, "lineup_len out of range");
+      if (t.bullpen_len[s] > MLBSIM_MAX_BULLPEN) return fail(ctx, MLBSIM_ERR_TABLE, "bullpen_len out of range");
+    }
+  }
+  CK(ctx, cudaSetDevice(ctx->device));
+  if (int rc = ensure_table_capacity(ctx, n_matchups)) return rc;
   ctx->n_tables = n_matchups;
   CK(ctx, cudaMemcpyAsync(ctx->tables_dev, tables, sizeof(mlbsim_table) * (size_t)n_matchups, cudaMemcpyHostToDevice, ctx->stream));
   mlbsim_stage_tables_kernel<<<n_matchups, 256, 0, ctx->stream>>>(ctx->tables_dev, ctx->staged_dev, n_matchups);
@@ -412,6 +421,101 @@ int mlbsim_alias_rows(mlbsim_ctx* ctx, const double* probs_host, int n_rows, int
     ctx->err = std::string("mlbsim_alias_rows: ") + cudaGetErrorString(e);
     return MLBSIM_ERR_CUDA;
   }
+  return MLBSIM_OK;
+}
+
+// Gauss-Legendre nodes and weights on (0, 1): Newton iteration on P_n (the table builder's quadrature)
+static void gauss_legendre_01(int n, double* y, double* w) {
+  const double pi = 3.14159265358979323846;
+  for (int i = 0; i < n; ++i) {
+    double x = std::cos(pi * (i + 0.75) / (n + 0.5)), dp = 1.0;
+    for (int it = 0; it < 100; ++it) {
+      double p0 = 1.0, p1 = x;
+      for (int k = 2; k <= n; ++k) {
+        const double p2 = ((2.0 * k - 1.0) * x * p1 - (k - 1.0) * p0) / k;
+        p0 = p1;
+        p1 = p2;
+      }
+      dp = n * (x * p1 - p0) / (x * x - 1.0);
+      const double dx = p1 / dp;
+      x -= dx;
+      if (std::fabs(dx) < 1e-16) break;
+    }
+    y[n - 1 - i] = 0.5 * (x + 1.0);
+    w[n - 1 - i] = 1.0 / ((1.0 - x * x) * dp * dp);
+  }
+}
+
+int mlbsim_build_tables(mlbsim_ctx* ctx, const mlbsim_params* params_host, int n_matchups, uint32_t flags) {
+  if (!ctx) return MLBSIM_ERR_ARG;
+  if (!params_host || n_matchups <= 0) return fail(ctx, MLBSIM_ERR_ARG, "mlbsim_build_tables: no matchups");
+  for (int i = 0; i < n_matchups; ++i) {
+    const mlbsim_params& p = params_host[i];
+    for (int s = 0; s < 2; ++s) {
+      if (p.lineup_len[s] < 1 || p.lineup_len[s] > MLBSIM_MAX_LINEUP) return fail(ctx, MLBSIM_ERR_TABLE, "lineup_len out of range");
+      if (p.bullpen_len[s] < 0 || p.bullpen_len[s] > MLBSIM_MAX_BULLPEN) return fail(ctx, MLBSIM_ERR_TABLE, "bullpen_len out of range");
+    }
+  }
+  CK(ctx, cudaSetDevice(ctx->device));
+  if (int rc = ensure_table_capacity(ctx, n_matchups)) return rc;
+  if (!ctx->nodes_set) {
+    double y[48], w[48];
+    gauss_legendre_01(48, y, w);
+    CK(ctx, mlbsim_table_set_nodes(y, w, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));   // y, w live on this stack frame
+    ctx->nodes_set = true;
+  }
+  mlbsim_params* p_dev = nullptr;
+  uint32_t* st_dev = nullptr;
+  std::vector<uint32_t> status((size_t)n_matchups);
+  cudaError_t e;
+  if ((e = cudaMalloc(&p_dev, sizeof(mlbsim_params) * (size_t)n_matchups)) != cudaSuccess ||
+      (e = cudaMalloc(&st_dev, sizeof(uint32_t) * (size_t)n_matchups)) != cudaSuccess) {
+    cudaFree(p_dev);
+    ctx->err = std::string("cudaMalloc: ") + cudaGetErrorString(e);
+    return MLBSIM_ERR_CUDA;
+  }
+  ctx->n_tables = n_matchups;
+  if ((e = cudaMemcpyAsync(p_dev, params_host, sizeof(mlbsim_params) * (size_t)n_matchups, cudaMemcpyHostToDevice, ctx->stream)) == cudaSuccess) {
+    mlbsim_build_tables_kernel<<<n_matchups, 256, 0, ctx->stream>>>(p_dev, ctx->tables_dev, st_dev, n_matchups);
+    mlbsim_stage_tables_kernel<<<n_matchups, 256, 0, ctx->stream>>>(ctx->tables_dev, ctx->staged_dev, n_matchups);
+    ctx->launches += 2;
+    if ((e = cudaGetLastError()) == cudaSuccess &&
+        (e = cudaMemcpyAsync(status.data(), st_dev, sizeof(uint32_t) * (size_t)n_matchups, cudaMemcpyDeviceToHost, ctx->stream)) == cudaSuccess)
+      e = cudaStreamSynchronize(ctx->stream);
+  }
+  cudaFree(p_dev);
+  cudaFree(st_dev);
+  if (e != cudaSuccess) {
+    ctx->n_tables = 0;
+    ctx->err = std::string("mlbsim_build_tables: ") + cudaGetErrorString(e);
+    return MLBSIM_ERR_CUDA;
+  }
+  if (!(flags & MLBSIM_BUILD_NO_VALIDATE)) {
+    std::string bad;
+    int n_bad = 0;
+    for (int i = 0; i < n_matchups; ++i)
+      if (status[(size_t)i]) {
+        if (n_bad < 8) bad += (n_bad ? ", " : "") + std::to_string(i);
+        ++n_bad;
+      }
+    if (n_bad) {
+      ctx->n_tables = 0;   // nothing is installed
+      ctx->err = "matchup(s) [" + bad + "]: no plate appearance of either side can put a runner on base, the game would never end";
+      return MLBSIM_ERR_CANNOT_SCORE;
+    }
+  }
+  return MLBSIM_OK;
+}
+
+int mlbsim_download_tables(mlbsim_ctx* ctx, int matchup_lo, int matchup_hi, mlbsim_table* out_host) {
+  if (!ctx) return MLBSIM_ERR_ARG;
+  if (!ctx->tables_dev || ctx->n_tables == 0) return fail(ctx, MLBSIM_ERR_STATE, "mlbsim_download_tables before tables were installed");
+  if (!out_host || matchup_lo < 0 || matchup_hi > ctx->n_tables || matchup_lo > matchup_hi) return fail(ctx, MLBSIM_ERR_ARG, "mlbsim_download_tables: bad argument");
+  if (matchup_lo == matchup_hi) return MLBSIM_OK;
+  CK(ctx, cudaSetDevice(ctx->device));
+  CK(ctx, cudaMemcpyAsync(out_host, ctx->tables_dev + matchup_lo, sizeof(mlbsim_table) * (size_t)(matchup_hi - matchup_lo), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
   return MLBSIM_OK;
 }
 

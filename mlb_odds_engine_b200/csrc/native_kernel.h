@@ -59,6 +59,10 @@ extern "C" __global__ void mlbsim_replay_flat_kernel(const ReplayArgs args, unsi
 extern "C" __global__ void mlbsim_replay_flat_nonoise_kernel(const ReplayArgs args, unsigned long long* counter, uint32_t chunk);
 extern "C" __global__ void mlbsim_summary_kernel(const mlbsim_hist* hist, mlbsim_summary* out);
 extern "C" __global__ void mlbsim_alias_rows_kernel(const double* probs, int n_rows, int n_own, uint32_t* out);
+
+// table_kernel.cu: mlbsim_params -> mlbsim_table on the device (status[m] = 1: nobody can reach base in matchup m)
+extern "C" __global__ void mlbsim_build_tables_kernel(const mlbsim_params* params, mlbsim_table* tables, uint32_t* status, int n_matchups);
+extern "C" cudaError_t mlbsim_table_set_nodes(const double* y, const double* w, cudaStream_t stream);
 #endif
 
 size_t mlbsim_native_smem_bytes(int threads_per_block);

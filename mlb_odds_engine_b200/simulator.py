@@ -85,6 +85,16 @@ class RunHistogram:
         return float((h * c).sum() / n), float((a * c).sum() / n)
 
 
+class _DeviceTables:
+    """Placeholder for tables that exist only in HBM (built by `Context.build_tables`) until somebody asks for them."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+
+    def fetch(self) -> np.ndarray:
+        return self.ctx.download_tables()
+
+
 class GpuSimulator:
     """Owns one device context and the uploaded matchup tables."""
 
@@ -97,11 +107,25 @@ class GpuSimulator:
         self.ctx.close()
 
     # ---- inputs ----
-    def load_matchups(self, matchups, use_noise: bool = True):
-        """`matchups`: iterable of `simulate_game` keyword dicts (or tables.Matchup)."""
+    def load_matchups(self, matchups, use_noise: bool = True, builder: str = "device"):
+        """`matchups`: iterable of `simulate_game` keyword dicts (or tables.Matchup).  `builder="device"` (default): the
+        raw numbers go up as `mlbsim_params` and the sampling tables are built in HBM (csrc/table_kernel.cu);
+        `builder="host"`: numpy / scipy build them (tables.build_tables, alias rows on the device) and they are
+        uploaded — same tables up to one unit of a 29/31-bit entry in rare rows (the noise quadrature)."""
         self.matchups = [tables.as_matchup(m, use_noise) for m in matchups]
+        if builder == "device":
+            return self.load_params(tables.params_batch(self.matchups), self.matchups)
+        if builder != "host":
+            raise ValueError(f"builder must be 'device' or 'host', not {builder!r}")
         self._tables = tables.build_tables(self.matchups, alias_fn=self.ctx.alias_rows)   # alias rows on the device (bit-identical)
         self.ctx.upload_tables(self._tables)
+        return self
+
+    def load_params(self, params: np.ndarray, matchups=None, validate: bool = True):
+        """Build and install tables on the device from PARAMS_DTYPE records (`tables.params_batch`, `sweep.grid_params`)."""
+        self.ctx.build_tables(params, validate=validate)
+        self.matchups = list(matchups) if matchups is not None else [None] * len(np.atleast_1d(params))
+        self._tables = _DeviceTables(self.ctx)
         return self
 
     def load_tables(self, tbl: np.ndarray, matchups=None):
@@ -110,6 +134,13 @@ class GpuSimulator:
         self.matchups = list(matchups) if matchups is not None else [None] * len(np.atleast_1d(tbl))
         self.ctx.upload_tables(tbl)
         return self
+
+    @property
+    def tables(self) -> np.ndarray:
+        """The installed tables as TABLE_DTYPE records on the host (downloaded once when they were built on the device)."""
+        if isinstance(self._tables, _DeviceTables):
+            self._tables = self._tables.fetch()
+        return self._tables
 
     # ---- native-RNG mode ----
     def simulate(self, n_sims: int, seed: int = 0, sim_lo: int = 0, matchup_lo: int = 0, matchup_hi: int | None = None,

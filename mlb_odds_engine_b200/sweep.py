@@ -55,6 +55,19 @@ def grid_tables(base: dict, side: str = "home", project: bool = False, use_noise
     `tables.tables_from_arrays` builds every table in one pass (1 024 points: ~0.35 s instead of ~1.2 s).
     Byte-identical to `tables.build_tables(grid_matchups(...)[0])`.  `alias_fn`: e.g. `Context.alias_rows`, the device
     builder of the alias rows (same bytes).  Returns (TABLE_DTYPE[n], points)."""
+    A, points = _grid_arrays(base, side, project, use_noise, **axes)
+    return tables.tables_from_arrays(A, alias_fn=alias_fn), points
+
+
+def grid_params(base: dict, side: str = "home", project: bool = False, use_noise: bool = True, **axes):
+    """The same grid as `mlbsim_params` records for the DEVICE table builder (`GpuSimulator.load_params`): a few array
+    copies on the host, the tables are built in HBM.  Returns (PARAMS_DTYPE[n], points)."""
+    A, points = _grid_arrays(base, side, project, use_noise, **axes)
+    return tables.params_from_arrays(A), points
+
+
+def _grid_arrays(base: dict, side: str, project: bool, use_noise: bool, **axes):
+    """Stacked per-matchup arrays (`tables.stack_matchups` layout) of a cartesian grid over one pitcher's fields."""
     names = list(axes)
     if project and "hr_pa_projected" in names:
         raise ValueError("hr_pa_projected cannot be a grid axis when project=True (it is recomputed)")
@@ -99,7 +112,7 @@ def grid_tables(base: dict, side: str = "home", project: bool = False, use_noise
             A["hit_prob"][g, s, 0, :L] = cache[key]
     # (axes the hot path never reads — Stuff+, ISO, HR/FB without project=True — leave every table equal to the base
     # table, as in the reference)
-    return tables.tables_from_arrays(A, alias_fn=alias_fn), points
+    return A, points
 
 
 def sensitivity_matchups(field: str, values, project: bool = False) -> list[dict]:

@@ -523,6 +523,28 @@ def stack_matchups(ms) -> dict:
     }
 
 
+def params_from_arrays(A: dict) -> np.ndarray:
+    """`mlbsim_params` records (PARAMS_DTYPE) of a batch of matchups given as stacked arrays (`stack_matchups`): the input
+    of the DEVICE table builder (`Context.build_tables`, csrc/table_kernel.cu) — and of replay mode, one record at a
+    time.  A few array copies; the tables themselves are then built in HBM."""
+    n = len(A["use_noise"])
+    out = np.zeros(n, dtype=_abi.PARAMS_DTYPE)
+    out["lineup_len"], out["bullpen_len"] = A["lineup_len"], A["bullpen_len"]
+    out["use_noise"] = A["use_noise"]
+    for f in ("k_mod", "bb_mod", "bat_k", "bat_bb", "pit_k", "pit_bb", "pit_hr", "hit_prob"):
+        out[f] = A[f]
+    out["cdf_bip"], out["cdf_hit"], out["cdf_fb"] = contact_cdfs()
+    return out
+
+
+def params_batch(matchups, use_noise=True) -> np.ndarray:
+    """`params_from_arrays` for `simulate_game` keyword dicts / Matchup objects."""
+    ms = [m if isinstance(m, Matchup) else as_matchup(m, use_noise) for m in matchups]
+    if not ms:
+        return np.zeros(0, dtype=_abi.PARAMS_DTYPE)
+    return params_from_arrays(stack_matchups(ms))
+
+
 def _cdf_tensor(A, valid, fl):
     """Cumulative outcome law of every valid (matchup, side, pitcher, tier, slot) row at fatigue level `fl`
     (0 = at most 75 pitches): the arithmetic of `outcome_cdf_batch`, same operations in the same order, evaluated
@@ -595,9 +617,7 @@ def _unique_rows(X: np.ndarray):
     return index, inverse.reshape(-1)
 
 
-class MatchupCannotScore(ValueError):
-    """Every reachable plate appearance of BOTH sides is a strikeout or an out: the game can never leave 0-0.  The
-    reference loops forever on such input (core/game_simulator.py:110-111); tables are refused instead."""
+MatchupCannotScore = _abi.MatchupCannotScore   # (defined beside the ABI: the device builder raises it too)
 
 
 def tables_from_arrays(A: dict, validate: bool = True, alias_fn=None) -> np.ndarray:

@@ -28,7 +28,7 @@ def main():
     ok = True
     if dist.get_rank() == 0:
         for m in range(3):
-            want = orc.native(S.sim._tables[m], m, 77, 77 + n, seed)
+            want = orc.native(S.sim.tables[m], m, 77, 77 + n, seed)
             if tot[m].tobytes() != want.tobytes():
                 ok = False
                 print(f"matchup {m}: all-reduced histogram differs from the oracle", flush=True)
