@@ -312,16 +312,16 @@ def extra_workloads(args, S_sims, local, world, rank, torch, dist):
     out = {}
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")
     for name, spec in bw.SPEC.items():
-        t_tbl = time.perf_counter()
-        tbl = bw.build_tables(name, alias_fn=S_sims.ctx.alias_rows)
-        t_tbl = time.perf_counter() - t_tbl
-        n_m = len(tbl)
         if spec["shard"] == "matchups":
             S_blk = S_blk or ShardedSimulator(local, shard="matchups")
             S = S_blk
         else:
             S = S_sims
-        S.load_tables(tbl)
+        t_tbl = time.perf_counter()          # dicts / grid axes -> mlbsim_params on the host -> tables built in HBM
+        params = bw.build_params(name)
+        S.load_params(params)
+        t_tbl = time.perf_counter() - t_tbl
+        n_m = len(params)
         sims = spec["sims"]
         steps, warm = (5, 2) if n_m * sims <= 20_000_000 else (3, 1)
 
@@ -405,15 +405,16 @@ def main():
     S = ShardedSimulator(local)
     if args.threads_per_block or args.blocks_per_sm:
         S.ctx.set_launch_config(args.threads_per_block, args.blocks_per_sm)
-    S.ctx.alias_rows(np.full((1, 8), 0.125))     # (first use of the device alias builder: module load kept out of the timing)
-    tables._CLIP_CACHE.clear()
-    t_build = time.perf_counter()
+    S.ctx.build_tables(tables.params_batch(ms[:1]))     # (first use of the device table builder: module load kept out of the timing)
+    t_build = time.perf_counter()               # dicts / grid axes -> mlbsim_params on the host -> tables built in HBM
     if getattr(args, "_grid", None):
         from mlb_odds_engine_b200 import sweep
-        tbl = sweep.grid_tables(args._grid[0], "home", alias_fn=S.ctx.alias_rows, **args._grid[1])[0]
+        params = sweep.grid_params(args._grid[0], "home", **args._grid[1])[0]
     else:
-        tbl = tables.build_tables(ms, alias_fn=S.ctx.alias_rows)
+        params = tables.params_batch(ms)
+    S.load_params(params, ms)
     t_build = time.perf_counter() - t_build
+    tbl = S.sim.tables                          # (downloaded: the e2e leg below uploads prebuilt tables from pinned memory)
     tbl_pinned = torch.from_numpy(tbl.view(np.uint8).reshape(-1).copy()).pin_memory()
     tbl_host = tbl_pinned.numpy().view(_abi.TABLE_DTYPE)
 

@@ -61,6 +61,17 @@ def build_tables(name: str, alias_fn=None) -> np.ndarray:
     return tables.build_tables(matchups(name), alias_fn=alias_fn)
 
 
+def build_params(name: str) -> np.ndarray:
+    """PARAMS_DTYPE array of a workload — the input of the DEVICE table builder (`ShardedSimulator.load_params`): the raw
+    numbers go up, the tables are built in HBM (same bytes as `build_tables` for every workload here; a test pins that)."""
+    from mlb_odds_engine_b200 import sweep, tables
+
+    if name == "sweep":
+        base, axes = sweep_grid()
+        return sweep.grid_params(base, "home", **axes)[0]
+    return tables.params_batch(matchups(name))
+
+
 def digest(records: np.ndarray) -> str:
     """sha256 over the raw bytes of HIST_DTYPE (sim shards) or SUMMARY_DTYPE (matchup shards) records, in matchup order."""
     return hashlib.sha256(np.ascontiguousarray(records).tobytes()).hexdigest()

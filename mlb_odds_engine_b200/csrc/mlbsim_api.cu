@@ -477,7 +477,8 @@ int mlbsim_build_tables(mlbsim_ctx* ctx, const mlbsim_params* params_host, int n
   }
   ctx->n_tables = n_matchups;
   if ((e = cudaMemcpyAsync(p_dev, params_host, sizeof(mlbsim_params) * (size_t)n_matchups, cudaMemcpyHostToDevice, ctx->stream)) == cudaSuccess) {
-    mlbsim_build_tables_kernel<<<n_matchups, 256, 0, ctx->stream>>>(p_dev, ctx->tables_dev, st_dev, n_matchups);
+    cudaMemsetAsync(st_dev, 0, sizeof(uint32_t) * (size_t)n_matchups, ctx->stream);
+    mlbsim_build_tables_kernel<<<n_matchups * MLBSIM_TABLE_BUILD_SPLIT, 256, 0, ctx->stream>>>(p_dev, ctx->tables_dev, st_dev, n_matchups);
     mlbsim_stage_tables_kernel<<<n_matchups, 256, 0, ctx->stream>>>(ctx->tables_dev, ctx->staged_dev, n_matchups);
     ctx->launches += 2;
     if ((e = cudaGetLastError()) == cudaSuccess &&
@@ -495,7 +496,7 @@ int mlbsim_build_tables(mlbsim_ctx* ctx, const mlbsim_params* params_host, int n
     std::string bad;
     int n_bad = 0;
     for (int i = 0; i < n_matchups; ++i)
-      if (status[(size_t)i]) {
+      if (!status[(size_t)i]) {
         if (n_bad < 8) bad += (n_bad ? ", " : "") + std::to_string(i);
         ++n_bad;
       }

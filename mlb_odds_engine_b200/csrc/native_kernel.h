@@ -60,7 +60,9 @@ extern "C" __global__ void mlbsim_replay_flat_nonoise_kernel(const ReplayArgs ar
 extern "C" __global__ void mlbsim_summary_kernel(const mlbsim_hist* hist, mlbsim_summary* out);
 extern "C" __global__ void mlbsim_alias_rows_kernel(const double* probs, int n_rows, int n_own, uint32_t* out);
 
-// table_kernel.cu: mlbsim_params -> mlbsim_table on the device (status[m] = 1: nobody can reach base in matchup m)
+// table_kernel.cu: mlbsim_params -> mlbsim_table on the device; grid = n_matchups * MLBSIM_TABLE_BUILD_SPLIT blocks of 256
+// threads; status[m] (zeroed by the caller) becomes 1 when somebody can reach base in matchup m
+#define MLBSIM_TABLE_BUILD_SPLIT 8
 extern "C" __global__ void mlbsim_build_tables_kernel(const mlbsim_params* params, mlbsim_table* tables, uint32_t* status, int n_matchups);
 extern "C" cudaError_t mlbsim_table_set_nodes(const double* y, const double* w, cudaStream_t stream);
 #endif

@@ -6,7 +6,7 @@
 // float64 numbers).  Output: one mlbsim_table per matchup, written straight into the context's device tables — a
 // 1 024-point sweep never materialises 20 MB of tables on the host.
 //
-// One block per matchup, one warp per table row (side, pitcher, TTO tier, lineup slot):
+// Eight blocks per matchup, one warp per table row (side, pitcher, TTO tier, lineup slot):
 //   * effective K / BB rates, the contact split and the cumulative law: plain float64 arithmetic in the host's operation
 //     order, compiled with -fmad=false — bit-identical to numpy;
 //   * E[min(1, X + 1.01 Y)], X ~ Beta(30k, 30(1-k)), Y ~ Beta(30bb, 30(1-bb)): 48-node Gauss-Legendre over y (lanes =
@@ -18,7 +18,7 @@
 //   * Walker alias row (alias_row.cuh, bit-identical to the host for the same probabilities), and for starters that are
 //     never replaced the 31-bit thresholds at 75 pitches with the integer slope per pitch fitted over 100 pitches.
 // A matchup in which no plate appearance of either side can put a runner on base (the game would never end:
-// core/game_simulator.py:110-111 has no inning cap) is reported through `status`.
+// core/game_simulator.py:110-111 has no inning cap) is reported through `status` (0 = nobody can reach base).
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -175,62 +175,73 @@ __device__ long long quantise31(double c) {
 
 }  // namespace
 
+// grid = n_matchups * MLBSIM_TABLE_BUILD_SPLIT blocks: block (m, part) fills its share of table m's words with the defaults and
+// builds rows part, part + SPLIT * warps, ... — a single matchup still spreads over 8 blocks x 8 warps.  `status` must be
+// zeroed by the caller: bit 0 is set as soon as somebody can reach base.
 extern "C" __global__ void __launch_bounds__(256)
 mlbsim_build_tables_kernel(const mlbsim_params* __restrict__ params, mlbsim_table* __restrict__ tables, uint32_t* __restrict__ status,
                            int n_matchups) {
-  const int m = blockIdx.x;
+  const int m = blockIdx.x / MLBSIM_TABLE_BUILD_SPLIT, part = blockIdx.x % MLBSIM_TABLE_BUILD_SPLIT;
   if (m >= n_matchups) return;
   const mlbsim_params& p = params[m];
   mlbsim_table& T = tables[m];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-  __shared__ int can_reach;
-  if (threadIdx.x == 0) can_reach = 0;
-  // defaults: unused alias rows are "always K" (never reached), thresholds 2^31 with slope 0
-  uint32_t* words = reinterpret_cast<uint32_t*>(&T);
-  constexpr int FTHR_OFF = offsetof(mlbsim_table, fthr) / 4,
-                FSLOPE_OFF = offsetof(mlbsim_table, fslope) / 4, TOTAL = sizeof(mlbsim_table) / 4;
-  for (int i = threadIdx.x; i < TOTAL; i += blockDim.x)
-    words[i] = (i >= FTHR_OFF && i < FSLOPE_OFF) ? 2147483648u : 0u;
-  __syncthreads();
-  const bool flagged = p.bullpen_len[0] == 0 || p.bullpen_len[1] == 0;   // some starter is never replaced
-  if (threadIdx.x == 0) {
-    T.magic = MLBSIM_TABLE_MAGIC;
-    T.flags = flagged ? MLBSIM_FLAG_FATIGUE : 0u;
-    T.lineup_len[0] = (uint32_t)p.lineup_len[0];
-    T.lineup_len[1] = (uint32_t)p.lineup_len[1];
-    T.bullpen_len[0] = (uint32_t)p.bullpen_len[0];
-    T.bullpen_len[1] = (uint32_t)p.bullpen_len[1];
-  }
   constexpr int ROWS = 2 * MLBSIM_MAX_PITCHERS * MLBSIM_N_TIERS * MLBSIM_MAX_LINEUP;
-  for (int r = warp; r < ROWS; r += n_warps) {
+  constexpr int HDR = offsetof(mlbsim_table, alias) / 4;
+  const bool flagged = p.bullpen_len[0] == 0 || p.bullpen_len[1] == 0;   // some starter is never replaced
+  uint32_t* words = reinterpret_cast<uint32_t*>(&T);
+  if (part == 0 && threadIdx.x < HDR) {
+    uint32_t v = 0u;
+    switch (threadIdx.x) {
+      case offsetof(mlbsim_table, magic) / 4: v = MLBSIM_TABLE_MAGIC; break;
+      case offsetof(mlbsim_table, flags) / 4: v = flagged ? MLBSIM_FLAG_FATIGUE : 0u; break;
+      case offsetof(mlbsim_table, lineup_len) / 4: v = (uint32_t)p.lineup_len[0]; break;
+      case offsetof(mlbsim_table, lineup_len) / 4 + 1: v = (uint32_t)p.lineup_len[1]; break;
+      case offsetof(mlbsim_table, bullpen_len) / 4: v = (uint32_t)p.bullpen_len[0]; break;
+      case offsetof(mlbsim_table, bullpen_len) / 4 + 1: v = (uint32_t)p.bullpen_len[1]; break;
+      default: break;
+    }
+    words[threadIdx.x] = v;
+  }
+  bool reach = false;
+  for (int r = part * n_warps + warp; r < ROWS; r += n_warps * MLBSIM_TABLE_BUILD_SPLIT) {
     const int slot = r % MLBSIM_MAX_LINEUP, tier = (r / MLBSIM_MAX_LINEUP) % MLBSIM_N_TIERS,
               pit = (r / (MLBSIM_MAX_LINEUP * MLBSIM_N_TIERS)) % MLBSIM_MAX_PITCHERS, s = r / (MLBSIM_MAX_LINEUP * MLBSIM_N_TIERS * MLBSIM_MAX_PITCHERS);
-    if (pit > p.bullpen_len[s] || slot >= p.lineup_len[s]) continue;   // (warp-uniform)
-    const RowLaw L0 = row_law(p, s, pit, tier, slot, 0.0, lane);
-    const bool fat = flagged && pit == 0;
-    RowLaw L1 = L0;
-    if (fat) L1 = row_law(p, s, pit, tier, slot, SLOPE_SPAN / 25, lane);
-    if (lane == 0) {
-      double probs[8];
-      probs[0] = L0.c[0] - 0.0;
+    const bool valid = pit <= p.bullpen_len[s] && slot < p.lineup_len[s];   // (warp-uniform)
+    const bool fat = valid && flagged && pit == 0;
+    uint32_t* arow = T.alias[s][pit][tier][slot];
+    if (!valid) {   // unused rows: "always K" (never reached)
+      if (lane < MLBSIM_ROW_WORDS) arow[lane] = 0u;
+    } else {
+      const RowLaw L0 = row_law(p, s, pit, tier, slot, 0.0, lane);
+      RowLaw L1 = L0;
+      if (fat) L1 = row_law(p, s, pit, tier, slot, SLOPE_SPAN / 25, lane);
+      if (lane == 0) {
+        double probs[8];
+        probs[0] = L0.c[0] - 0.0;
 #pragma unroll
-      for (int i = 1; i < 6; ++i) probs[i] = L0.c[i] - L0.c[i - 1];
-      probs[6] = 1.0 - L0.c[5];
-      if (probs[0] + probs[6] < 1.0) can_reach = 1;   // somebody can reach base (K = column 0, OUT = column 6)
-      const double adv = probs[2] * P_FIRST_TO_SECOND;   // tables.py::outcome_variants
-      probs[7] = adv;
-      probs[2] = probs[2] - adv;
-      mlbsim_alias_row(probs, 8, T.alias[s][pit][tier][slot]);
-      if (fat) {
+        for (int i = 1; i < 6; ++i) probs[i] = L0.c[i] - L0.c[i - 1];
+        probs[6] = 1.0 - L0.c[5];
+        if (probs[0] + probs[6] < 1.0) reach = true;       // somebody can reach base (K = column 0, OUT = column 6)
+        const double adv = probs[2] * P_FIRST_TO_SECOND;   // tables.py::outcome_variants
+        probs[7] = adv;
+        probs[2] = probs[2] - adv;
+        mlbsim_alias_row(probs, 8, arow);
+        if (fat) {
 #pragma unroll
-        for (int i = 0; i < 6; ++i) {
-          const long long q0 = quantise31(L0.c[i]), q1 = quantise31(L1.c[i]);
-          T.fthr[s][tier][slot][i] = (uint32_t)q0;
-          T.fslope[s][tier][slot][i] = (int32_t)rint((double)(q1 - q0) / SLOPE_SPAN);
+          for (int i = 0; i < 6; ++i) {
+            const long long q0 = quantise31(L0.c[i]), q1 = quantise31(L1.c[i]);
+            T.fthr[s][tier][slot][i] = (uint32_t)q0;
+            T.fslope[s][tier][slot][i] = (int32_t)rint((double)(q1 - q0) / SLOPE_SPAN);
+          }
         }
       }
     }
+    // pitch-count rows exist for the starters only (pit == 0 owns them); defaults: threshold 2^31, slope 0
+    if (pit == 0 && lane < MLBSIM_ROW_WORDS && (!fat || lane >= 6)) {
+      T.fthr[s][tier][slot][lane] = 2147483648u;
+      T.fslope[s][tier][slot][lane] = 0;
+    }
   }
-  __syncthreads();
-  if (threadIdx.x == 0) status[m] = can_reach ? 0u : 1u;
+  if (reach) atomicOr(&status[m], 1u);
 }

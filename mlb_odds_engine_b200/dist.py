@@ -115,11 +115,29 @@ class ShardedSimulator:
                 self.summary_pinned = torch.zeros(self.world * self.block_cap * swords, dtype=torch.int64).pin_memory()
             self.n_matchups, self.n_total = n_matchups, n_total
 
-    def load_matchups(self, matchups, use_noise=True):
+    def load_matchups(self, matchups, use_noise=True, builder="device"):
         from . import tables
 
         ms = [tables.as_matchup(m, use_noise) for m in matchups]
+        if builder == "device":
+            return self.load_params(tables.params_batch(ms), ms)
         return self.load_tables(tables.build_tables(ms, alias_fn=self.ctx.alias_rows), ms)
+
+    def load_params(self, params, matchups=None):
+        """`params`: PARAMS_DTYPE array of the WHOLE job (`tables.params_batch`, `sweep.grid_params`); this rank's tables
+        are built on its own device (csrc/table_kernel.cu) — a matchup shard builds only its block."""
+        params = np.atleast_1d(params)
+        n_total = len(params)
+        if self.shard == "matchups":
+            self.m_lo, m_hi = shard_range(0, n_total, self.rank, self.world)
+            if m_hi > self.m_lo:
+                self.sim.load_params(params[self.m_lo:m_hi], None if matchups is None else list(matchups)[self.m_lo:m_hi])
+            self.ctx.set_matchup_base(self.m_lo)
+            self._ensure(m_hi - self.m_lo, n_total)
+        else:
+            self.sim.load_params(params, matchups)
+            self._ensure(n_total, n_total)
+        return self
 
     def load_tables(self, tbl, matchups=None):
         """`tbl`: TABLE_DTYPE array of the WHOLE job (may live in pinned memory); one H2D copy of what this rank needs."""
