@@ -154,6 +154,8 @@ def run_sweep(matchups, n_sims: int = 100_000, seed: int = 0, sim: GpuSimulator 
     sim = sim or GpuSimulator(0)
     if isinstance(matchups, np.ndarray) and matchups.dtype == _abi.TABLE_DTYPE:   # prebuilt tables (`grid_tables`)
         sim.load_tables(matchups)
+    elif isinstance(matchups, np.ndarray) and matchups.dtype == _abi.PARAMS_DTYPE:  # raw numbers (`grid_params`): built in HBM
+        sim.load_params(matchups)
     else:
         sim.load_matchups(matchups, use_noise=use_noise)
     rows = [summary_row(r) for r in sim.simulate_summary(n_sims, seed=seed)]
