@@ -82,6 +82,14 @@ __device__ __forceinline__ uint32_t lanemask_lt() {
 }
 
 // window read: entry pos + i of the lane's tape, 0.5 past the end (flagged later through pos > len)
+#ifndef REPLAY_PREFETCH
+#define REPLAY_PREFETCH 32  /* > 0: the plate-appearance window also prefetches the line this many entries ahead of it (REPLAY_PREFETCH_LEVEL
+                               1 = into L1, 2 = into L2); measured +3 % at 32 entries into L1, nothing at 16, worse into L2
+                               (profiles/r02_rp4_prefetch.log) */
+#endif
+#ifndef REPLAY_PREFETCH_LEVEL
+#define REPLAY_PREFETCH_LEVEL 1
+#endif
 #ifndef REPLAY_VEC
 #define REPLAY_VEC 2   /* tape entries per window load: 1 = LDG.64, 2 = LDG.128, 4 = LDG.256 (aligned units) */
 #endif
@@ -94,6 +102,15 @@ __device__ __forceinline__ uint32_t lanemask_lt() {
 template <int N>
 __device__ __forceinline__ void peek_window(const double* p, uint32_t pos, uint32_t len, double (&w)[N]) {
   const double* q = p + pos;
+#if REPLAY_PREFETCH > 0
+  if (N >= 9) {
+#if REPLAY_PREFETCH_LEVEL == 1
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(pos + REPLAY_PREFETCH < len ? q + REPLAY_PREFETCH : q));   // (stays inside this game's tape)
+#else
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(pos + REPLAY_PREFETCH < len ? q + REPLAY_PREFETCH : q));
+#endif
+  }
+#endif
 #if REPLAY_VEC == 1
 #pragma unroll
   for (int i = 0; i < N; ++i) asm volatile("ld.global.nc.L2::256B.f64 %0, [%1];" : "=d"(w[i]) : "l"(q + i));
