@@ -80,13 +80,14 @@ typedef struct mlbsim_replay_game {
  * alias method on 8 columns — the seven outcomes K BB 1B 2B 3B HR OUT, with the single split by the
  * independent 0.8 draw "runner on first takes second" (core/half_inning_simulator.py:105):
  * variant 2 = single, runner holds; variant 7 (MLBSIM_V_1B_ADV) = single, runner advances:
- *     col = w0 >> 29;  e = alias[side][pit][tier][slot][col];
- *     variant = ((w0 & 0x1FFFFFFF) < (e >> 3)) ? col : (e & 7)
- * i.e. one table word per PA.  Starters past 75 pitches (fatigue_modeling.py:38; only possible
+ *     col = w0 >> 29;  e = alias[side][pit][tier][slot][col];      e = (2^29 - 1 - cut) << 3 | alias
+ *     variant = ((w0 & 0x1FFFFFFF) > (e >> 3)) ? col : (e & 7)    (== (w0 << 3) > e: one shift, one compare)
+ * i.e. one table word per PA, and exactly `cut` of the 2^29 draws of a column keep the column's own variant — a
+ * variant of probability 0 never occurs (the complemented cut makes the tie with the alias bits fall to the alias).  Starters past 75 pitches (fatigue_modeling.py:38; only possible
  * for a staff without a bullpen, MLBSIM_FLAG_FATIGUE) use cumulative 31-bit thresholds instead:
  *     u = w0 >> 1;  outcome = #{ j < 6 : u >= fthr[..][j] + (pitch_count - 75) * fslope[..][j] }
  * and take the 0.8 draw from the low 16 bits of w1.                                              */
-#define MLBSIM_TABLE_MAGIC 0x4d4c4232u /* "2BLM": alias rows hold the 8 draw variants */
+#define MLBSIM_TABLE_MAGIC 0x4d4c4233u /* "3BLM": alias rows hold the 8 draw variants, cuts stored complemented */
 #define MLBSIM_V_1B_ADV 7
 #define MLBSIM_ROW_WORDS 8
 #define MLBSIM_FLAG_FATIGUE 1u /* some staff has no bullpen: pitch_count can exceed 75 */
@@ -187,7 +188,7 @@ int mlbsim_upload_tables(mlbsim_ctx* ctx, const mlbsim_table* tables, int n_matc
 int mlbsim_set_matchup_base(mlbsim_ctx* ctx, int base);
 
 /* Table construction helper: Walker alias rows for `n_rows` probability rows of `n_own` (7 or 8) float64 entries each
- * (host pointers; out receives n_rows * 8 words, entry = cut29 << 3 | alias as in mlbsim_table.alias).  Bit-identical
+ * (host pointers; out receives n_rows * 8 words, entry = (2^29 - 1 - cut29) << 3 | alias as in mlbsim_table.alias).  Bit-identical
  * to the host builder (mlb_odds_engine_b200/tables.py::alias_rows): one thread per row runs the same float64
  * operations in the same order.  Replaces nothing in the reference (it samples with np.random.choice per PA,
  * core/pa_simulator.py:54-79); it takes the per-row Python/numpy work out of building 10^3-point sweeps. */

@@ -25,7 +25,7 @@ REPLAY_MAX_USED = 16
 OUTCOMES = ("K", "BB", "1B", "2B", "3B", "HR", "OUT")
 CAPS = (1, 3, 5, 7, None)  # innings cap of joint[c]; None = full game
 
-TABLE_MAGIC = 0x4D4C4232
+TABLE_MAGIC = 0x4D4C4233
 FLAG_FATIGUE = 1
 
 ST_INNINGS_OVERFLOW = 1

@@ -5,8 +5,8 @@
 // to the host's for the same input probabilities.
 //
 // Row law: probabilities p[0..n_own) (n_own = 7 or 8) on 8 columns; q = p * 8 / sum(p); columns with q < 1 are topped up
-// from columns with q >= 1, highest column index first (two stacks).  Entry = cut29 << 3 | alias; a full column is
-// encoded as "cut 0, alias = own outcome".  (What the alias row is for: include/mlbsim.h, native mode.)
+// from columns with q >= 1, highest column index first (two stacks).  Entry = (2^29 - 1 - cut29) << 3 | alias (own outcome
+// iff (draw << 3) > entry: exactly cut29 of a column's 2^29 draws); a full column is encoded as "cut 0, alias = own outcome".  (What the alias row is for: include/mlbsim.h, native mode.)
 #pragma once
 #include <stdint.h>
 
@@ -55,6 +55,6 @@ __device__ __forceinline__ void mlbsim_alias_row(const double* p_in, int n_own, 
     if (full && i < n_own) a = i;
     if (full || i >= n_own) c = 0;
     if (c < 0) c = 0;
-    out[i] = (uint32_t)((c << 3) | (long long)a);
+    out[i] = (uint32_t)(((one - 1 - c) << 3) | (long long)a);   // complemented cut: own iff (w0 << 3) > entry
   }
 }

@@ -387,8 +387,9 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
       // (a half always starts at step 0 of a round: new halves come out of the boundary pass, new games out of the refill)
       if (rep == 0 && hs < HS_FIRST_PA_BELOW) w1_first = w1;
 
-      // Walker alias draw: one shared-memory word per PA.  Entry = cut29 << 3 | alias; the column is kept iff
-      // (w0 << 3) < entry — the low 29 bits of w0 against the cut, the entry's alias bits breaking the (2^-29) tie.
+      // Walker alias draw: one shared-memory word per PA.  Entry = (2^29 - 1 - cut29) << 3 | alias; the column is kept iff
+      // (w0 << 3) > entry — for exactly cut29 of the column's 2^29 draws: the tie with the entry's alias bits falls to
+      // the alias, so an outcome of probability 0 never occurs.
       const uint32_t col = w0 >> 29;
       const uint32_t row = cur & CX_ROW_BYTES;
 #ifdef MLBSIM_DEBUG_BOUNDS   // (compute-sanitizer stand-in: scripts/r02_cycle.sh runs the GPU suite on a build with these traps)
@@ -403,7 +404,7 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
       }
 #endif
       const uint32_t e = lds32(A_ALIAS + row + (col << 2));
-      uint32_t o = ((w0 << 3) < e) ? col : (e & 7u);   // draw variant 0..7 (7 = single, runner on first advances)
+      uint32_t o = ((w0 << 3) > e) ? col : (e & 7u);   // draw variant 0..7 (7 = single, runner on first advances)
       if (FATIGUE) {
         if ((cur & CX_PC_BITS) >= ((uint32_t)(FATIGUE_START + 1) << CX_PC_SHIFT)) {   // past 75 pitches (rare)
           uint32_t T = (cur >> CX_T_SHIFT) & 31u;  // pit*4 + tier
@@ -801,7 +802,7 @@ mlbsim_persim_kernel(const PersimArgs args) {
           } else {
             const uint32_t col = w0 >> 29;
             const uint32_t e = T->alias[side][pit[side]][tier][sl][col];
-            o = ((w0 << 3) < e) ? (int)col : (int)(e & 7u);
+            o = ((w0 << 3) > e) ? (int)col : (int)(e & 7u);
             dB = o == MLBSIM_V_1B_ADV;
             if (dB) o = MLBSIM_1B;
           }

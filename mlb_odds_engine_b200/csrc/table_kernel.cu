@@ -210,7 +210,7 @@ mlbsim_build_tables_kernel(const mlbsim_params* __restrict__ params, mlbsim_tabl
     const bool valid = pit <= p.bullpen_len[s] && slot < p.lineup_len[s];   // (warp-uniform)
     const bool fat = valid && flagged && pit == 0;
     uint32_t* arow = T.alias[s][pit][tier][slot];
-    if (!valid) {   // unused rows: "always K" (never reached)
+    if (!valid) {   // unused rows: zero words (never reached)
       if (lane < MLBSIM_ROW_WORDS) arow[lane] = 0u;
     } else {
       const RowLaw L0 = row_law(p, s, pit, tier, slot, 0.0, lane);

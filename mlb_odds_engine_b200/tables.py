@@ -359,8 +359,10 @@ def outcome_variants(probs) -> np.ndarray:
 
 def alias_row(p) -> np.ndarray:
     """Walker/Vose alias table for 7 or 8 probabilities `p` on 8 columns (with 7, column 7 carries
-    no mass of its own).  Entry = cut << 3 | alias with cut in [0, 2^29): a draw w0 picks column
-    w0 >> 29 and keeps the column's own outcome iff (w0 & (2^29 - 1)) < cut.  Deterministic."""
+    no mass of its own).  Entry = (2^29 - 1 - cut) << 3 | alias with cut in [0, 2^29): a draw w0 picks column
+    w0 >> 29 and keeps the column's own outcome iff (w0 << 3) > entry, i.e. for exactly `cut` of the column's 2^29
+    draws (the complemented form makes the tie with the alias bits fall to the alias: an outcome of probability 0
+    never occurs).  Deterministic."""
     n_own = len(p)
     q = np.zeros(ALIAS_COLS)
     q[:n_own] = np.asarray(p, dtype=np.float64) * ALIAS_COLS / float(np.sum(p))
@@ -381,14 +383,14 @@ def alias_row(p) -> np.ndarray:
     one = 1 << ALIAS_FRAC_BITS
     out = np.zeros(ALIAS_COLS, dtype=np.uint32)
     for i in range(ALIAS_COLS):
-        c = int(math.floor(cut[i] * one + 0.5))
+        c = int(math.floor(cut[i] * one + 0.5))     # how many of the column's 2^29 draws keep the column's own outcome
         a = int(alias[i])
         if c >= one:             # full column: encode as "always alias" with alias = own outcome
             c, a = 0, (i if i < n_own else a)
         if i >= n_own:
             c = 0
         c = max(c, 0)
-        out[i] = (c << 3) | a
+        out[i] = ((one - 1 - c) << 3) | a
     return out
 
 
@@ -442,17 +444,17 @@ def alias_rows(P) -> np.ndarray:
     full = c >= one
     a = np.where(full & (cols < n_own), cols, alias)
     c = np.where(full | (cols >= n_own), 0, np.maximum(c, 0))
-    return ((c << 3) | a).astype(np.uint32)
+    return (((one - 1 - c) << 3) | a).astype(np.uint32)
 
 
 def alias_variant_probabilities(row) -> np.ndarray:
     """Exact probabilities of the 8 draw variants an alias row encodes (for tests)."""
-    one = float(1 << ALIAS_FRAC_BITS)
+    one = 1 << ALIAS_FRAC_BITS
     p = np.zeros(8)
     for col in range(ALIAS_COLS):
-        c, a = int(row[col]) >> 3, int(row[col]) & 7
-        p[col] += c / one / ALIAS_COLS
-        p[a] += (1.0 - c / one) / ALIAS_COLS
+        c, a = one - 1 - (int(row[col]) >> 3), int(row[col]) & 7      # exactly c of the column's 2^29 draws keep `col`
+        p[col] += c / float(one) / ALIAS_COLS
+        p[a] += (1.0 - c / float(one)) / ALIAS_COLS
     return p
 
 
@@ -637,7 +639,7 @@ def tables_from_arrays(A: dict, validate: bool = True, alias_fn=None) -> np.ndar
     slot = np.arange(B_)[None, None, None, None, :]
     valid = (pit <= A["bullpen_len"][:, :, None, None, None]) & (slot < A["lineup_len"][:, :, None, None, None])
     valid = np.broadcast_to(valid, (n, 2, P_, T_, B_))
-    alias = np.zeros((n,) + _abi.TABLE_DTYPE["alias"].shape, dtype=np.uint32)   # unused rows: always K (never reached)
+    alias = np.zeros((n,) + _abi.TABLE_DTYPE["alias"].shape, dtype=np.uint32)   # unused rows: zero words (never reached)
     fthr = np.full((n,) + _abi.TABLE_DTYPE["fthr"].shape, 2147483648, dtype=np.uint32)
     fslope = np.zeros((n,) + _abi.TABLE_DTYPE["fslope"].shape, dtype=np.int32)
     c0, inv0, where = _cdf_tensor(A, valid, 0.0)

@@ -565,7 +565,7 @@ static void native_game(const mlbsim_table* T, uint32_t matchup, uint32_t key, u
              by the 0.8 draw (variant 7 = single on which the runner on first advances) */
           uint32_t col = w[0] >> 29;
           uint32_t e = T->alias[side][st[side].pit][tier][sl][col];
-          o = ((uint32_t)(w[0] << 3) < e) ? (int)col : (int)(e & 7u); /* entry = cut29 << 3 | alias: the alias bits break the 2^-29 tie */
+          o = ((uint32_t)(w[0] << 3) > e) ? (int)col : (int)(e & 7u); /* entry = (2^29 - 1 - cut29) << 3 | alias: exactly cut29 of the column's 2^29 draws keep it */
           dB = (o == MLBSIM_V_1B_ADV);
           if (dB) o = MLBSIM_1B;
         }

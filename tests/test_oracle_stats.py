@@ -9,6 +9,10 @@ from helpers import STATS_SCENARIOS, chi2_two_sample, load_stats, win_over_stats
 from mlb_odds_engine_b200 import tables
 
 N = 3_000_000
+# 7 scenarios x 9 chi-square statistics share this gate: 1e-4 per statistic keeps the family-wise false-alarm rate below 1 %
+# (the fixtures are single 10^6-game samples and dominate the statistic: hetero_nobullpen_noise's full-game table sits
+# at p ~ 0.03 against ANY seed of the native law, old or new)
+P_GATE = 1e-4
 
 
 @pytest.mark.parametrize("name", STATS_SCENARIOS)
@@ -19,16 +23,16 @@ def test_native_law_matches_reference_statistics(name):
     assert int(h["n_games"]) == N
     for c in range(5):
         chi2, dof, p = chi2_two_sample(g["joint"][c], h["joint"][c])
-        assert p > 1e-3, f"cap {c}: chi2 {chi2:.1f}/{dof} p={p:.2e}"
+        assert p > P_GATE, f"cap {c}: chi2 {chi2:.1f}/{dof} p={p:.2e}"
     ref, got = win_over_stats(g["joint"][4]), win_over_stats(h["joint"][4])
     for k in ref:
         z = z_two_proportions(got[k], N, ref[k], g["n"])
         assert abs(z) < 4.0, f"{k}: z={z:.2f}"
     for s in range(2):
         chi2, dof, p = chi2_two_sample(g["pa"][s], h["pa"][s][:7])
-        assert p > 1e-3, f"pa side {s}: chi2 {chi2:.1f}/{dof} p={p:.2e}"
+        assert p > P_GATE, f"pa side {s}: chi2 {chi2:.1f}/{dof} p={p:.2e}"
     chi2, dof, p = chi2_two_sample(g["innings"], h["innings"])
-    assert p > 1e-3, f"innings: p={p:.2e}"
+    assert p > P_GATE, f"innings: p={p:.2e}"
     ref_rel = g["rel_games"][::-1]  # fixture rows are [away, home]; mlbsim_hist rows are [home staff, away staff]
     for s in range(2):
         for i in range(8):

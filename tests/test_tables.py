@@ -86,7 +86,7 @@ def test_alias_rows_degenerate_and_uniform():
         assert tables.alias_probabilities(row).tolist() == [float(x) for x in p]   # exactly, no 2^-32 leak
     row = tables.alias_row([1 / 7] * 7)
     assert np.abs(tables.alias_probabilities(row) - 1 / 7).max() < 2.0**-31
-    assert (row >> 3).max() < 2**29 and (row[7] >> 3) == 0
+    assert (row >> 3).max() < 2**29 and (row[7] >> 3) == 2**29 - 1      # column 7 of a 7-outcome row never keeps itself (complemented cut)
     # eight variants: all columns carry mass; batch builder = row builder
     rng = np.random.default_rng(5)
     P = tables.outcome_variants(rng.dirichlet(np.ones(7), size=500))
@@ -203,3 +203,37 @@ def test_matchup_that_cannot_score_is_refused():
     for b in m["home_lineup"]:
         b["k_rate"] = 0.2
     assert len(tables.build_tables([m], use_noise=False)) == 1
+
+
+def test_alias_draw_rule_is_exact_on_the_tie():
+    """include/mlbsim.h: variant = ((w0 << 3) > e) ? col : (e & 7) with e = (2^29 - 1 - cut) << 3 | alias.  Exactly `cut` of
+    a column's 2^29 draws keep the column — checked on the draws either side of the cut — and a column whose own
+    outcome has probability 0 never returns it, not even on the draw whose fraction ties with the stored cut (the
+    alias bits sit BELOW the cut in the compared word; storing the cut complemented makes that tie fall to the alias)."""
+    one = 1 << 29
+
+    def variant(w0, row):
+        col = w0 >> 29
+        e = int(row[col])
+        fast = col if ((w0 << 3) & 0xFFFFFFFF) > e else e & 7
+        assert fast == (col if (w0 & (one - 1)) > (e >> 3) else e & 7)      # the two statements of the header agree
+        return fast
+
+    rng = np.random.default_rng(3)
+    P = tables.outcome_variants(rng.dirichlet(np.full(7, 0.5), size=200))
+    P[:50, 0] = 0.0                      # K impossible
+    P[:50] /= P[:50].sum(axis=1, keepdims=True)
+    for p, row in zip(P, tables.alias_rows(P)):
+        for col in range(8):
+            cut = one - 1 - (int(row[col]) >> 3)            # draws of this column that keep it
+            alias = int(row[col]) & 7
+            keep = [variant((col << 29) | f, row) == col for f in (0, 1, one - cut - 1, one - cut, one - 2, one - 1) if 0 <= f < one]
+            fr = [f for f in (0, 1, one - cut - 1, one - cut, one - 2, one - 1) if 0 <= f < one]
+            for f, k in zip(fr, keep):
+                if alias != col:
+                    assert k == (f >= one - cut), (col, f, cut)     # the top `cut` fractions keep the column, nothing else
+            if p[col] == 0.0:
+                assert cut == 0 or alias == col
+                assert all(variant((col << 29) | f, row) != col or alias == col for f in (0, 1, 2, one - 1))
+        got = tables.alias_variant_probabilities(row)
+        assert got[0] == 0.0 if p[0] == 0.0 else True
