@@ -41,6 +41,7 @@ struct mlbsim_ctx {
   int threads_per_block = 0;
   int blocks_per_sm = 0;
   int occ_threads = -1, occ_blocks = 0;   // cached occupancy query of the native kernel
+  bool replay_attr_set = false;           // the replay kernels have been granted their dynamic shared memory on this device
   bool nodes_set = false;                 // quadrature nodes of the table builder are in this device's constant memory
   uint64_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -561,8 +562,14 @@ int mlbsim_run_replay_dev(mlbsim_ctx* ctx, const mlbsim_params* params_host, con
     if (chunk < 32) chunk = 32;
     if (chunk > 256) chunk = 256;
     CK(ctx, cudaMemsetAsync(ctx->counters_dev, 0, sizeof(unsigned long long), ctx->stream));
-    if (params_host->use_noise) mlbsim_replay_flat_kernel<<<grid, threads, 0, ctx->stream>>>(a, ctx->counters_dev, (uint32_t)chunk);
-    else mlbsim_replay_flat_nonoise_kernel<<<grid, threads, 0, ctx->stream>>>(a, ctx->counters_dev, (uint32_t)chunk);
+    const size_t dyn = MLBSIM_REPLAY_DYN_SMEM;
+    if (dyn > 0 && !ctx->replay_attr_set) {   // the per-lane tape rings: more than the 48 KB a kernel gets without asking
+      CK(ctx, cudaFuncSetAttribute(mlbsim_replay_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+      CK(ctx, cudaFuncSetAttribute(mlbsim_replay_flat_nonoise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+      ctx->replay_attr_set = true;
+    }
+    if (params_host->use_noise) mlbsim_replay_flat_kernel<<<grid, threads, dyn, ctx->stream>>>(a, ctx->counters_dev, (uint32_t)chunk);
+    else mlbsim_replay_flat_nonoise_kernel<<<grid, threads, dyn, ctx->stream>>>(a, ctx->counters_dev, (uint32_t)chunk);
   }
   CK(ctx, cudaGetLastError());
   CK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));

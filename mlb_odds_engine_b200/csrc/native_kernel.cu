@@ -58,6 +58,12 @@
 #ifndef OPT_PIPELINE_PHILOX
 #define OPT_PIPELINE_PHILOX 1  /* 1: the Philox block of a lane's next plate appearance is drawn one step ahead, inside the current step's basic block (+1.2 %, profiles/r02_v22_variants.log) */
 #endif
+#ifndef OPT_REFILL_INLINE
+#define OPT_REFILL_INLINE 0  /* 1: a lane whose game ends takes its next sim right there in the boundary pass (one shared-memory fetch-and-add
+                                on the warp's chunk cursor); the warp-wide ballot refill at the top of a round then runs only when the chunk is used
+                                up.  Bit-exact, but -0.7 %: the returning ATOMS inside the divergent game-over branch costs more than the ballot
+                                refill it saves (profiles/r02_v25_variants.log) */
+#endif
 #ifndef OPT_TMA
 #define OPT_TMA 1      /* 1: tables reach shared memory as cp.async.bulk copies of the pre-laid-out device image (mbarrier completion) */
 #endif
@@ -108,6 +114,9 @@ struct __align__(16) Smem {
   uint32_t rel_picks[16];
   uint32_t truncated;
   uint32_t go;  // block-uniform "this matchup still has work"
+#if OPT_REFILL_INLINE
+  uint32_t wnext[MLBSIM_NATIVE_MAX_THREADS / 32];   // per warp: next unassigned sim of the warp's chunk (offset from sim_lo)
+#endif
   unsigned long long mbar;   // completion barrier of the table copies
 };
 constexpr int PA_FIELDS = 16;  // [side][draw variant]: the two single variants are added up at the flush
@@ -159,6 +168,12 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   return v;
 }
 __device__ __forceinline__ void red_inc_shared(uint32_t addr) { asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr)); }
+__device__ __forceinline__ uint32_t fetch_inc_shared(uint32_t addr) {
+  uint32_t v;
+  asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 
 // ---- bulk-copy engine (TMA, 1-D form) + mbarrier ------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t arrivals) {
@@ -319,6 +334,12 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
   const uint32_t pa_mine = smem_dynamic_base() + DYN_JOINT_BYTES + threadIdx.x * 4u;
 #endif
 
+#if OPT_REFILL_INLINE
+  const uint32_t A_WNEXT = sb + (uint32_t)offsetof(Smem, wnext) + (threadIdx.x >> 5) * 4u;
+  if (lane == 0) sts32(A_WNEXT, 0u);
+  __syncwarp();
+#endif
+
   // ---- warp-uniform work state ----
   uint32_t chunk_next = 0, chunk_end = 0;
   bool exhausted = false;
@@ -347,6 +368,13 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
     if (__any_sync(0xffffffffu, hs == HS_DEAD)) {
 #endif
       const uint32_t need = __ballot_sync(0xffffffffu, hs == HS_DEAD);
+#if OPT_REFILL_INLINE
+      // the chunk cursor lives in shared memory (lanes advance it on their own when their game ends; it may have run
+      // past the end of the chunk by the number of lanes that found it empty)
+      chunk_next = lds32(A_WNEXT);
+      if (chunk_next > chunk_end) chunk_next = chunk_end;
+      __syncwarp();
+#endif
       if (chunk_next >= chunk_end && !exhausted) {
         unsigned long long base = 0;
         if (lane == 0) base = atomicAdd(counter, (unsigned long long)args.chunk);
@@ -370,6 +398,10 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
       }
       const uint32_t want = __popc(need);
       chunk_next += want < avail ? want : avail;
+#if OPT_REFILL_INLINE
+      if (lane == 0) sts32(A_WNEXT, chunk_next);
+      __syncwarp();
+#endif
       if (exhausted && !__any_sync(0xffffffffu, hs != HS_DEAD)) break;
     }
 
@@ -525,6 +557,18 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
           red_inc_shared(A_INN + ((inn < MLBSIM_INN_BINS - 1 ? inn : MLBSIM_INN_BINS - 1) << 2));
           if (a_ == h_) red_inc_shared(A_TRUNC);
           hs = HS_DEAD;
+#if OPT_REFILL_INLINE
+          // next game of this lane: the next unassigned sim of the warp's chunk, if there is one (which lane plays a sim
+          // does not matter to its result); if not, the lane stays dead until the ballot refill has fetched a chunk
+          const uint32_t k = fetch_inc_shared(A_WNEXT);
+          if (k < chunk_end) {
+            const unsigned long long sim = (unsigned long long)args.sim_lo + k;
+            c0 = (uint32_t)sim;
+            c1 = ((uint32_t)(sim >> 32) << RNG_SIMHI_SHIFT) | rng_matchup;
+            cur = init0; oth = init1;
+            sc = 0; hidx = 0; hs = hs_new_half; used = 0;
+          }
+#endif
         }
       }
     }

@@ -69,9 +69,17 @@ extern "C" cudaError_t mlbsim_table_set_nodes(const double* y, const double* w, 
 
 size_t mlbsim_native_smem_bytes(int threads_per_block);
 #define MLBSIM_SUMMARY_THREADS 256
+// Replay kernel.  MLBSIM_REPLAY_RING = 1: every lane streams its tape through a 256-byte ring of its own in shared memory
+// (cp.async, each byte fetched from HBM once, the plate-appearance window read with LDS); 0: windows loaded straight from
+// global memory (the round-2 "flat" kernel, kept for A/B).
+#ifndef MLBSIM_REPLAY_RING
+#define MLBSIM_REPLAY_RING 1
+#endif
+#define MLBSIM_REPLAY_RING_LANE_BYTES 256
 #ifndef MLBSIM_REPLAY_FLAT_THREADS
-#define MLBSIM_REPLAY_FLAT_THREADS 256
+#define MLBSIM_REPLAY_FLAT_THREADS (MLBSIM_REPLAY_RING ? 768 : 256)
 #endif
 #ifndef MLBSIM_REPLAY_FLAT_BLOCKS
-#define MLBSIM_REPLAY_FLAT_BLOCKS 3   /* 768 threads per SM at 80 registers (the 11-entry tape window lives in registers): measured best (profiles/r02_rp1.log, r02_rp4.log) */
+#define MLBSIM_REPLAY_FLAT_BLOCKS (MLBSIM_REPLAY_RING ? 1 : 3)   /* 768 threads per SM at 80 registers either way; the rings take 192 KB of shared memory */
 #endif
+#define MLBSIM_REPLAY_DYN_SMEM (MLBSIM_REPLAY_RING ? (size_t)MLBSIM_REPLAY_FLAT_THREADS * MLBSIM_REPLAY_RING_LANE_BYTES : (size_t)0)

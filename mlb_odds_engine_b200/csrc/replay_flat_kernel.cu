@@ -25,7 +25,13 @@
 #include "native_kernel.h"
 
 #ifndef REPLAY_UNROLL
-#define REPLAY_UNROLL 4
+#define REPLAY_UNROLL 3   /* plate-appearance steps per round (ring kernel: 2 / 3 / 4 / 5 measured, profiles/r02_rp6.log, r02_rp7.log) */
+#endif
+#ifndef REPLAY_STEP_LOOP
+#define REPLAY_STEP_LOOP 0   /* 1: the steps of a round as a real loop (a quarter of the code) instead of unrolled copies */
+#endif
+#ifndef REPLAY_FILL_UNROLL
+#define REPLAY_FILL_UNROLL 0 /* ring fill: granule requests laid out straight-line per step before the general loop (0: the loop alone, +4.5 %: less code, profiles/r02_rp6.log) */
 #endif
 #define REPLAY_FLAT_THREADS MLBSIM_REPLAY_FLAT_THREADS
 #define REPLAY_FLAT_BLOCKS MLBSIM_REPLAY_FLAT_BLOCKS
@@ -156,6 +162,61 @@ __device__ __forceinline__ double take(const double* p, uint32_t& pos, uint32_t 
   return v;
 }
 
+#if MLBSIM_REPLAY_RING
+// ---- per-lane tape ring -------------------------------------------------------------------------
+// Every lane streams its game's tape through RING_BYTES of shared memory of its own: eight 32-byte granules, granule g
+// of the lane's (32-byte aligned) tape in slot g & 7.  cp.async (LDGSTS, 16 bytes each, L1 bypassed) moves every byte
+// from HBM exactly once, asked for up to 256 bytes ahead of the read position; the plate-appearance window is then
+// read with LDS.128 — no L1 wavefront per 8 useful bytes, no window re-reads through a thrashing L1, and the global
+// latency is paid a step ahead instead of inside the step.
+constexpr uint32_t RING_BYTES = MLBSIM_REPLAY_RING_LANE_BYTES;   // 256
+constexpr uint32_t RING_GRANULES = RING_BYTES / 32u;              // 8
+static_assert(RING_BYTES == 256, "ring addressing below assumes 16 units of 16 bytes");
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global.L2::128B [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void lds128_f64(uint32_t addr, double& a, double& b) {
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(addr));
+}
+
+// granule `g` of the lane's tape -> its ring slot (two 16-byte copies)
+__device__ __forceinline__ void ring_fetch(uint32_t ring, const double* p, uint32_t g) {
+  const uint32_t dst = ring | ((g & (RING_GRANULES - 1u)) << 5);
+  const double* src = p + ((size_t)g << 2);
+  cp_async16(dst, src);
+  cp_async16(dst + 16u, src + 2);
+}
+
+// tape entry `idx` of the lane, out of its ring (resident: see the fill rule in the step)
+__device__ __forceinline__ double ring_at(uint32_t ring, uint32_t idx) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(ring | ((idx << 3) & (RING_BYTES - 8u))));
+  return v;
+}
+
+// A window that reaches past the game's last draw (the last plate appearance or two of a game): the entries past the end
+// must read 0.5 (flagged later through pos > len).  Their ring slots hold whatever follows the game in the tape buffer,
+// or nothing yet — put 0.5 there, so that no read in the step has to look at `len`.  (Everything asked for has landed
+// before this is called and nothing past the game's last granule is ever asked for: the patch stays.)
+template <int N>
+__device__ __forceinline__ void ring_patch_tail(uint32_t ring, uint32_t pos, uint32_t len) {
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+    if (pos + (uint32_t)i >= len) asm volatile("st.shared.f64 [%0], %1;" ::"r"(ring | (((pos + (uint32_t)i) << 3) & (RING_BYTES - 8u))), "d"(0.5) : "memory");
+}
+
+__device__ __forceinline__ double ring_take(uint32_t ring, uint32_t& pos, uint32_t len, bool want) {
+  double v = 0.5;
+  if (want) {
+    if (pos < len) v = ring_at(ring, pos);
+    ++pos;
+  }
+  return v;
+}
+#endif
+
 template <bool NOISE>
 __device__ __forceinline__ void replay_body(const ReplayArgs& args, unsigned long long* counter, uint32_t chunk) {
   __shared__ FlatSmem S;
@@ -183,6 +244,13 @@ __device__ __forceinline__ void replay_body(const ReplayArgs& args, unsigned lon
 
   uint32_t chunk_next = 0, chunk_end = 0;
   bool exhausted = false;
+#if MLBSIM_REPLAY_RING
+  extern __shared__ __align__(256) unsigned char replay_ring_smem[];
+  const uint32_t ring = (uint32_t)__cvta_generic_to_shared(replay_ring_smem) + threadIdx.x * RING_BYTES;
+  // Ring coordinates: `tp` is moved back to the 32-byte granule holding the game's first draw and `pos` / `len` count
+  // from there (the 0..3 entries of shift ride in the top bits of `status` and come off again when the game is written).
+  uint32_t req_g = 0, end_g = 0;   // next granule to ask for; granules of this game's tape
+#endif
 
   // lane state
   const double* tp = nullptr;
@@ -213,15 +281,32 @@ __device__ __forceinline__ void replay_body(const ReplayArgs& args, unsigned lon
       if (hs == HS_DEAD && rank < avail) {
         game = chunk_next + rank;
         const uint64_t lo = args.offsets[game], hi = args.offsets[game + 1];
+#if MLBSIM_REPLAY_RING
+        const uint32_t shift = (uint32_t)lo & 3u;
+        tp = args.tape + (lo - shift); len = (uint32_t)(hi - lo) + shift; pos = shift;
+        status = shift << 30;
+        end_g = (len + 3u) >> 2;
+        // the first window (at most entries 3 .. 14 of the aligned tape) needs granules 0 .. 3 before anything else
+#pragma unroll
+        for (uint32_t g = 0; g < 4u; ++g)
+          if (g < end_g) ring_fetch(ring, tp, g);
+        req_g = 4u;
+        cur = 0; oth = 0; sc = 0; hidx = 0; hs = HS_NEW_HALF; nused = 0; pa_cur = 0; pa_oth = 0;
+#else
         tp = args.tape + lo; len = (uint32_t)(hi - lo); pos = 0;
         cur = 0; oth = 0; sc = 0; hidx = 0; hs = HS_NEW_HALF; nused = 0; status = 0; pa_cur = 0; pa_oth = 0;
+#endif
       }
       const uint32_t want = __popc(need);
       chunk_next += want < avail ? want : avail;
       if (exhausted && !__any_sync(0xffffffffu, hs != HS_DEAD)) break;
     }
 
+#if REPLAY_STEP_LOOP
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
     for (int rep = 0; rep < REPLAY_UNROLL; ++rep)
     if ((hs & (HS_OVER | HS_DEAD)) == 0u) {
       // ---------------- one plate appearance (core/pa_simulator.py:91-143) ----------------
@@ -241,21 +326,50 @@ __device__ __forceinline__ void replay_body(const ReplayArgs& args, unsigned lon
       uint32_t o;
       double h1, h2, h3;
       bool is_out, is_1b, held;
+#if MLBSIM_REPLAY_RING
+      {
+        // Fill rule.  Everything asked for before this step has landed after the wait; then ask for the granules up to
+        // 256 bytes past the read position.  A step (plus a boundary pass) moves the position by at most 14 entries =
+        // 4 granules and its window ends at most 3 granules past the position's own, so asking up to position + 8 at
+        // every step keeps the next step's window inside what was asked for one step earlier.
+        cp_async_wait_all();
+        const uint32_t want = (pos >> 2) + RING_GRANULES;
+        const uint32_t lim = want < end_g ? want : end_g;
+#pragma unroll
+        for (int k = 0; k < REPLAY_FILL_UNROLL; ++k)
+          if (req_g < lim) { ring_fetch(ring, tp, req_g); ++req_g; }
+#pragma unroll 1
+        while (req_g < lim) { ring_fetch(ring, tp, req_g); ++req_g; }   // (the first step of a game asks for four)
+      }
+#endif
       if (!noise || (has_k && has_b)) {
         // ---- window path: every draw of this plate appearance sits at a known slot of tape[pos .. pos + B + 8] ----
         constexpr int B = NOISE ? 2 : 0;
+#if MLBSIM_REPLAY_RING
+        // entry by entry out of the ring: the eight leading entries sit at fixed offsets (independent loads), the three
+        // base-running draws at offsets computed below
+        if (pos + (uint32_t)(B + 9) > len) ring_patch_tail<B + 9>(ring, pos, len);
+        const double kp = NOISE ? ring_at(ring, pos) : k;
+        const double bp = __dmul_rn(NOISE ? ring_at(ring, pos + 1u) : bb, 1.01);
+        const double u = ring_at(ring, pos + B), uhr = ring_at(ring, pos + B + 1);   // u_hr is always consumed (:126)
+#else
         double w[B + 9];
         peek_window<B + 9>(tp, pos, len, w);
         const double kp = NOISE ? w[0] : k;
         const double bp = __dmul_rn(NOISE ? w[1] : bb, 1.01);
         const double u = w[B], uhr = w[B + 1];                          // u_hr is always consumed (:126)
+#endif
         const bool is_k = u < kp;
         const bool is_bb = !is_k && (u < __dadd_rn(kp, bp));
         const bool contact = !is_k && !is_bb;
         const bool is_hr = contact && (uhr < P.pit_hr[side][pit]);
         const bool bip = contact && !is_hr;
         // resolve_contact (:51-88)
+#if MLBSIM_REPLAY_RING
+        const double ubip = ring_at(ring, pos + B + 2), uhit = ring_at(ring, pos + B + 3), u7 = ring_at(ring, pos + B + 4), u8 = ring_at(ring, pos + B + 5);
+#else
         const double ubip = w[B + 2], uhit = w[B + 3], u7 = w[B + 4], u8 = w[B + 5];
+#endif
         uint32_t type = (uint32_t)(P.cdf_bip[0] <= ubip) + (uint32_t)(P.cdf_bip[1] <= ubip) + (uint32_t)(P.cdf_bip[2] <= ubip) +
                         (uint32_t)(P.cdf_bip[3] <= ubip);
         if (type > 3u) type = 3u;
@@ -274,35 +388,51 @@ __device__ __forceinline__ void replay_body(const ReplayArgs& args, unsigned lon
         const bool is_2b = o == MLBSIM_2B;
         const bool need1 = (is_out && on1 && outs < 2u) || (is_1b && on2) || (is_2b && on1);   // double play | runner on 2B on a single | runner on 1B on a double
         const bool need2 = is_1b && on1;                                                         // runner on 1B on a single
+#if MLBSIM_REPLAY_RING
+        const uint32_t i1 = pos + (uint32_t)B + 2u + (bip ? 3u + (uint32_t)fb : 0u);
+        const uint32_t i2 = i1 + (uint32_t)need1, i3 = i2 + (uint32_t)need2;
+        h1 = ring_at(ring, i1);
+        h2 = ring_at(ring, i2);   // (read whether or not it is a draw of this plate appearance: the transition ignores what it does not need)
+        h3 = ring_at(ring, i3);
+        held = is_1b && on2 && !(h1 < 0.4);
+        const bool need3 = held && outs == 2u;                                                   // two outs, runner from 2B held at 3B
+        pos = i3 + (uint32_t)need3;
+#else
         h1 = bip ? (fb ? w[B + 6] : w[B + 5]) : w[B + 2];
         h2 = fb ? (need1 ? w[B + 7] : w[B + 6]) : (need1 ? w[B + 6] : w[B + 5]);                 // (a single is always a ball in play)
         held = is_1b && on2 && !(h1 < 0.4);
         const bool need3 = held && outs == 2u;                                                   // two outs, runner from 2B held at 3B
         h3 = need2 ? (fb ? w[B + 8] : w[B + 7]) : (fb ? w[B + 7] : w[B + 6]);                    // (held => need1)
         pos += (uint32_t)B + 2u + (bip ? 3u + (uint32_t)fb : 0u) + (uint32_t)need1 + (uint32_t)need2 + (uint32_t)need3;
+#endif
       } else {
         // ---- degenerate rate (k or bb outside (0, 1)): draw by draw ----
-        const double vk = take(tp, pos, len, has_k);
-        const double vb = take(tp, pos, len, has_b);
+#if MLBSIM_REPLAY_RING
+#define TAKE(want) ring_take(ring, pos, len, (want))
+#else
+#define TAKE(want) take(tp, pos, len, (want))
+#endif
+        const double vk = TAKE(has_k);
+        const double vb = TAKE(has_b);
         const double kp = k <= 0.0 ? 0.0 : k >= 1.0 ? 1.0 : vk;
         double bp = bb <= 0.0 ? 0.0 : bb >= 1.0 ? 1.0 : vb;
         bp = __dmul_rn(bp, 1.01);
-        const double u = take(tp, pos, len, true);
-        const double uhr = take(tp, pos, len, true);
+        const double u = TAKE(true);
+        const double uhr = TAKE(true);
         const bool is_k = u < kp;
         const bool is_bb = !is_k && (u < __dadd_rn(kp, bp));
         const bool contact = !is_k && !is_bb;
         const bool is_hr = contact && (uhr < P.pit_hr[side][pit]);
         const bool bip = contact && !is_hr;
-        const double ubip = take(tp, pos, len, bip);
+        const double ubip = TAKE(bip);
         uint32_t type = (uint32_t)(P.cdf_bip[0] <= ubip) + (uint32_t)(P.cdf_bip[1] <= ubip) + (uint32_t)(P.cdf_bip[2] <= ubip) +
                         (uint32_t)(P.cdf_bip[3] <= ubip);
         if (type > 3u) type = 3u;
-        const double uhit = take(tp, pos, len, bip);
+        const double uhit = TAKE(bip);
         const bool hit = bip && (uhit < P.hit_prob[side][pit][slot][type]);
-        const double u7 = take(tp, pos, len, bip);
+        const double u7 = TAKE(bip);
         const bool fb = bip && !hit && (u7 < 0.10);
-        const double u8 = take(tp, pos, len, fb);
+        const double u8 = TAKE(fb);
         o = MLBSIM_OUT;
         if (hit) o = MLBSIM_1B + (uint32_t)(P.cdf_hit[0] <= u7) + (uint32_t)(P.cdf_hit[1] <= u7) + (uint32_t)(P.cdf_hit[2] <= u7);
         if (fb) o = MLBSIM_1B + (uint32_t)(P.cdf_fb[0] <= u8) + (uint32_t)(P.cdf_fb[1] <= u8);
@@ -312,11 +442,12 @@ __device__ __forceinline__ void replay_body(const ReplayArgs& args, unsigned lon
         is_out = (o == MLBSIM_K) || (o == MLBSIM_OUT);
         is_1b = o == MLBSIM_1B;
         const bool is_2b = o == MLBSIM_2B;
-        h1 = take(tp, pos, len, (is_out && on1 && outs < 2u) || (is_1b && on2) || (is_2b && on1));
-        h2 = take(tp, pos, len, is_1b && on1);
+        h1 = TAKE((is_out && on1 && outs < 2u) || (is_1b && on2) || (is_2b && on1));
+        h2 = TAKE(is_1b && on1);
         held = is_1b && on2 && !(h1 < 0.4);
-        h3 = take(tp, pos, len, held && outs == 2u);
+        h3 = TAKE(held && outs == 2u);
       }
+#undef TAKE
       bool dA;
       if (is_out) dA = h1 < 0.14;
       else if (is_1b) dA = (h1 < 0.4) || (held && outs == 2u && h3 < 0.10);
@@ -341,9 +472,15 @@ __device__ __forceinline__ void replay_body(const ReplayArgs& args, unsigned lon
       uint32_t runs = (hs >> 16) & 63u;
       const bool reached = (hs & HS_REACHED) != 0u;
       // misc run, ghost run, reliever pick: at most three consecutive entries, loaded together
+#if MLBSIM_REPLAY_RING
+      cp_async_wait_all();   // (the granules of these entries were asked for at the last step's start at the latest)
+      if (pos + 3u > len) ring_patch_tail<3>(ring, pos, len);
+      const double b0 = ring_at(ring, pos), b1 = ring_at(ring, pos + 1u), b2 = ring_at(ring, pos + 2u);
+#else
       double bw[3];
       peek_window<3>(tp, pos, len, bw);
       const double b0 = bw[0], b1 = bw[1], b2 = bw[2];
+#endif
       const bool need_m = reached && runs == 0u;
       const double um = b0, ug = need_m ? b1 : b0;
       const double upick = reached ? (need_m ? b2 : b1) : b0;
@@ -385,8 +522,13 @@ __device__ __forceinline__ void replay_body(const ReplayArgs& args, unsigned lon
         if (pos > len) status |= MLBSIM_ST_TAPE_UNDERRUN;
         // side at bat when the game ended: pa_cur belongs to it
         const unsigned long long pa0 = side ? pa_oth : pa_cur, pa1 = side ? pa_cur : pa_oth;
+#if MLBSIM_REPLAY_RING
+        reinterpret_cast<int4*>(R)[0] = make_int4((int)h, (int)a, (int)inning, (int)(pos - (status >> 30)));
+        reinterpret_cast<int4*>(R)[1] = make_int4((int)(nused & 255u), (int)((nused >> 8) & 255u), (int)(status & 0x3FFFFFFFu), 0);
+#else
         reinterpret_cast<int4*>(R)[0] = make_int4((int)h, (int)a, (int)inning, (int)pos);
         reinterpret_cast<int4*>(R)[1] = make_int4((int)(nused & 255u), (int)((nused >> 8) & 255u), (int)status, 0);
+#endif
 #pragma unroll
         for (int o = 0; o < MLBSIM_N_OUTCOMES; ++o) {
           const uint16_t c0 = (uint16_t)((pa0 >> (9 * o)) & 511ull), c1 = (uint16_t)((pa1 >> (9 * o)) & 511ull);

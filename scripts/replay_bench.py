@@ -23,20 +23,29 @@ def main():
     m = synth.make_matchup("2025-04-04-TEX@HOU")
     params = tables.build_params(m)
     t0 = time.time()
-    parts, lens, recs = [], [], []
-    chunk = 25_000
-    for lo in range(0, n, chunk):          # chunked: a 4096-draw stride covers any plausible game
-        hi = min(n, lo + chunk)
-        _, g, tape, tlen = orc.grammar(params, seed=3, game_lo=lo, game_hi=hi, want_games=True, tape_stride=4096)
-        mask = np.arange(4096)[None, :] < tlen[:, None]
-        parts.append(tape[mask])
-        lens.append(tlen)
-        recs.append(g)
-    tlen = np.concatenate(lens)
-    games = np.concatenate(recs)
-    flat = np.concatenate(parts)
-    offsets = np.zeros(n + 1, dtype=np.uint64)
-    offsets[1:] = np.cumsum(tlen)
+    cache = f"/tmp/replay_bench_tapes_{n}.npz"   # (A/B runs of several libraries in one GPU call: generate once)
+    if os.path.exists(cache):
+        z = np.load(cache)
+        flat, offsets, games = z["flat"], z["offsets"], z["games"]
+    else:
+        parts, lens, recs = [], [], []
+        chunk = 25_000
+        for lo in range(0, n, chunk):          # chunked: a 4096-draw stride covers any plausible game
+            hi = min(n, lo + chunk)
+            _, g, tape, tlen = orc.grammar(params, seed=3, game_lo=lo, game_hi=hi, want_games=True, tape_stride=4096)
+            mask = np.arange(4096)[None, :] < tlen[:, None]
+            parts.append(tape[mask])
+            lens.append(tlen)
+            recs.append(g)
+        tlen = np.concatenate(lens)
+        games = np.concatenate(recs)
+        flat = np.concatenate(parts)
+        offsets = np.zeros(n + 1, dtype=np.uint64)
+        offsets[1:] = np.cumsum(tlen)
+        try:
+            np.savez(cache, flat=flat, offsets=offsets, games=games)
+        except OSError:
+            pass
     t_gen = time.time() - t0
     ctx = Context(0)
     d_tape = ctx.malloc(flat.nbytes); ctx.h2d(d_tape, flat)
