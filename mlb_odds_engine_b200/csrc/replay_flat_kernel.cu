@@ -27,8 +27,16 @@
 #ifndef REPLAY_UNROLL
 #define REPLAY_UNROLL 3   /* plate-appearance steps per round (ring kernel: 2 / 3 / 4 / 5 measured, profiles/r02_rp6.log, r02_rp7.log) */
 #endif
+#ifndef REPLAY_RATE_TABLES
+#define REPLAY_RATE_TABLES 3   /* 1: final rates tabulated up to 75 pitches, computed beyond; 2: factored tables (six float64 operations per plate
+                                  appearance) at every pitch count: -2.6 % on a matchup with bullpens, where nobody passes 75 pitches
+                                  (profiles/r02_rp8.log); 3: final rates up to 75 pitches, factored tables beyond */
+#endif
 #ifndef REPLAY_STEP_LOOP
 #define REPLAY_STEP_LOOP 0   /* 1: the steps of a round as a real loop (a quarter of the code) instead of unrolled copies */
+#endif
+#ifndef REPLAY_FILL_NESTED
+#define REPLAY_FILL_NESTED 1 /* ring fill as nested early exits with immediate offsets instead of a loop with pointer increments */
 #endif
 #ifndef REPLAY_FILL_UNROLL
 #define REPLAY_FILL_UNROLL 0 /* ring fill: granule requests laid out straight-line per step before the general loop (0: the loop alone, +4.5 %: less code, profiles/r02_rp6.log) */
@@ -58,10 +66,24 @@ constexpr uint32_t HS_DEAD = 1u << 15;
 
 constexpr int KB_ENTRIES = 2 * MLBSIM_MAX_PITCHERS * MLBSIM_N_TIERS * MLBSIM_MAX_LINEUP;   // 504
 
+constexpr int BASE_ENTRIES = 2 * MLBSIM_MAX_PITCHERS * MLBSIM_N_TIERS;   // 56
+constexpr int FAT_ENTRIES = 64;                                           // pitch counts 75 .. 138 (beyond: computed on the spot)
+
 struct FlatSmem {
   mlbsim_params P;
   uint32_t lut[LUT_WORDS];
+#if REPLAY_RATE_TABLES >= 2
+  // The pitcher's side of the K / BB rates, factored the way core/fatigue_modeling.py:25-43 multiplies it:
+  // base[side][pit][tier] = {pit_k * (1 - tto_penalty), pit_bb * (1 + tto_penalty)}, fat[e] = {1 - 0.02 * fl, 1 + 0.03 * fl} with
+  // fl = max(pitch_count - 75, 0) / 25 — every entry the reference's own operations in the reference's order, so that a
+  // plate appearance at any pitch count is two table reads and the remaining six float64 operations (a starter spends
+  // 15 of his ~90 plate appearances past 75 pitches: computing fl there took a float64 division in most steps).
+  double2 base[BASE_ENTRIES];
+  double2 fat[FAT_ENTRIES];
+#endif
+#if REPLAY_RATE_TABLES != 2
   double2 kb[KB_ENTRIES];   // {k, bb} before noise at pitch_count <= 75: [side][pit][tier][slot]
+#endif
 };
 
 // effective K / BB rates of one plate appearance before noise: fatigue-adjusted pitcher rate averaged with the batter's,
@@ -189,6 +211,13 @@ __device__ __forceinline__ void ring_fetch(uint32_t ring, const double* p, uint3
   cp_async16(dst + 16u, src + 2);
 }
 
+// the same with the granule number as an immediate offset from a base (`so` = byte offset of the base granule, unwrapped)
+__device__ __forceinline__ void ring_fetch_at(uint32_t ring, uint32_t so, const double* src, int k) {
+  const uint32_t dst = ring | ((so + 32u * (uint32_t)k) & (RING_BYTES - 32u));
+  cp_async16(dst, src + 4 * k);
+  cp_async16(dst + 16u, src + 4 * k + 2);
+}
+
 // tape entry `idx` of the lane, out of its ring (resident: see the fill rule in the step)
 __device__ __forceinline__ double ring_at(uint32_t ring, uint32_t idx) {
   double v;
@@ -230,10 +259,24 @@ __device__ __forceinline__ void replay_body(const ReplayArgs& args, unsigned lon
     }
   }
   __syncthreads();
+#if REPLAY_RATE_TABLES >= 2
+  for (int i = threadIdx.x; i < BASE_ENTRIES; i += blockDim.x) {
+    const uint32_t tier = (uint32_t)i % MLBSIM_N_TIERS, sp = (uint32_t)i / MLBSIM_N_TIERS;
+    const double pen = tier == 0 ? 0.0 : tier == 1 ? 0.015 : tier == 2 ? 0.035 : 0.060;
+    S.base[i] = make_double2(__dmul_rn(S.P.pit_k[sp / MLBSIM_MAX_PITCHERS][sp % MLBSIM_MAX_PITCHERS], __dsub_rn(1.0, pen)),
+                             __dmul_rn(S.P.pit_bb[sp / MLBSIM_MAX_PITCHERS][sp % MLBSIM_MAX_PITCHERS], __dadd_rn(1.0, pen)));
+  }
+  for (int e = threadIdx.x; e < FAT_ENTRIES; e += blockDim.x) {
+    const double fl = __ddiv_rn((double)e, 25.0);   // e = max(pitch_count - 75, 0)
+    S.fat[e] = make_double2(__dsub_rn(1.0, __dmul_rn(0.02, fl)), __dadd_rn(1.0, __dmul_rn(0.03, fl)));
+  }
+#endif
+#if REPLAY_RATE_TABLES != 2
   for (int i = threadIdx.x; i < KB_ENTRIES; i += blockDim.x) {
     const uint32_t slot = (uint32_t)i % MLBSIM_MAX_LINEUP, g = (uint32_t)i / MLBSIM_MAX_LINEUP;
     S.kb[i] = effective_rates(S.P, g / (MLBSIM_MAX_PITCHERS * MLBSIM_N_TIERS), (g / MLBSIM_N_TIERS) % MLBSIM_MAX_PITCHERS, g % MLBSIM_N_TIERS, slot, 0);
   }
+#endif
   __syncthreads();
   const mlbsim_params& P = S.P;
   const int lane = threadIdx.x & 31;
@@ -315,8 +358,25 @@ __device__ __forceinline__ void replay_body(const ReplayArgs& args, unsigned lon
       const uint32_t tier = (cur >> 4) & 3u;
       const uint32_t pit = (cur >> CX_PIT_SHIFT) & 7u;
       const int pc = (int)(cur >> CX_PC_SHIFT);
+#if REPLAY_RATE_TABLES >= 2
+      double2 rates;
+#if REPLAY_RATE_TABLES == 3
+      if (pc <= 75) {
+        rates = S.kb[((side * MLBSIM_MAX_PITCHERS + pit) * MLBSIM_N_TIERS + tier) * MLBSIM_MAX_LINEUP + slot];
+      } else
+#endif
+      if (pc < 75 + FAT_ENTRIES) {
+        const double2 b = S.base[(side * MLBSIM_MAX_PITCHERS + pit) * MLBSIM_N_TIERS + tier];
+        const double2 f = S.fat[pc > 75 ? pc - 75 : 0];
+        rates.x = __dmul_rn(__ddiv_rn(__dadd_rn(P.bat_k[side][slot], __dmul_rn(b.x, f.x)), 2.0), P.k_mod);
+        rates.y = __dmul_rn(__ddiv_rn(__dadd_rn(P.bat_bb[side][slot], __dmul_rn(b.y, f.y)), 2.0), P.bb_mod);
+      } else {
+        rates = effective_rates(P, side, pit, tier, slot, pc);
+      }
+#else
       const double2 rates = pc <= 75 ? S.kb[((side * MLBSIM_MAX_PITCHERS + pit) * MLBSIM_N_TIERS + tier) * MLBSIM_MAX_LINEUP + slot]
                                      : effective_rates(P, side, pit, tier, slot, pc);
+#endif
       const double k = rates.x, bb = rates.y;
       // beta_noise (core/pa_simulator.py:23-32): a draw only when 0 < p < 1
       const bool has_k = noise && k > 0.0 && k < 1.0, has_b = noise && bb > 0.0 && bb < 1.0;
@@ -335,11 +395,33 @@ __device__ __forceinline__ void replay_body(const ReplayArgs& args, unsigned lon
         cp_async_wait_all();
         const uint32_t want = (pos >> 2) + RING_GRANULES;
         const uint32_t lim = want < end_g ? want : end_g;
+#if REPLAY_FILL_NESTED
+        // up to four granules per step (the first step of a game asks for four, a step after a maximal step and a boundary
+        // pass likewise): nested early exits, addresses as immediates off one base
+        if (req_g < lim) {
+          const uint32_t n = lim - req_g;
+#ifdef MLBSIM_DEBUG_BOUNDS
+          if (n > 4u) __trap();   // a step plus a boundary pass moves the position by at most 14 entries
+#endif
+          const double* src = tp + ((size_t)req_g << 2);
+          const uint32_t so = req_g << 5;
+          req_g = lim;
+          ring_fetch_at(ring, so, src, 0);
+          if (n > 1u) {
+            ring_fetch_at(ring, so, src, 1);
+            if (n > 2u) {
+              ring_fetch_at(ring, so, src, 2);
+              if (n > 3u) ring_fetch_at(ring, so, src, 3);
+            }
+          }
+        }
+#else
 #pragma unroll
         for (int k = 0; k < REPLAY_FILL_UNROLL; ++k)
           if (req_g < lim) { ring_fetch(ring, tp, req_g); ++req_g; }
 #pragma unroll 1
         while (req_g < lim) { ring_fetch(ring, tp, req_g); ++req_g; }   // (the first step of a game asks for four)
+#endif
       }
 #endif
       if (!noise || (has_k && has_b)) {

@@ -20,10 +20,11 @@ from mlb_odds_engine_b200._lib import Context  # noqa: E402
 
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 400_000
-    m = synth.make_matchup("2025-04-04-TEX@HOU")
+    bullpens = "--no-bullpens" not in sys.argv   # no bullpens: starters pitch on past 75 pitches (fatigue ramp, TTO 4+)
+    m = synth.make_matchup("2025-04-04-TEX@HOU", bullpens=bullpens)
     params = tables.build_params(m)
     t0 = time.time()
-    cache = f"/tmp/replay_bench_tapes_{n}.npz"   # (A/B runs of several libraries in one GPU call: generate once)
+    cache = f"/tmp/replay_bench_tapes_{n}_{int(bullpens)}.npz"   # (A/B runs of several libraries in one GPU call: generate once)
     if os.path.exists(cache):
         z = np.load(cache)
         flat, offsets, games = z["flat"], z["offsets"], z["games"]
@@ -66,7 +67,7 @@ def main():
     except Exception:
         pass
     print(json.dumps({
-        "mode": "replay", "games": n, "draws": int(len(flat)), "bit_exact_vs_oracle": bool(ok), "kernel_ms": best,
+        "mode": "replay", "bullpens": bullpens, "games": n, "draws": int(len(flat)), "bit_exact_vs_oracle": bool(ok), "kernel_ms": best,
         "games_per_s": n / (best * 1e-3), "algorithmic_bytes": int(bytes_alg), "achieved_gbs": bytes_alg / (best * 1e-3) / 1e9,
         "hbm_peak_gbs": peaks.get("hbm_gbs"), "frac_of_hbm": (bytes_alg / (best * 1e-3) / 1e9) / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None,
         "tape_generation_s_cpu": t_gen,

@@ -1,11 +1,11 @@
 #!/bin/bash
 # On the GPU box: replay-mode throughput (scripts/replay_bench.py, bit-exactness checked in the same run) for the
-# product library and every variants/libmlbsim_rp*.so.  usage: bash scripts/replay_variant_bench.sh <tag> [n_games]
-TAG=${1:-replay}; N=${2:-800000}
+# product library and every variants/libmlbsim_rp*.so.  usage: bash scripts/replay_variant_bench.sh <tag> [n_games] [--no-bullpens]
+TAG=${1:-replay}; N=${2:-800000}; EXTRA=${3:-}
 mkdir -p gpurun_out; LOG=gpurun_out/${TAG}.log; : > $LOG
 for lib in mlb_odds_engine_b200/libmlbsim_b200.so variants/libmlbsim_rp*.so; do
   [ -f "$lib" ] || continue
-  MLBSIM_LIB=$PWD/$lib python scripts/replay_bench.py $N 2>gpurun_out/_rp.err | tail -1 > gpurun_out/_rp.json
+  MLBSIM_LIB=$PWD/$lib python scripts/replay_bench.py $N $EXTRA 2>gpurun_out/_rp.err | tail -1 > gpurun_out/_rp.json
   python - "$lib" >> $LOG <<'PY'
 import json, sys
 try:
