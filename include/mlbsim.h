@@ -262,10 +262,10 @@ int mlbsim_run_persim(mlbsim_ctx* ctx, int matchup, uint64_t sim_lo, uint64_t si
 int mlbsim_run_replay(mlbsim_ctx* ctx, const mlbsim_params* params, const double* tape,
                       const uint64_t* tape_offsets, int64_t n_games, mlbsim_replay_game* out);
 
-/* Device-pointer variant (tape, offsets and out already resident in HBM); asynchronous.  The kernel loads the tape
- * in windows of up to 11 entries as aligned 16-byte units, so `tape_dev` must be 16-byte aligned and READABLE for 16
- * entries (128 bytes) past the last draw (tape_offsets[n_games]); what the slack holds does not matter.  Buffers from
- * mlbsim_malloc qualify. */
+/* Device-pointer variant (tape, offsets and out already resident in HBM); asynchronous.  The kernel streams every game's
+ * tape into shared memory in aligned 32-byte granules (16-byte cp.async copies), so `tape_dev` must be 16-byte aligned
+ * and READABLE for 16 entries (128 bytes) past the last draw (tape_offsets[n_games]); what the slack holds does not
+ * matter.  Buffers from mlbsim_malloc qualify.  Per-game outcome counters are exact below 512 equal outcomes per side. */
 int mlbsim_run_replay_dev(mlbsim_ctx* ctx, const mlbsim_params* params_host, const double* tape_dev,
                           const uint64_t* tape_offsets_dev, int64_t n_games, mlbsim_replay_game* out_dev);
 
