@@ -77,9 +77,9 @@ size_t mlbsim_native_smem_bytes(int threads_per_block);
 #endif
 #define MLBSIM_REPLAY_RING_LANE_BYTES 256
 #ifndef MLBSIM_REPLAY_FLAT_THREADS
-#define MLBSIM_REPLAY_FLAT_THREADS (MLBSIM_REPLAY_RING ? 768 : 256)
+#define MLBSIM_REPLAY_FLAT_THREADS (MLBSIM_REPLAY_RING ? 800 : 256)   /* ring: 25 warps = what 80 registers allow (768 / 800 / 832 at 72 registers: 5.79 / 5.95 / 5.94e8, profiles/r02_rp10.log) */
 #endif
 #ifndef MLBSIM_REPLAY_FLAT_BLOCKS
-#define MLBSIM_REPLAY_FLAT_BLOCKS (MLBSIM_REPLAY_RING ? 1 : 3)   /* 768 threads per SM at 80 registers either way; the rings take 192 KB of shared memory */
+#define MLBSIM_REPLAY_FLAT_BLOCKS (MLBSIM_REPLAY_RING ? 1 : 3)   /* the rings take 200 KB of shared memory; the window-load kernel runs 3 x 256 threads */
 #endif
 #define MLBSIM_REPLAY_DYN_SMEM (MLBSIM_REPLAY_RING ? (size_t)MLBSIM_REPLAY_FLAT_THREADS * MLBSIM_REPLAY_RING_LANE_BYTES : (size_t)0)

@@ -15,7 +15,7 @@
 // use.  A plate appearance reads its entries from the ring with LDS.64: the eight leading entries at fixed offsets
 // (independent loads), the three base-running draws at offsets the grammar computes.  The last entries of a game are
 // patched to 0.5 in the ring (what a read past the end of the tape must yield), so no read in the step looks at the
-// tape length.  768 threads per SM (one block), 192 KB of rings.  Measured: 5.7e8 games/s against 5.1e8 for the window
+// tape length.  800 threads per SM (one block), 200 KB of rings.  Measured: 5.7e8 games/s against 5.1e8 for the window
 // loads it replaces (profiles/r02_rp5 .. rp9.log); the kernel is now bound by instruction issue and dependent latencies
 // (issue active 61 %, long-scoreboard stalls 0.7 per issue, was 5.9), no longer by L1 wavefronts.
 //
