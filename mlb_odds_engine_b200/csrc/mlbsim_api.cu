@@ -546,7 +546,10 @@ int mlbsim_run_replay_dev(mlbsim_ctx* ctx, const mlbsim_params* params_host, con
   // and a second call cannot overwrite it under a copy still in flight.
   std::memcpy(&ctx->params_stage, params_host, sizeof(mlbsim_params));
   CK(ctx, cudaMemcpyAsync(ctx->params_dev, &ctx->params_stage, sizeof(mlbsim_params), cudaMemcpyHostToDevice, ctx->stream));
-  ReplayArgs a{ctx->params_dev, tape_dev, tape_offsets_dev, out_dev, (long long)n_games};
+  ReplayArgs a{ctx->params_dev, tape_dev, tape_offsets_dev, out_dev, (long long)n_games, {}, {}, {}};
+  std::memcpy(a.cdf_bip, params_host->cdf_bip, sizeof(a.cdf_bip));
+  std::memcpy(a.cdf_hit, params_host->cdf_hit, sizeof(a.cdf_hit));
+  std::memcpy(a.cdf_fb, params_host->cdf_fb, sizeof(a.cdf_fb));
   if (ctx->counters_cap < 1) {
     CK(ctx, cudaMalloc(&ctx->counters_dev, sizeof(unsigned long long)));
     ctx->counters_cap = 1;

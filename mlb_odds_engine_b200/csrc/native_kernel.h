@@ -40,6 +40,9 @@ struct ReplayArgs {
   const uint64_t* offsets;      // device, n_games + 1
   mlbsim_replay_game* out;      // device
   long long n_games;
+  // the launch-uniform split points of resolve_contact, by value: kernel arguments sit in the constant bank, so a compare
+  // reads them as an operand (no shared-memory load, no register)
+  double cdf_bip[4], cdf_hit[3], cdf_fb[2];
 };
 
 struct PersimArgs {

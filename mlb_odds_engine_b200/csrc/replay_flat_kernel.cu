@@ -39,6 +39,9 @@
 #ifndef REPLAY_UNROLL
 #define REPLAY_UNROLL 3   /* plate-appearance steps per round (ring kernel: 2 / 3 / 4 / 5 measured, profiles/r02_rp6.log, r02_rp7.log) */
 #endif
+#ifndef REPLAY_STRAIGHT
+#define REPLAY_STRAIGHT MLBSIM_REPLAY_RING   /* 1: the plate appearance as straight-line code (every compare evaluated, bit operations, split points from the constant bank) */
+#endif
 #ifndef REPLAY_RATE_TABLES
 #define REPLAY_RATE_TABLES 3   /* 1: final rates tabulated up to 75 pitches, computed beyond; 2: factored tables (six float64 operations per plate
                                   appearance) at every pitch count: -2.6 % on a matchup with bullpens, where nobody passes 75 pitches
@@ -453,6 +456,32 @@ __device__ __forceinline__ void replay_body(const ReplayArgs& args, unsigned lon
         const double bp = __dmul_rn(NOISE ? w[1] : bb, 1.01);
         const double u = w[B], uhr = w[B + 1];                          // u_hr is always consumed (:126)
 #endif
+#if REPLAY_STRAIGHT
+        // every compare evaluated, outcomes combined with bit operations: straight-line code instead of a branch (and a
+        // reconvergence point) per alternative; the split points come from the constant bank
+        const bool is_k = u < kp;
+        const bool lt_kb = u < __dadd_rn(kp, bp);
+        const bool is_bb = !is_k & lt_kb;
+        const bool contact = !is_k & !lt_kb;
+        const bool lt_hr = uhr < P.pit_hr[side][pit];
+        const bool is_hr = contact & lt_hr;
+        const bool bip = contact & !lt_hr;
+        // resolve_contact (:51-88)
+        const double ubip = ring_at(ring, pos + B + 2), uhit = ring_at(ring, pos + B + 3), u7 = ring_at(ring, pos + B + 4), u8 = ring_at(ring, pos + B + 5);
+        uint32_t type = (uint32_t)(args.cdf_bip[0] <= ubip) + (uint32_t)(args.cdf_bip[1] <= ubip) + (uint32_t)(args.cdf_bip[2] <= ubip) +
+                        (uint32_t)(args.cdf_bip[3] <= ubip);
+        type = type > 3u ? 3u : type;
+        const double hp = P.hit_prob[side][pit][slot][type];
+        const bool hit = bip & (uhit < hp);                                   // stdlib stream (core/bip_resolution.py:62)
+        const bool fb = bip & !hit & (u7 < 0.10);                             // u7: 1B/2B/3B split of a hit, else the 10 % fallback draw
+        const uint32_t o_hit = MLBSIM_1B + (uint32_t)(args.cdf_hit[0] <= u7) + (uint32_t)(args.cdf_hit[1] <= u7) + (uint32_t)(args.cdf_hit[2] <= u7);
+        const uint32_t o_fb = MLBSIM_1B + (uint32_t)(args.cdf_fb[0] <= u8) + (uint32_t)(args.cdf_fb[1] <= u8);
+        o = hit ? o_hit : (uint32_t)MLBSIM_OUT;
+        o = fb ? o_fb : o;
+        o = is_hr ? (uint32_t)MLBSIM_HR : o;
+        o = is_bb ? (uint32_t)MLBSIM_BB : o;
+        o = is_k ? (uint32_t)MLBSIM_K : o;
+#else
         const bool is_k = u < kp;
         const bool is_bb = !is_k && (u < __dadd_rn(kp, bp));
         const bool contact = !is_k && !is_bb;
@@ -475,21 +504,22 @@ __device__ __forceinline__ void replay_body(const ReplayArgs& args, unsigned lon
         if (is_hr) o = MLBSIM_HR;
         if (is_bb) o = MLBSIM_BB;
         if (is_k) o = MLBSIM_K;
+#endif
         // ---- handler draws (core/half_inning_simulator.py:73-136, :28-39): they follow the B + 2 (+3 if in play, +1 if
         //      the fallback drew) entries above ----
-        is_out = (o == MLBSIM_K) || (o == MLBSIM_OUT);
+        is_out = (o == MLBSIM_K) | (o == MLBSIM_OUT);
         is_1b = o == MLBSIM_1B;
         const bool is_2b = o == MLBSIM_2B;
-        const bool need1 = (is_out && on1 && outs < 2u) || (is_1b && on2) || (is_2b && on1);   // double play | runner on 2B on a single | runner on 1B on a double
-        const bool need2 = is_1b && on1;                                                         // runner on 1B on a single
+        const bool need1 = (is_out & on1 & (outs < 2u)) | (is_1b & on2) | (is_2b & on1);       // double play | runner on 2B on a single | runner on 1B on a double
+        const bool need2 = is_1b & on1;                                                          // runner on 1B on a single
 #if MLBSIM_REPLAY_RING
         const uint32_t i1 = pos + (uint32_t)B + 2u + (bip ? 3u + (uint32_t)fb : 0u);
         const uint32_t i2 = i1 + (uint32_t)need1, i3 = i2 + (uint32_t)need2;
         h1 = ring_at(ring, i1);
         h2 = ring_at(ring, i2);   // (read whether or not it is a draw of this plate appearance: the transition ignores what it does not need)
         h3 = ring_at(ring, i3);
-        held = is_1b && on2 && !(h1 < 0.4);
-        const bool need3 = held && outs == 2u;                                                   // two outs, runner from 2B held at 3B
+        held = is_1b & on2 & !(h1 < 0.4);
+        const bool need3 = held & (outs == 2u);                                                  // two outs, runner from 2B held at 3B
         pos = i3 + (uint32_t)need3;
 #else
         h1 = bip ? (fb ? w[B + 6] : w[B + 5]) : w[B + 2];
@@ -542,10 +572,15 @@ __device__ __forceinline__ void replay_body(const ReplayArgs& args, unsigned lon
         h3 = TAKE(held && outs == 2u);
       }
 #undef TAKE
+#if REPLAY_STRAIGHT
+      const bool lt14 = h1 < 0.14, lt40 = h1 < 0.4, lt10 = h3 < 0.10;
+      const bool dA = is_out ? lt14 : (lt40 | (held & (outs == 2u) & lt10));   // (held implies a single)
+#else
       bool dA;
       if (is_out) dA = h1 < 0.14;
       else if (is_1b) dA = (h1 < 0.4) || (held && outs == 2u && h3 < 0.10);
       else dA = h1 < 0.4;
+#endif
       const bool dB = h2 < 0.8;
       const uint32_t ent = S.lut[(ob << 5) + (o << 2) + (dA ? 2u : 0u) + (dB ? 1u : 0u)];
       hs = (hs & ~HS_OB) + HS_PA_ONE + ent;
