@@ -269,6 +269,18 @@ int mlbsim_run_replay(mlbsim_ctx* ctx, const mlbsim_params* params, const double
 int mlbsim_run_replay_dev(mlbsim_ctx* ctx, const mlbsim_params* params_host, const double* tape_dev,
                           const uint64_t* tape_offsets_dev, int64_t n_games, mlbsim_replay_game* out_dev);
 
+/* Which instance of the replay kernel these parameters select (host-only, needs no device, ctx may be NULL):
+ * MLBSIM_REPLAY_KIND_NONOISE (use_noise == 0), MLBSIM_REPLAY_KIND_REGULAR (noise on, a bullpen on both sides — so nobody
+ * pitches past 120 plate appearances, core/game_simulator.py:8-12 — and every K / BB rate of core/fatigue_modeling.py:25-43 +
+ * core/pa_simulator.py:108-114 strictly inside (0, 1) over the tabulated range: every plate appearance draws both Beta values,
+ * the draw-by-draw path is not instantiated), else MLBSIM_REPLAY_KIND_GENERAL.  Same integers from every instance; the
+ * environment variable MLBSIM_REPLAY_GENERAL=1 makes mlbsim_run_replay* use the general instance where it would pick the
+ * regular one (tests, A/B).  Negative = MLBSIM_ERR_ARG. */
+#define MLBSIM_REPLAY_KIND_GENERAL 0
+#define MLBSIM_REPLAY_KIND_REGULAR 1
+#define MLBSIM_REPLAY_KIND_NONOISE 2
+int mlbsim_replay_kernel_kind(const mlbsim_params* params);
+
 /* Device memory helpers so a ctypes-only caller needs no CUDA binding. */
 int mlbsim_malloc(mlbsim_ctx* ctx, size_t bytes, void** dev_ptr);
 int mlbsim_free(mlbsim_ctx* ctx, void* dev_ptr);

@@ -20,7 +20,7 @@ SYMBOLS = [
     "mlbsim_run_persim", "mlbsim_malloc", "mlbsim_free", "mlbsim_memset", "mlbsim_memcpy_h2d", "mlbsim_memcpy_d2h",
     "mlbsim_launch_count", "mlbsim_set_launch_config", "mlbsim_last_kernel_ms",
     "mlbsim_summarize", "mlbsim_run_native_summary_host", "mlbsim_allreduce", "mlbsim_set_matchup_base",
-    "mlbsim_alias_rows", "mlbsim_build_tables", "mlbsim_download_tables",
+    "mlbsim_alias_rows", "mlbsim_build_tables", "mlbsim_download_tables", "mlbsim_replay_kernel_kind",
 ]
 
 ERR_NAMES = {1: "CUDA", 2: "ARG", 3: "TABLE", 4: "NO_DEVICE", 5: "STATE", 6: "CANNOT_SCORE"}
@@ -92,6 +92,7 @@ def load() -> ctypes.CDLL:
         "mlbsim_alias_rows": (i32, [vp, vp, i32, i32, vp]),
         "mlbsim_build_tables": (i32, [vp, vp, i32, u32]),
         "mlbsim_download_tables": (i32, [vp, i32, i32, vp]),
+        "mlbsim_replay_kernel_kind": (i32, [vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(L, name)  # AttributeError if the library lacks a declared symbol
@@ -102,6 +103,18 @@ def load() -> ctypes.CDLL:
     _abi.check_sizes(L.mlbsim_struct_size)
     _lib = L
     return L
+
+
+REPLAY_KINDS = {0: "general", 1: "regular", 2: "nonoise"}
+
+
+def replay_kernel_kind(params: np.ndarray) -> str:
+    """Which replay-kernel instance `mlbsim_run_replay*` picks for these parameters (host-only; include/mlbsim.h)."""
+    params = np.ascontiguousarray(params)
+    rc = load().mlbsim_replay_kernel_kind(_ptr(params))
+    if rc < 0:
+        raise MlbsimError(-rc, "mlbsim_replay_kernel_kind: bad parameters")
+    return REPLAY_KINDS[rc]
 
 
 def _ptr(a):

@@ -530,6 +530,40 @@ int mlbsim_last_kernel_ms(mlbsim_ctx* ctx, float* ms) {
   return MLBSIM_OK;
 }
 
+// Replay-kernel dispatch: true when every plate appearance of every game these parameters can produce draws both Beta values
+// and reads its K / BB rates from the kernel's tables — noise on, a bullpen on both sides (nobody then passes 120 pitches:
+// game_simulator.py:8-12 at every half-inning boundary, at most 30 plate appearances per half) and every rate
+// (core/fatigue_modeling.py:25-43, core/pa_simulator.py:108-114) strictly inside (0, 1) from 0 to 138 pitches, the range the
+// tables cover.  The rates are linear in the pitch count past 75, so the two ends decide; the margin makes the answer
+// independent of the last bit of this host arithmetic.  Anything else runs the general kernel.
+static bool replay_params_regular(const mlbsim_params* P) {
+  if (!P->use_noise || P->bullpen_len[0] <= 0 || P->bullpen_len[1] <= 0) return false;
+  static const double pen[MLBSIM_N_TIERS] = {0.0, 0.015, 0.035, 0.060};
+  const double lo = 1e-9, hi = 1.0 - 1e-9;
+  for (int side = 0; side < 2; ++side)
+    for (int pit = 0; pit <= P->bullpen_len[side]; ++pit)
+      for (int tier = 0; tier < MLBSIM_N_TIERS; ++tier)
+        for (int slot = 0; slot < P->lineup_len[side]; ++slot)
+          for (int end = 0; end < 2; ++end) {
+            const double fl = end ? (138.0 - 75.0) / 25.0 : 0.0;
+            const double ak = P->pit_k[side][pit] * (1.0 - pen[tier]) * (1.0 - 0.02 * fl);
+            const double ab = P->pit_bb[side][pit] * (1.0 + pen[tier]) * (1.0 + 0.03 * fl);
+            const double k = (P->bat_k[side][slot] + ak) / 2.0 * P->k_mod, bb = (P->bat_bb[side][slot] + ab) / 2.0 * P->bb_mod;
+            if (!(k > lo && k < hi && bb > lo && bb < hi)) return false;
+          }
+  return true;
+}
+
+int mlbsim_replay_kernel_kind(const mlbsim_params* params) {
+  if (!params) return -MLBSIM_ERR_ARG;
+  if (!params->use_noise) return MLBSIM_REPLAY_KIND_NONOISE;
+  for (int s = 0; s < 2; ++s) {
+    if (params->lineup_len[s] < 1 || params->lineup_len[s] > MLBSIM_MAX_LINEUP) return -MLBSIM_ERR_ARG;
+    if (params->bullpen_len[s] < 0 || params->bullpen_len[s] > MLBSIM_MAX_BULLPEN) return -MLBSIM_ERR_ARG;
+  }
+  return replay_params_regular(params) ? MLBSIM_REPLAY_KIND_REGULAR : MLBSIM_REPLAY_KIND_GENERAL;
+}
+
 int mlbsim_run_replay_dev(mlbsim_ctx* ctx, const mlbsim_params* params_host, const double* tape_dev,
                           const uint64_t* tape_offsets_dev, int64_t n_games, mlbsim_replay_game* out_dev) {
   if (!ctx) return MLBSIM_ERR_ARG;
@@ -546,7 +580,7 @@ int mlbsim_run_replay_dev(mlbsim_ctx* ctx, const mlbsim_params* params_host, con
   // and a second call cannot overwrite it under a copy still in flight.
   std::memcpy(&ctx->params_stage, params_host, sizeof(mlbsim_params));
   CK(ctx, cudaMemcpyAsync(ctx->params_dev, &ctx->params_stage, sizeof(mlbsim_params), cudaMemcpyHostToDevice, ctx->stream));
-  ReplayArgs a{ctx->params_dev, tape_dev, tape_offsets_dev, out_dev, (long long)n_games, {}, {}, {}};
+  ReplayArgs a{ctx->params_dev, tape_dev, tape_offsets_dev, out_dev, (long long)n_games, {}, {}, {}, {1.01, 0.10, 0.4, 0.14, 0.8}};
   std::memcpy(a.cdf_bip, params_host->cdf_bip, sizeof(a.cdf_bip));
   std::memcpy(a.cdf_hit, params_host->cdf_hit, sizeof(a.cdf_hit));
   std::memcpy(a.cdf_fb, params_host->cdf_fb, sizeof(a.cdf_fb));
@@ -569,10 +603,16 @@ int mlbsim_run_replay_dev(mlbsim_ctx* ctx, const mlbsim_params* params_host, con
     if (dyn > 0 && !ctx->replay_attr_set) {   // the per-lane tape rings: more than the 48 KB a kernel gets without asking
       CK(ctx, cudaFuncSetAttribute(mlbsim_replay_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
       CK(ctx, cudaFuncSetAttribute(mlbsim_replay_flat_nonoise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+      CK(ctx, cudaFuncSetAttribute(mlbsim_replay_flat_regular_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
       ctx->replay_attr_set = true;
     }
-    if (params_host->use_noise) mlbsim_replay_flat_kernel<<<grid, threads, dyn, ctx->stream>>>(a, ctx->counters_dev, (uint32_t)chunk);
-    else mlbsim_replay_flat_nonoise_kernel<<<grid, threads, dyn, ctx->stream>>>(a, ctx->counters_dev, (uint32_t)chunk);
+    // MLBSIM_REPLAY_GENERAL=1 (environment; tests and A/B): never pick the specialised instance
+    const char* force_general = std::getenv("MLBSIM_REPLAY_GENERAL");
+    const int kind = mlbsim_replay_kernel_kind(params_host);   // (arguments were range-checked above)
+    if (kind == MLBSIM_REPLAY_KIND_NONOISE) mlbsim_replay_flat_nonoise_kernel<<<grid, threads, dyn, ctx->stream>>>(a, ctx->counters_dev, (uint32_t)chunk);
+    else if (kind == MLBSIM_REPLAY_KIND_REGULAR && !(force_general && force_general[0] == '1'))
+      mlbsim_replay_flat_regular_kernel<<<grid, threads, dyn, ctx->stream>>>(a, ctx->counters_dev, (uint32_t)chunk);
+    else mlbsim_replay_flat_kernel<<<grid, threads, dyn, ctx->stream>>>(a, ctx->counters_dev, (uint32_t)chunk);
   }
   CK(ctx, cudaGetLastError());
   CK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));

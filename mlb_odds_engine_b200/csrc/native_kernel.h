@@ -43,6 +43,7 @@ struct ReplayArgs {
   // the launch-uniform split points of resolve_contact, by value: kernel arguments sit in the constant bank, so a compare
   // reads them as an operand (no shared-memory load, no register)
   double cdf_bip[4], cdf_hit[3], cdf_fb[2];
+  double consts[5];   // 1.01, 0.10, 0.4, 0.14, 0.8: the step's float64 literals without an immediate form (REPLAY_CONST_BANK)
 };
 
 struct PersimArgs {
@@ -60,6 +61,7 @@ extern "C" __global__ void mlbsim_native_kernel(const NativeArgs args);
 extern "C" __global__ void mlbsim_stage_tables_kernel(const mlbsim_table* tables, mlbsim_staged_table* staged, int n);
 extern "C" __global__ void mlbsim_replay_flat_kernel(const ReplayArgs args, unsigned long long* counter, uint32_t chunk);
 extern "C" __global__ void mlbsim_replay_flat_nonoise_kernel(const ReplayArgs args, unsigned long long* counter, uint32_t chunk);
+extern "C" __global__ void mlbsim_replay_flat_regular_kernel(const ReplayArgs args, unsigned long long* counter, uint32_t chunk);
 extern "C" __global__ void mlbsim_summary_kernel(const mlbsim_hist* hist, mlbsim_summary* out);
 extern "C" __global__ void mlbsim_alias_rows_kernel(const double* probs, int n_rows, int n_own, uint32_t* out);
 

@@ -47,6 +47,23 @@
                                   appearance) at every pitch count: -2.6 % on a matchup with bullpens, where nobody passes 75 pitches
                                   (profiles/r02_rp8.log); 3: final rates up to 75 pitches, factored tables beyond */
 #endif
+#ifndef REPLAY_CONST_BANK
+#define REPLAY_CONST_BANK 0  /* 1: the step's float64 literals that have no immediate form (1.01, 0.1, 0.4, 0.14, 0.8) come from the kernel-argument
+                                constant bank as compare operands instead of being built in registers every step */
+#endif
+#if REPLAY_CONST_BANK
+#define RC_101 args.consts[0]
+#define RC_010 args.consts[1]
+#define RC_040 args.consts[2]
+#define RC_014 args.consts[3]
+#define RC_080 args.consts[4]
+#else
+#define RC_101 1.01
+#define RC_010 0.10
+#define RC_040 0.4
+#define RC_014 0.14
+#define RC_080 0.8
+#endif
 #ifndef REPLAY_STEP_LOOP
 #define REPLAY_STEP_LOOP 0   /* 1: the steps of a round as a real loop (a quarter of the code) instead of unrolled copies */
 #endif
@@ -261,7 +278,11 @@ __device__ __forceinline__ double ring_take(uint32_t ring, uint32_t& pos, uint32
 }
 #endif
 
-template <bool NOISE>
+// REGULAR (host-verified, mlbsim_api.cu `replay_params_regular`): noise on, both staffs have a bullpen — so no pitcher ever
+// passes 120 pitches (game_simulator.py:8-12 takes him out at the first half-inning boundary past 90) — and every K / BB rate
+// up to there lies strictly inside (0, 1): every plate appearance draws both Beta values, the draw-by-draw path and the
+// on-the-spot rate computation are not instantiated (2 096 instead of 3 096 SASS instructions, 64 instead of 72 registers).
+template <bool NOISE, bool REGULAR>
 __device__ __forceinline__ void replay_body(const ReplayArgs& args, unsigned long long* counter, uint32_t chunk) {
   __shared__ FlatSmem S;
   {
@@ -380,9 +401,13 @@ __device__ __forceinline__ void replay_body(const ReplayArgs& args, unsigned lon
         rates = S.kb[((side * MLBSIM_MAX_PITCHERS + pit) * MLBSIM_N_TIERS + tier) * MLBSIM_MAX_LINEUP + slot];
       } else
 #endif
-      if (pc < 75 + FAT_ENTRIES) {
+      if (REGULAR || pc < 75 + FAT_ENTRIES) {
         const double2 b = S.base[(side * MLBSIM_MAX_PITCHERS + pit) * MLBSIM_N_TIERS + tier];
-        const double2 f = S.fat[pc > 75 ? pc - 75 : 0];
+        const int fe = pc > 75 ? pc - 75 : 0;
+#ifdef MLBSIM_DEBUG_BOUNDS
+        if (REGULAR && fe >= FAT_ENTRIES) __trap();   // the dispatch rule promised pc <= 120
+#endif
+        const double2 f = S.fat[REGULAR && fe >= FAT_ENTRIES ? FAT_ENTRIES - 1 : fe];   // (REGULAR: pc <= 120 by construction; the clamp only keeps the read inside the table)
         rates.x = __dmul_rn(__ddiv_rn(__dadd_rn(P.bat_k[side][slot], __dmul_rn(b.x, f.x)), 2.0), P.k_mod);
         rates.y = __dmul_rn(__ddiv_rn(__dadd_rn(P.bat_bb[side][slot], __dmul_rn(b.y, f.y)), 2.0), P.bb_mod);
       } else {
@@ -394,7 +419,7 @@ __device__ __forceinline__ void replay_body(const ReplayArgs& args, unsigned lon
 #endif
       const double k = rates.x, bb = rates.y;
       // beta_noise (core/pa_simulator.py:23-32): a draw only when 0 < p < 1
-      const bool has_k = noise && k > 0.0 && k < 1.0, has_b = noise && bb > 0.0 && bb < 1.0;
+      const bool has_k = REGULAR || (noise && k > 0.0 && k < 1.0), has_b = REGULAR || (noise && bb > 0.0 && bb < 1.0);
       const uint32_t ob = hs & HS_OB;
       const uint32_t outs = ob >> 3;
       const bool on1 = (ob & 1u) != 0, on2 = (ob & 2u) != 0;
@@ -439,7 +464,7 @@ __device__ __forceinline__ void replay_body(const ReplayArgs& args, unsigned lon
 #endif
       }
 #endif
-      if (!noise || (has_k && has_b)) {
+      if (!noise || REGULAR || (has_k && has_b)) {
         // ---- window path: every draw of this plate appearance sits at a known slot of tape[pos .. pos + B + 8] ----
         constexpr int B = NOISE ? 2 : 0;
 #if MLBSIM_REPLAY_RING
@@ -447,7 +472,7 @@ __device__ __forceinline__ void replay_body(const ReplayArgs& args, unsigned lon
         // base-running draws at offsets computed below
         if (pos + (uint32_t)(B + 9) > len) ring_patch_tail<B + 9>(ring, pos, len);
         const double kp = NOISE ? ring_at(ring, pos) : k;
-        const double bp = __dmul_rn(NOISE ? ring_at(ring, pos + 1u) : bb, 1.01);
+        const double bp = __dmul_rn(NOISE ? ring_at(ring, pos + 1u) : bb, RC_101);
         const double u = ring_at(ring, pos + B), uhr = ring_at(ring, pos + B + 1);   // u_hr is always consumed (:126)
 #else
         double w[B + 9];
@@ -473,7 +498,7 @@ __device__ __forceinline__ void replay_body(const ReplayArgs& args, unsigned lon
         type = type > 3u ? 3u : type;
         const double hp = P.hit_prob[side][pit][slot][type];
         const bool hit = bip & (uhit < hp);                                   // stdlib stream (core/bip_resolution.py:62)
-        const bool fb = bip & !hit & (u7 < 0.10);                             // u7: 1B/2B/3B split of a hit, else the 10 % fallback draw
+        const bool fb = bip & !hit & (u7 < RC_010);                           // u7: 1B/2B/3B split of a hit, else the 10 % fallback draw
         const uint32_t o_hit = MLBSIM_1B + (uint32_t)(args.cdf_hit[0] <= u7) + (uint32_t)(args.cdf_hit[1] <= u7) + (uint32_t)(args.cdf_hit[2] <= u7);
         const uint32_t o_fb = MLBSIM_1B + (uint32_t)(args.cdf_fb[0] <= u8) + (uint32_t)(args.cdf_fb[1] <= u8);
         o = hit ? o_hit : (uint32_t)MLBSIM_OUT;
@@ -518,7 +543,7 @@ __device__ __forceinline__ void replay_body(const ReplayArgs& args, unsigned lon
         h1 = ring_at(ring, i1);
         h2 = ring_at(ring, i2);   // (read whether or not it is a draw of this plate appearance: the transition ignores what it does not need)
         h3 = ring_at(ring, i3);
-        held = is_1b & on2 & !(h1 < 0.4);
+        held = is_1b & on2 & !(h1 < RC_040);
         const bool need3 = held & (outs == 2u);                                                  // two outs, runner from 2B held at 3B
         pos = i3 + (uint32_t)need3;
 #else
@@ -573,7 +598,7 @@ __device__ __forceinline__ void replay_body(const ReplayArgs& args, unsigned lon
       }
 #undef TAKE
 #if REPLAY_STRAIGHT
-      const bool lt14 = h1 < 0.14, lt40 = h1 < 0.4, lt10 = h3 < 0.10;
+      const bool lt14 = h1 < RC_014, lt40 = h1 < RC_040, lt10 = h3 < RC_010;
       const bool dA = is_out ? lt14 : (lt40 | (held & (outs == 2u) & lt10));   // (held implies a single)
 #else
       bool dA;
@@ -581,7 +606,7 @@ __device__ __forceinline__ void replay_body(const ReplayArgs& args, unsigned lon
       else if (is_1b) dA = (h1 < 0.4) || (held && outs == 2u && h3 < 0.10);
       else dA = h1 < 0.4;
 #endif
-      const bool dB = h2 < 0.8;
+      const bool dB = h2 < RC_080;
       const uint32_t ent = S.lut[(ob << 5) + (o << 2) + (dA ? 2u : 0u) + (dB ? 1u : 0u)];
       hs = (hs & ~HS_OB) + HS_PA_ONE + ent;
       pa_cur += 1ull << (9u * o);
@@ -675,10 +700,15 @@ __device__ __forceinline__ void replay_body(const ReplayArgs& args, unsigned lon
 
 extern "C" __global__ void __launch_bounds__(REPLAY_FLAT_THREADS, REPLAY_FLAT_BLOCKS)
 mlbsim_replay_flat_kernel(const ReplayArgs args, unsigned long long* counter, uint32_t chunk) {
-  replay_body<true>(args, counter, chunk);     // simulate_game(use_noise=True)
+  replay_body<true, false>(args, counter, chunk);     // simulate_game(use_noise=True), any rates
+}
+
+extern "C" __global__ void __launch_bounds__(REPLAY_FLAT_THREADS, REPLAY_FLAT_BLOCKS)
+mlbsim_replay_flat_regular_kernel(const ReplayArgs args, unsigned long long* counter, uint32_t chunk) {
+  replay_body<true, true>(args, counter, chunk);      // use_noise=True, bullpens on both sides, all rates inside (0, 1)
 }
 
 extern "C" __global__ void __launch_bounds__(REPLAY_FLAT_THREADS, REPLAY_FLAT_BLOCKS)
 mlbsim_replay_flat_nonoise_kernel(const ReplayArgs args, unsigned long long* counter, uint32_t chunk) {
-  replay_body<false>(args, counter, chunk);
+  replay_body<false, false>(args, counter, chunk);
 }
