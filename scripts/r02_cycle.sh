@@ -21,5 +21,5 @@ fi
 # replay kernel: throughput (bit-exactness checked in the same run) and one ncu --set full capture
 timeout 300 python scripts/replay_bench.py 800000 > $OUT/${TAG}_replay.json 2> $OUT/${TAG}_replay.err; tail -c 600 $OUT/${TAG}_replay.json
 if [ $NCU == 1 ]; then
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:mlbsim_replay_flat_kernel -s 3 -c 1 -o $OUT/${TAG}_replay python scripts/replay_bench.py 400000 > $OUT/${TAG}_replay_ncu.log 2>&1
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:mlbsim_replay_flat -s 3 -c 1 -o $OUT/${TAG}_replay python scripts/replay_bench.py 400000 > $OUT/${TAG}_replay_ncu.log 2>&1
 fi
