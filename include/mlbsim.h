@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define MLBSIM_ABI_VERSION 5
+#define MLBSIM_ABI_VERSION 6
 
 /* ---- model dimensions ------------------------------------------------------------------- */
 #define MLBSIM_MAX_LINEUP 9   /* len(lineup); 9 in every caller (half_inning_simulator.py:175) */

@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import numpy as np
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 MAX_LINEUP = 9
 MAX_BULLPEN = 6
