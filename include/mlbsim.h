@@ -177,8 +177,10 @@ int mlbsim_set_stream(mlbsim_ctx* ctx, uintptr_t stream);
 int mlbsim_synchronize(mlbsim_ctx* ctx);
 
 /* Copies `n_matchups` host tables to the device (replaces the per-call dict arguments of
- * simulate_game, core/game_simulator.py:14-21, for native mode).  Synchronous w.r.t. the host
- * buffer: it may be reused on return. */
+ * simulate_game, core/game_simulator.py:14-21, for native mode).  The host buffer may be reused on return.  Up to
+ * 1 MiB of tables (50 matchups) are copied through a pinned buffer of the context and the call does not wait for the
+ * device: the copy and the staging kernel are ordered on the context's stream ahead of whatever is launched next
+ * (mlbsim_set_stream makes a new stream wait for them).  Larger uploads return when the copy has completed. */
 int mlbsim_upload_tables(mlbsim_ctx* ctx, const mlbsim_table* tables, int n_matchups);
 
 /* Matchup sharding ("for the sweep: by matchup block"): a rank that uploads only the tables of its

@@ -37,6 +37,11 @@ struct mlbsim_ctx {
   mlbsim_summary* summary_scratch = nullptr;
   int summary_scratch_cap = 0;
   mlbsim_params* params_dev = nullptr;
+  // small table uploads go through a context-owned pinned buffer: the caller's buffer is free on return and the call does not
+  // wait for the device (the copy, the staging kernel and whatever is launched next queue up on the stream back to back)
+  void* upload_stage = nullptr;
+  cudaEvent_t upload_ev = nullptr;   // recorded behind the staging kernel of the last staged upload
+  bool upload_pending = false;
   mlbsim_params params_stage{};   // context-owned pageable copy: the caller's buffer is free as soon as a replay call returns
   int threads_per_block = 0;
   int blocks_per_sm = 0;
@@ -124,6 +129,9 @@ void mlbsim_destroy(mlbsim_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
+  if (ctx->upload_pending) cudaEventSynchronize(ctx->upload_ev);   // (a copy out of the pinned staging buffer may still be in flight on a caller's stream)
+  if (ctx->upload_ev) cudaEventDestroy(ctx->upload_ev);
+  if (ctx->upload_stage) cudaFreeHost(ctx->upload_stage);
   cudaFree(ctx->tables_dev);
   cudaFree(ctx->staged_dev);
   cudaFree(ctx->counters_dev);
@@ -149,7 +157,12 @@ int mlbsim_device_info(const mlbsim_ctx* ctx, int* sm_count, int* sm_clock_khz, 
 
 int mlbsim_set_stream(mlbsim_ctx* ctx, uintptr_t stream) {
   if (!ctx) return MLBSIM_ERR_ARG;
-  ctx->stream = stream ? reinterpret_cast<cudaStream_t>(stream) : ctx->own_stream;
+  cudaStream_t s = stream ? reinterpret_cast<cudaStream_t>(stream) : ctx->own_stream;
+  if (s != ctx->stream && ctx->upload_pending) {   // tables uploaded on the old stream must be in place for launches on the new one
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaStreamWaitEvent(s, ctx->upload_ev, 0));
+  }
+  ctx->stream = s;
   return MLBSIM_OK;
 }
 
@@ -180,6 +193,8 @@ int mlbsim_set_matchup_base(mlbsim_ctx* ctx, int base) {
 }
 
 // device buffers for n_matchups tables (raw + staged image) and their work counters
+constexpr size_t UPLOAD_STAGE_BYTES = 1u << 20;   // 50 tables: single games and slates; sweeps upload from the caller's buffer
+
 static int ensure_table_capacity(mlbsim_ctx* ctx, int n_matchups) {
   if (n_matchups > ctx->tables_cap) {
     CK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -216,11 +231,28 @@ int mlbsim_upload_tables(mlbsim_ctx* ctx, const mlbsim_table* tables, int n_matc
   CK(ctx, cudaSetDevice(ctx->device));
   if (int rc = ensure_table_capacity(ctx, n_matchups)) return rc;
   ctx->n_tables = n_matchups;
-  CK(ctx, cudaMemcpyAsync(ctx->tables_dev, tables, sizeof(mlbsim_table) * (size_t)n_matchups, cudaMemcpyHostToDevice, ctx->stream));
+  const size_t bytes = sizeof(mlbsim_table) * (size_t)n_matchups;
+  const bool staged = bytes <= UPLOAD_STAGE_BYTES;
+  const void* src = tables;
+  if (staged) {
+    if (!ctx->upload_stage) {
+      CK(ctx, cudaMallocHost(&ctx->upload_stage, UPLOAD_STAGE_BYTES));
+      CK(ctx, cudaEventCreateWithFlags(&ctx->upload_ev, cudaEventDisableTiming));
+    }
+    if (ctx->upload_pending) CK(ctx, cudaEventSynchronize(ctx->upload_ev));   // the previous upload has left the staging buffer
+    std::memcpy(ctx->upload_stage, tables, bytes);
+    src = ctx->upload_stage;
+  }
+  CK(ctx, cudaMemcpyAsync(ctx->tables_dev, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
   mlbsim_stage_tables_kernel<<<n_matchups, 256, 0, ctx->stream>>>(ctx->tables_dev, ctx->staged_dev, n_matchups);
   CK(ctx, cudaGetLastError());
   ctx->launches++;
-  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  if (staged) {
+    CK(ctx, cudaEventRecord(ctx->upload_ev, ctx->stream));
+    ctx->upload_pending = true;
+  } else {
+    CK(ctx, cudaStreamSynchronize(ctx->stream));   // large uploads are read straight from the caller's buffer
+  }
   return MLBSIM_OK;
 }
 

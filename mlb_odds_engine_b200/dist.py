@@ -106,6 +106,7 @@ class ShardedSimulator:
             self.summary_dev = torch.zeros(max(1, n_matchups) * swords, dtype=torch.int64, device=dev)
             if self.shard == "sims":
                 self.hist_pinned = torch.zeros(words, dtype=torch.int64).pin_memory()
+                self._hist_host = self.hist_pinned.numpy().view(np.uint64).view(_abi.HIST_DTYPE)   # (one wrapper, not one per call)
                 self.summary_pinned = torch.zeros(n_matchups * swords, dtype=torch.int64).pin_memory()
             else:
                 # all-gather buffers: one padded block per rank (blocks differ by at most one matchup)
@@ -208,7 +209,7 @@ class ShardedSimulator:
         self.run_device(n_sims_total, seed, sim_lo, count_pa)
         self.hist_pinned.copy_(self.hist_dev, non_blocking=True)
         self.torch.cuda.current_stream().synchronize()
-        out = self.hist_pinned.numpy().view(np.uint64).view(_abi.HIST_DTYPE).copy()
+        out = self._hist_host.copy()
         check_terminated(out)
         return out
 
