@@ -64,6 +64,16 @@
 #define RC_014 0.14
 #define RC_080 0.8
 #endif
+#ifndef REPLAY_OFFSET_CACHE
+#define REPLAY_OFFSET_CACHE 0   /* 1: the tape offsets of the warp's next 32 games sit in registers (one game per lane, handed out by shuffle)
+                                and the first lines of their tapes are asked into L2 when the window is loaded: a lane that starts a game no longer
+                                pays two dependent trips to HBM (offsets, then the first granules) with the whole warp waiting behind it.
+                                Measured: -0.5 % (6.48 vs 6.51e8, profiles/r02_rp15.log) — the offsets are L2 hits already */
+#endif
+#ifndef REPLAY_FILL_FIRST
+#define REPLAY_FILL_FIRST 0   /* 1: a step first asks for its new granules (their own cp.async group), then waits for everything but that group:
+                                 the requests leave before the lane stalls on the older ones instead of after */
+#endif
 #ifndef REPLAY_STEP_LOOP
 #define REPLAY_STEP_LOOP 0   /* 1: the steps of a round as a real loop (a quarter of the code) instead of unrolled copies */
 #endif
@@ -227,10 +237,20 @@ constexpr uint32_t RING_BYTES = MLBSIM_REPLAY_RING_LANE_BYTES;   // 256
 constexpr uint32_t RING_GRANULES = RING_BYTES / 32u;              // 8
 static_assert(RING_BYTES == 256, "ring addressing below assumes 16 units of 16 bytes");
 
+#ifndef REPLAY_RING_L2_HINT
+#define REPLAY_RING_L2_HINT 256   /* L2 prefetch size carried by the ring's cp.async copies: 64 / 128 / 256 bytes -> 5.03 / 6.32 / 6.51e8 games/s (profiles/r02_rp14.log) */
+#endif
+#ifndef REPLAY_RING_PREFETCH
+#define REPLAY_RING_PREFETCH 0    /* > 0: every fill also asks L2 for the line this many bytes past the last granule it requested */
+#endif
+#define RP_STR2(x) #x
+#define RP_STR(x) RP_STR2(x)
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global.L2::128B [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+  asm volatile("cp.async.cg.shared.global.L2::" RP_STR(REPLAY_RING_L2_HINT) "B [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all_but_last() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 __device__ __forceinline__ void lds128_f64(uint32_t addr, double& a, double& b) {
   asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(addr));
 }
@@ -323,6 +343,12 @@ __device__ __forceinline__ void replay_body(const ReplayArgs& args, unsigned lon
 
   uint32_t chunk_next = 0, chunk_end = 0;
   bool exhausted = false;
+#if REPLAY_OFFSET_CACHE
+  // offsets window: lane l holds the tape bounds of game oc_base + l
+  uint32_t oc_base = 0, oc_len = 0;
+  bool oc_valid = false;
+  uint64_t oc_lo = 0;
+#endif
 #if MLBSIM_REPLAY_RING
   extern __shared__ __align__(256) unsigned char replay_ring_smem[];
   const uint32_t ring = (uint32_t)__cvta_generic_to_shared(replay_ring_smem) + threadIdx.x * RING_BYTES;
@@ -357,9 +383,37 @@ __device__ __forceinline__ void replay_body(const ReplayArgs& args, unsigned lon
       }
       const uint32_t avail = chunk_end - chunk_next;
       const uint32_t rank = __popc(need & lanemask_lt());
+#if REPLAY_OFFSET_CACHE
+      // games chunk_next .. chunk_next + min(want, avail) - 1 are about to be handed out: slide the window when they do not all
+      // lie inside it (once per <= 32 games; warp-uniform)
+      {
+        const uint32_t want0 = __popc(need);
+        const uint32_t take = want0 < avail ? want0 : avail;
+        if (take != 0u && (!oc_valid || chunk_next < oc_base || chunk_next + take > oc_base + 32u)) {
+          oc_base = chunk_next;
+          oc_valid = true;
+          const uint32_t g0 = oc_base + (uint32_t)lane, g = g0 < n_games ? g0 : n_games;
+          const uint32_t g1 = g < n_games ? g + 1u : n_games;
+          oc_lo = args.offsets[g];
+          oc_len = (uint32_t)(args.offsets[g1] - oc_lo);
+          if (g0 < chunk_end) {   // this game will be played by this warp: its tape's first lines into L2 now
+            const double* t0 = args.tape + (oc_lo & ~(uint64_t)15);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(t0));
+            if (oc_len > 16u) asm volatile("prefetch.global.L2 [%0];" ::"l"(t0 + 16));
+          }
+        }
+      }
+      const uint32_t oc_idx = (hs == HS_DEAD && rank < avail) ? chunk_next + rank - oc_base : 0u;
+      const uint64_t sh_lo = __shfl_sync(0xffffffffu, oc_lo, (int)oc_idx);
+      const uint32_t sh_len = __shfl_sync(0xffffffffu, oc_len, (int)oc_idx);
+#endif
       if (hs == HS_DEAD && rank < avail) {
         game = chunk_next + rank;
+#if REPLAY_OFFSET_CACHE
+        const uint64_t lo = sh_lo, hi = sh_lo + sh_len;
+#else
         const uint64_t lo = args.offsets[game], hi = args.offsets[game + 1];
+#endif
 #if MLBSIM_REPLAY_RING
         const uint32_t shift = (uint32_t)lo & 3u;
         tp = args.tape + (lo - shift); len = (uint32_t)(hi - lo) + shift; pos = shift;
@@ -370,6 +424,9 @@ __device__ __forceinline__ void replay_body(const ReplayArgs& args, unsigned lon
         for (uint32_t g = 0; g < 4u; ++g)
           if (g < end_g) ring_fetch(ring, tp, g);
         req_g = 4u;
+#if REPLAY_FILL_FIRST
+        cp_async_commit();   // the first window's granules are a group of their own: the first step's wait must cover them
+#endif
         cur = 0; oth = 0; sc = 0; hidx = 0; hs = HS_NEW_HALF; nused = 0; pa_cur = 0; pa_oth = 0;
 #else
         tp = args.tape + lo; len = (uint32_t)(hi - lo); pos = 0;
@@ -432,7 +489,9 @@ __device__ __forceinline__ void replay_body(const ReplayArgs& args, unsigned lon
         // 256 bytes past the read position.  A step (plus a boundary pass) moves the position by at most 14 entries =
         // 4 granules and its window ends at most 3 granules past the position's own, so asking up to position + 8 at
         // every step keeps the next step's window inside what was asked for one step earlier.
+#if !REPLAY_FILL_FIRST
         cp_async_wait_all();
+#endif
         const uint32_t want = (pos >> 2) + RING_GRANULES;
         const uint32_t lim = want < end_g ? want : end_g;
 #if REPLAY_FILL_NESTED
@@ -445,6 +504,9 @@ __device__ __forceinline__ void replay_body(const ReplayArgs& args, unsigned lon
 #endif
           const double* src = tp + ((size_t)req_g << 2);
           const uint32_t so = req_g << 5;
+#if REPLAY_RING_PREFETCH > 0
+          if (lim + REPLAY_RING_PREFETCH / 32 < end_g) asm volatile("prefetch.global.L2 [%0];" ::"l"(tp + ((size_t)lim << 2) + REPLAY_RING_PREFETCH / 8));
+#endif
           req_g = lim;
           ring_fetch_at(ring, so, src, 0);
           if (n > 1u) {
@@ -461,6 +523,11 @@ __device__ __forceinline__ void replay_body(const ReplayArgs& args, unsigned lon
           if (req_g < lim) { ring_fetch(ring, tp, req_g); ++req_g; }
 #pragma unroll 1
         while (req_g < lim) { ring_fetch(ring, tp, req_g); ++req_g; }   // (the first step of a game asks for four)
+#endif
+#if REPLAY_FILL_FIRST
+        // this step's window lies in granules asked for at an earlier step (the fill rule): only those must have landed
+        cp_async_commit();
+        cp_async_wait_all_but_last();
 #endif
       }
 #endif
