@@ -64,6 +64,11 @@
                                 up.  Bit-exact, but -0.7 %: the returning ATOMS inside the divergent game-over branch costs more than the ballot
                                 refill it saves (profiles/r02_v25_variants.log) */
 #endif
+#ifndef OPT_ALIAS_OR
+#define OPT_ALIAS_OR 0   /* 1: the staged alias table sits at a 32 KB-aligned shared-memory address (in dynamic shared memory, behind the histograms),
+                            so the row address is (ctx & row bits) | base — one LOP3 — instead of a mask and an add: 43 instead of 44 instructions per step.
+                            Bit-exact; 3.195 vs 3.187e9 games/s (+0.1 ... +0.4 %, inside the run-to-run spread; profiles/r02_v30_variants.log): off */
+#endif
 #ifndef OPT_TMA
 #define OPT_TMA 1      /* 1: tables reach shared memory as cp.async.bulk copies of the pre-laid-out device image (mbarrier completion) */
 #endif
@@ -103,7 +108,9 @@ constexpr int ALIAS_WORDS = MLBSIM_STAGED_ALIAS_WORDS;                          
 
 struct __align__(16) Smem {
   uint32_t lut[LUT_WORDS];   // first: its rows are addressed by absolute 14-bit shared addresses kept in the state word
+#if !OPT_ALIAS_OR
   uint32_t alias[ALIAS_WORDS];   // static, so that the hot loop's LDS carries its address as an immediate
+#endif
   uint32_t fthr[FAT_WORDS];  // (fthr and fslope are contiguous: one bulk copy)
   int32_t fslope[FAT_WORDS];
 #if OPT_WRAP_LUT
@@ -154,6 +161,18 @@ __device__ __forceinline__ uint32_t smem_dynamic_base() {
   asm("mov.u32 %0, mlbsim_S_pa;" : "=r"(a));
   return a;
 }
+
+#if OPT_ALIAS_OR
+// shared-window address of the staged alias table: the first 32 KB boundary behind the histograms and PA counters
+// (rounded down inside an asm statement: a compiler that knows the low bits are zero turns the OR of the lookup back into mask + add)
+__device__ __forceinline__ uint32_t alias_base() {
+  uint32_t a = smem_dynamic_base() + DYN_JOINT_BYTES + DYN_PA_BYTES + 0x7FFFu;
+  asm("and.b32 %0, %0, 0xFFFF8000;" : "+r"(a));
+  return a;
+}
+#else
+__device__ __forceinline__ uint32_t alias_base() { return smem_static_base() + (uint32_t)offsetof(Smem, alias); }
+#endif
 
 // All hot shared-memory traffic uses 32-bit shared-window addresses (ld/st/red.shared), so the
 // loop carries one base register instead of 64-bit generic pointers.
@@ -307,7 +326,7 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
   const int lane = threadIdx.x & 31;
   const uint32_t n_sims = args.n_sims;
   const uint32_t sb = smem_static_base();
-  const uint32_t A_ALIAS = sb + (uint32_t)offsetof(Smem, alias);
+  const uint32_t A_ALIAS = alias_base();
   const uint32_t init0 = (16u - L0) * ((1u << CX_BIAS_SHIFT) + (1u << CX_SLOT_SHIFT));   // bias nibble + biased slot 0, side 0
   const uint32_t init1 = (16u - L1) * ((1u << CX_BIAS_SHIFT) + (1u << CX_SLOT_SHIFT)) | CX_SIDE;
   const uint32_t A_FTHR = sb + (uint32_t)offsetof(Smem, fthr);
@@ -454,7 +473,11 @@ __device__ __forceinline__ void play_matchup(const NativeArgs& args, unsigned lo
         if ((c1 & 0x1FFFu) == 0u) __trap();   // the PA field of the Philox counter wrapped
       }
 #endif
+#if OPT_ALIAS_OR
+      const uint32_t e = lds32(((cur & CX_ROW_BYTES) | A_ALIAS) + (col << 2));   // (A_ALIAS has no bit in common with the row field)
+#else
       const uint32_t e = lds32(A_ALIAS + row + (col << 2));
+#endif
       uint32_t o = ((w0 << 3) > e) ? col : (e & 7u);   // draw variant 0..7 (7 = single, runner on first advances)
       if (FATIGUE) {
         if ((cur & CX_PC_BITS) >= ((uint32_t)(FATIGUE_START + 1) << CX_PC_SHIFT)) {   // past 75 pitches (rare)
@@ -701,12 +724,15 @@ mlbsim_native_kernel(const NativeArgs args) {
         const uint32_t bytes = ALIAS_BYTES + (fatigue ? 2u * FAT_WORDS * 4u : 0u);
         fence_proxy_async();   // the previous matchup's generic-proxy accesses to these buffers are ordered before the async writes
         mbar_arrive_expect_tx(mbar, bytes);
-        bulk_copy_g2s(smem_static_base() + (uint32_t)offsetof(Smem, alias), T->alias, ALIAS_BYTES, mbar);
+        bulk_copy_g2s(alias_base(), T->alias, ALIAS_BYTES, mbar);
         if (fatigue) bulk_copy_g2s(smem_static_base() + (uint32_t)offsetof(Smem, fthr), T->fthr, 2u * FAT_WORDS * 4u, mbar);
       }
 #else
       const uint4* src = reinterpret_cast<const uint4*>(T->alias);
-      uint4* dst = reinterpret_cast<uint4*>(S.alias);
+      uint4* dst = reinterpret_cast<uint4*>(S_pa + ((alias_base() - smem_dynamic_base()) >> 2));   // (OPT_ALIAS_OR; the static layout is `S.alias`)
+#if !OPT_ALIAS_OR
+      dst = reinterpret_cast<uint4*>(S.alias);
+#endif
       for (int i = tid; i < ALIAS_WORDS / 4; i += blockDim.x) dst[i] = __ldg(src + i);
       if (fatigue) {
         const uint4* fsrc = reinterpret_cast<const uint4*>(T->fthr);
@@ -904,5 +930,9 @@ mlbsim_persim_kernel(const PersimArgs args) {
 }
 
 size_t mlbsim_native_smem_bytes(int /*threads_per_block*/) {   // dynamic part only; independent of the block size
+#if OPT_ALIAS_OR
+  return (size_t)DYN_JOINT_BYTES + (size_t)DYN_PA_BYTES + 0x8000u + (size_t)ALIAS_BYTES;   // + alignment slack + the alias table
+#else
   return (size_t)DYN_JOINT_BYTES + (size_t)DYN_PA_BYTES;
+#endif
 }
