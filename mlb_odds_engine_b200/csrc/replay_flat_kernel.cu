@@ -74,6 +74,11 @@
 #define REPLAY_FILL_FIRST 0   /* 1: a step first asks for its new granules (their own cp.async group), then waits for everything but that group:
                                  the requests leave before the lane stalls on the older ones instead of after */
 #endif
+#ifndef REPLAY_BOUNDARY_SKIP_WAIT
+#define REPLAY_BOUNDARY_SKIP_WAIT 0   /* 1: the boundary pass waits for outstanding cp.async copies only when one of its (at most three) entries lies in a
+                                         granule asked for at the lane's latest fill; everything older landed at that step's own wait.  +0.7 % (6.50 vs 6.45e8,
+                                         profiles/r02_rp17.log): the copies are tracked per warp, so the wait goes only when no lane needs it — off */
+#endif
 #ifndef REPLAY_STEP_LOOP
 #define REPLAY_STEP_LOOP 0   /* 1: the steps of a round as a real loop (a quarter of the code) instead of unrolled copies */
 #endif
@@ -355,6 +360,9 @@ __device__ __forceinline__ void replay_body(const ReplayArgs& args, unsigned lon
   // Ring coordinates: `tp` is moved back to the 32-byte granule holding the game's first draw and `pos` / `len` count
   // from there (the 0..3 entries of shift ride in the top bits of `status` and come off again when the game is written).
   uint32_t req_g = 0, end_g = 0;   // next granule to ask for; granules of this game's tape
+#if REPLAY_BOUNDARY_SKIP_WAIT
+  uint32_t landed_g = 0;           // granules below this one were asked for before the lane's latest fill: they have landed
+#endif
 #endif
 
   // lane state
@@ -424,6 +432,9 @@ __device__ __forceinline__ void replay_body(const ReplayArgs& args, unsigned lon
         for (uint32_t g = 0; g < 4u; ++g)
           if (g < end_g) ring_fetch(ring, tp, g);
         req_g = 4u;
+#if REPLAY_BOUNDARY_SKIP_WAIT
+        landed_g = 0u;
+#endif
 #if REPLAY_FILL_FIRST
         cp_async_commit();   // the first window's granules are a group of their own: the first step's wait must cover them
 #endif
@@ -494,6 +505,9 @@ __device__ __forceinline__ void replay_body(const ReplayArgs& args, unsigned lon
 #endif
         const uint32_t want = (pos >> 2) + RING_GRANULES;
         const uint32_t lim = want < end_g ? want : end_g;
+#if REPLAY_BOUNDARY_SKIP_WAIT
+        landed_g = req_g;
+#endif
 #if REPLAY_FILL_NESTED
         // up to four granules per step (the first step of a game asks for four, a step after a maximal step and a boundary
         // pass likewise): nested early exits, addresses as immediates off one base
@@ -694,7 +708,11 @@ __device__ __forceinline__ void replay_body(const ReplayArgs& args, unsigned lon
       const bool reached = (hs & HS_REACHED) != 0u;
       // misc run, ghost run, reliever pick: at most three consecutive entries, loaded together
 #if MLBSIM_REPLAY_RING
+#if REPLAY_BOUNDARY_SKIP_WAIT
+      if (((pos + 2u) >> 2) >= landed_g) cp_async_wait_all();   // (rare: the last step moved the position by almost four granules)
+#else
       cp_async_wait_all();   // (the granules of these entries were asked for at the last step's start at the latest)
+#endif
       if (pos + 3u > len) ring_patch_tail<3>(ring, pos, len);
       const double b0 = ring_at(ring, pos), b1 = ring_at(ring, pos + 1u), b2 = ring_at(ring, pos + 2u);
 #else
