@@ -74,6 +74,15 @@
 #define REPLAY_FILL_FIRST 0   /* 1: a step first asks for its new granules (their own cp.async group), then waits for everything but that group:
                                  the requests leave before the lane stalls on the older ones instead of after */
 #endif
+#ifndef REPLAY_INLINE_BOUNDARY
+#define REPLAY_INLINE_BOUNDARY 0   /* 1 (ring kernel): a half inning that ends inside a round goes on into the next half right there when nothing rare
+                                      happens (no game over, no pitcher change, entries already in the ring, not at the end of the tape); the rare
+                                      cases wait for the round-end pass as before.  Lanes no longer idle for the rest of the round.  Bit-exact; +0.9 / +1.0 / -1.5 % at
+                                      3 / 4 / 5 steps per round (profiles/r02_rp18.log): the inline block costs ~96 instructions per step — off */
+#endif
+#if REPLAY_INLINE_BOUNDARY && !defined(REPLAY_BOUNDARY_SKIP_WAIT)
+#define REPLAY_BOUNDARY_SKIP_WAIT 1   /* (the inline boundary needs the landed-granule bookkeeping) */
+#endif
 #ifndef REPLAY_BOUNDARY_SKIP_WAIT
 #define REPLAY_BOUNDARY_SKIP_WAIT 0   /* 1: the boundary pass waits for outstanding cp.async copies only when one of its (at most three) entries lies in a
                                          granule asked for at the lane's latest fill; everything older landed at that step's own wait.  +0.7 % (6.50 vs 6.45e8,
@@ -110,6 +119,7 @@ constexpr uint32_t HS_PA_ONE = 1u << 8;
 constexpr uint32_t HS_OVER = (1u << 30) | (1u << 14);
 constexpr uint32_t HS_REACHED = 0x3Fu << 24;
 constexpr uint32_t HS_DEAD = 1u << 15;
+constexpr uint32_t HS_PARKED = 1u << 31;   // (inline boundary) half over, left to the round-end pass
 
 constexpr int KB_ENTRIES = 2 * MLBSIM_MAX_PITCHERS * MLBSIM_N_TIERS * MLBSIM_MAX_LINEUP;   // 504
 
@@ -454,7 +464,7 @@ __device__ __forceinline__ void replay_body(const ReplayArgs& args, unsigned lon
 #else
 #pragma unroll
 #endif
-    for (int rep = 0; rep < REPLAY_UNROLL; ++rep)
+    for (int rep = 0; rep < REPLAY_UNROLL; ++rep) {
     if ((hs & (HS_OVER | HS_DEAD)) == 0u) {
       // ---------------- one plate appearance (core/pa_simulator.py:91-143) ----------------
       const uint32_t side = hidx & 1u;
@@ -699,6 +709,45 @@ __device__ __forceinline__ void replay_body(const ReplayArgs& args, unsigned lon
       if ((hs & HS_OVER) == 0u) {
         if (wrapped && (cur & CX_TIER_MASK) != CX_TIER_MASK) cur += CX_TIER_ONE;   // :177-178
       }
+    }
+#if REPLAY_INLINE_BOUNDARY && MLBSIM_REPLAY_RING
+    // ---------------- end of half inning, common case, inside the round ----------------
+    // Same arithmetic as the round-end pass below, evaluated into temporaries and committed only when nothing rare happens;
+    // otherwise the lane is parked untouched and the round-end pass does the whole boundary.
+    if (rep + 1 < REPLAY_UNROLL && (hs & HS_OVER) != 0u && (hs & HS_PARKED) == 0u) {
+      const uint32_t side = hidx & 1u;
+      uint32_t runs = (hs >> 16) & 63u;
+      const bool reached = (hs & HS_REACHED) != 0u;
+      // the (at most two) entries read here landed at this step's own wait, and none of them lies past the end of the tape
+      bool fast = (((pos + 2u) >> 2) < landed_g) & (pos + 3u <= len);
+      const double b0 = ring_at(ring, pos), b1 = ring_at(ring, pos + 1u);
+      const bool need_m = reached & (runs == 0u);
+      const double ug = need_m ? b1 : b0;
+      const uint32_t npos = pos + (uint32_t)need_m + (uint32_t)reached;
+      runs += (uint32_t)(need_m & (b0 < 0.011)) + (uint32_t)(reached & (ug < 0.01));
+      const uint32_t nsc = sc + (runs << (side * 16u));
+      const uint32_t inning = (hidx >> 1) + 1u;
+      const uint32_t a = nsc & 0xFFFFu, h = nsc >> 16;
+      const bool over = ((side != 0u) & (hidx >= 17u) & (a != h)) | ((hidx == 16u) & (h > a));
+      const uint32_t nb = side ? nb0 : nb1;     // staff that takes the mound next: its context is `oth`
+      const bool hook = (nb != 0u) & (((oth & CX_TIER_GE2) != 0u) | (oth >= ((uint32_t)91 << CX_PC_SHIFT)));
+      fast = fast & !over & !hook & (inning <= (uint32_t)MLBSIM_REPLAY_MAX_INNINGS);
+      if (fast) {
+        pos = npos;
+        sc = nsc;
+        if (runs) {
+          mlbsim_replay_game* const R = args.out + game;
+          (side ? R->home_runs : R->away_runs)[inning - 1] = (uint8_t)(runs > 255u ? 255u : runs);
+        }
+        hs = HS_NEW_HALF;
+        ++hidx;
+        { const uint32_t t = cur; cur = oth; oth = t; }
+        { const unsigned long long t = pa_cur; pa_cur = pa_oth; pa_oth = t; }
+      } else {
+        hs |= HS_PARKED;
+      }
+    }
+#endif
     }
 
     if ((hs & HS_OVER) != 0u) {
