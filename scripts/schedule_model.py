@@ -17,6 +17,8 @@ round (2.90 / 3.05 / 3.085 / 3.00 x 10^9 games/s).  It is then used for the sche
   * two games per lane with a switch at any step,
   * the common-case boundary inline in the step, rare cases parked for a round-end pass (native and replay).
 A model is not a measurement: the numbers below are the reason these variants were not given GPU time, nothing more.
+(The replay kernel's inline boundary WAS built afterwards — REPLAY_INLINE_BOUNDARY, profiles/r02_rp18.log: the block came out at
+~96 instructions per step and measured +0.9 / +1.0 % at 3 / 4 steps per round, where the "+80" rows below say +1 %.)
 """
 import numpy as np
 
